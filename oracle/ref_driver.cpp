@@ -84,6 +84,15 @@ int main(int argc, char **argv) {
     const double t0 = now_s();
     platform->reset_kv_position(model_id);
     platform->ggml_backends[model_id]->setup_threadpool();
+    // Work around a latent heap overflow in the reference: GGMLBackend::setup_work_data (src/backend/ggml/ggml.cpp:
+    // 98-109) adds the per-thread cache-line padding only when it grows the buffer, and returns early when the new
+    // request fits the PADDED size — so as n_kv grows by one per decode step, softmax's per-thread scratch
+    // (ggml.c:14891, offset (nc+16)*ith) runs up to 64*n_threads bytes past the allocation (ASan: heap-buffer-
+    // overflow in ggml_vec_cpy_f32 <- ggml_compute_forward_soft_max_f32; "double free or corruption" without ASan).
+    // Pre-sizing the scratch once through the backend's own public method avoids it without touching arithmetic.
+    platform->ggml_backends[model_id]->setup_work_data(
+        size_t(64) << 20 | (size_t(batch_size) * cfg->llm.hidden_dim * 2 + size_t(cfg->llm.seq_len + 64) * 4 * (n_threads + 1))
+    );
     size_t n_prefilled = 0;
     while (n_prefilled + 1 < prompt.size()) {
         size_t bs = std::min(batch_size, prompt.size() - n_prefilled - 1);
