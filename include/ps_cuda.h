@@ -1,0 +1,148 @@
+/* include/ps_cuda.h — C ABI of the B200-native CUDA backend for PowerServe's decode / prefill hot path.
+ *
+ * This is the drop-in boundary: one shared library (libps_cuda.so), plain pointers and sizes only, no C++ or torch
+ * types.  A PowerServe maintainer binds it from a `CUDABackend` class that mirrors `powerserve::ggml::GGMLBackend`
+ * (/root/reference/src/backend/ggml/ggml.hpp:186-250) — see INTEGRATION.md for the stub — exactly the way the QNN
+ * backend is bound today (src/backend/platform.hpp:31-33, src/executor/executor.cpp:142-165).
+ *
+ * Conventions
+ *   - ggml dimension order everywhere: ne0 is the contiguous dim; a weight W is {K, N} = N rows of K quantised
+ *     elements; activations are {dim, bs} fp32 (src/core/tensor.hpp:27-31, src/graph/graph.cpp:64-76).
+ *   - every call enqueues on the context's stream and returns an int status: 0 = ok, otherwise an error whose text
+ *     `ps_cuda_last_error` returns.  The C++ side converts non-zero into POWERSERVE_ABORT to keep the reference's
+ *     error convention (src/core/logger.hpp:56-82).
+ *   - results are BIT-IDENTICAL to the reference's x86 AVX2+FMA build (see DESIGN.md "Numerics contract").
+ *   - there is NO CPU fallback: without a CUDA device every entry point fails (PS_CUDA_ERR_NO_DEVICE).
+ */
+#ifndef PS_CUDA_H
+#define PS_CUDA_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PS_CUDA_ABI_VERSION 1
+
+/* ggml type ids as stored in GGUF (libs/ggml/include/ggml.h:386-401) */
+enum ps_cuda_type { PS_TYPE_F32 = 0, PS_TYPE_Q4_0 = 2, PS_TYPE_Q8_0 = 8, PS_TYPE_Q4_K = 12, PS_TYPE_Q6_K = 14 };
+
+enum ps_cuda_status {
+    PS_CUDA_OK = 0,
+    PS_CUDA_ERR_NO_DEVICE = 1,
+    PS_CUDA_ERR_CUDA = 2,
+    PS_CUDA_ERR_INVALID = 3,
+    PS_CUDA_ERR_UNSUPPORTED = 4,
+    PS_CUDA_ERR_OOM = 5,
+    PS_CUDA_ERR_KV_FULL = 6
+};
+
+typedef struct ps_cuda_ctx ps_cuda_ctx;
+
+/* Mirrors ModelConfig::LLMConfig + RopeConfig (src/core/config.hpp:86-109) — the fields the hot path reads. */
+typedef struct {
+    int32_t dim, ffn_dim, n_layers, n_heads, n_kv_heads, head_size, vocab_size;
+    int32_t n_ctx;          /* KV slots to allocate (cap of model.json's n_ctx) */
+    float   norm_eps;
+    int32_t rope_n_dims;    /* == head_size (asserted by NormAttention::build, norm_attention.cpp:38) */
+    int32_t rope_type;      /* mode & 2 -> NEOX pairs, else adjacent pairs (ggml.c:15440) */
+    float   rope_freq_base, rope_freq_scale, rope_attn_factor;
+    int32_t qkv_bias;       /* Qwen2 (src/model/qwen2/qwen2_model.cpp:89) */
+    int32_t max_batch;      /* largest bs a forward() will see (prefill chunk / verify width); workspace is sized once */
+    int32_t tp_rank, tp_size; /* tensor-parallel position of this context (1 = single GPU) */
+} ps_cuda_model_desc;
+
+typedef struct { const void *host; int32_t type; int32_t _pad; } ps_cuda_tensor; /* host pointer into GGUF memory */
+
+/* Same names as LayerWeights / Weight (src/model/common/weights.hpp:24-74). */
+typedef struct {
+    ps_cuda_tensor attn_norm, ffn_norm, attn_q, attn_k, attn_v, attn_output, ffn_gate, ffn_up, ffn_down;
+    ps_cuda_tensor attn_q_bias, attn_k_bias, attn_v_bias;
+} ps_cuda_layer_weights;
+
+typedef struct {
+    ps_cuda_tensor token_embd, output_norm, output; /* output.host == token_embd.host when tied (weights.hpp:67) */
+    const ps_cuda_layer_weights *layers;            /* n_layers entries */
+} ps_cuda_model_weights;
+
+/* ---------------------------------------------------------------------------------------------- lifecycle
+ * replaces Platform::init_ggml_backend / destroy_ggml_backend (src/backend/platform.cpp:19-25) */
+int  ps_cuda_abi_version(void);
+int  ps_cuda_device_count(void);
+int  ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc);
+void ps_cuda_destroy(ps_cuda_ctx *ctx);
+const char *ps_cuda_last_error(const ps_cuda_ctx *ctx); /* ctx may be NULL: error of a failed create */
+int  ps_cuda_sync(ps_cuda_ctx *ctx);
+void *ps_cuda_stream(ps_cuda_ctx *ctx);                 /* the cudaStream_t every call enqueues on */
+
+/* ---------------------------------------------------------------------------------------------- memory
+ * CUDABuffer backing for graph intermediates (replaces CPUBuffer::create_buffer, src/backend/cpu_buffer.hpp:41-51)
+ * and the weight registry: graph leaves arrive as CPUBuffer views of GGUF memory (weights.hpp:45-52), so weights are
+ * uploaded once and looked up by host pointer. */
+int   ps_cuda_malloc(ps_cuda_ctx *ctx, size_t bytes, void **dev);
+int   ps_cuda_free(ps_cuda_ctx *ctx, void *dev);
+int   ps_cuda_memcpy_h2d(ps_cuda_ctx *ctx, void *dev, const void *host, size_t bytes);
+int   ps_cuda_memcpy_d2h(ps_cuda_ctx *ctx, void *host, const void *dev, size_t bytes);  /* synchronises */
+int   ps_cuda_register_weight(ps_cuda_ctx *ctx, const void *host, int type, int64_t ne0, int64_t ne1, void **dev);
+void *ps_cuda_lookup_weight(ps_cuda_ctx *ctx, const void *host);
+
+/* ---------------------------------------------------------------------------------------------- operator table
+ * One entry per GGMLBackend method on the hot path (ggml.hpp:216-244); all pointers are DEVICE pointers except
+ * `tokens` / `pos`, which are host arrays like the reference's std::vector<int> arguments. */
+int ps_cuda_get_embedding(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype, int64_t dim, const int32_t *tokens, int64_t bs);
+int ps_cuda_rmsnorm(ps_cuda_ctx *ctx, float *dst, const float *x, const float *w, int64_t dim, int64_t bs, float eps);
+int ps_cuda_matmul(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype, int64_t K, int64_t N, const float *x, int64_t bs);
+int ps_cuda_rope(ps_cuda_ctx *ctx, float *dst, const float *src, int64_t head_size, int64_t n_heads, int64_t bs, const int32_t *pos);
+int ps_cuda_add(ps_cuda_ctx *ctx, float *dst, const float *a, const float *b, int64_t n, int64_t nb); /* b row-broadcast */
+int ps_cuda_silu_hadamard(ps_cuda_ctx *ctx, float *dst, const float *gate, const float *up, int64_t n);
+int ps_cuda_get_mask(ps_cuda_ctx *ctx, float *mask, int64_t n_kv, int64_t bs, const int32_t *pos);
+int ps_cuda_softmax_ext(ps_cuda_ctx *ctx, float *dst, const float *x, const float *mask, int64_t ne0, int64_t ne1, int64_t ne2, float scale);
+/* the two fp32 attention matmuls over the reference's cache layout: K {kv_dim, n_kv} rows, V transposed
+ * {n_ctx, kv_dim} (norm_attention.cpp:82-147); q is the rope output {head_size, n_heads, bs}. */
+int ps_cuda_attn_scores(ps_cuda_ctx *ctx, float *kq, const float *k_cache, const float *q, int64_t head_size, int64_t n_heads,
+                        int64_t n_kv_heads, int64_t n_kv, int64_t bs);
+int ps_cuda_attn_pv(ps_cuda_ctx *ctx, float *out, const float *v_cache_t, const float *p, int64_t head_size, int64_t n_heads,
+                    int64_t n_kv_heads, int64_t n_kv, int64_t n_ctx, int64_t bs);
+/* strided fp32 copy (GGMLBackend::copy / cont -> powerserve_compute_forward_dup): 2-D, byte strides */
+int ps_cuda_copy_2d(ps_cuda_ctx *ctx, void *dst, int64_t dst_stride0, int64_t dst_stride1, const void *src,
+                    int64_t src_stride0, int64_t src_stride1, int64_t ne0, int64_t ne1);
+
+/* ---------------------------------------------------------------------------------------------- KV cache
+ * Device implementation of the position bookkeeping of KVCacheInterface (src/core/kv_cache.hpp:97-163) that
+ * Platform::get/reset_kv_position (src/backend/platform.cpp:34-50) and LlamaModel::forward (:84-86,109) use. */
+int     ps_cuda_kv_position(ps_cuda_ctx *ctx);
+int     ps_cuda_kv_reset(ps_cuda_ctx *ctx);                    /* truncate_tokens(0) */
+int     ps_cuda_kv_truncate(ps_cuda_ctx *ctx, int n_tokens);   /* truncate_tokens(n) */
+int     ps_cuda_kv_rollback(ps_cuda_ctx *ctx, int n_tokens);   /* rollback_tokens(n) */
+int     ps_cuda_kv_advance(ps_cuda_ctx *ctx, int n_tokens);    /* advance_tokens(n) */
+float  *ps_cuda_kv_k(ps_cuda_ctx *ctx, int layer);             /* device ptr, [n_ctx][kv_dim] */
+float  *ps_cuda_kv_v(ps_cuda_ctx *ctx, int layer);             /* device ptr, [kv_dim][n_ctx] (transposed) */
+
+/* ---------------------------------------------------------------------------------------------- whole-model path
+ * The QNN precedent (`g.qnn_forward`, llama_model.cpp:66-77): one graph op that runs the whole forward pass inside
+ * the backend.  bind uploads every weight; forward == LlamaModel::forward / Qwen2Model::forward (llama_model.cpp:
+ * 52-117): tokens/pos are HOST arrays, logits_host (may be NULL when lm_head == 0) receives [bs][vocab] fp32 and the
+ * call returns after the copy has landed; the KV position advances by bs. */
+int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w);
+int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, int lm_head, float *logits_host);
+/* Model::decode with top_k = 1 (llama_model.cpp:119-132): forward + arg-max on the device; only the token id comes
+ * back.  `n_steps` > 1 keeps feeding the produced id back in without a host round trip (ids_host gets n_steps ids). */
+int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, int32_t *ids_host);
+/* device-side logits of the last forward ([bs][vocab]) for callers that sample on the GPU */
+const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
+
+/* execution switches (0/1): "graph" = replay the decode step as a captured CUDA graph, "fused" = fused decode
+ * kernels instead of one kernel per table op.  Both produce bit-identical results; they exist so tests can prove it. */
+int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
+/* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes" */
+int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name);
+
+/* host-side restatement of glibc expf used by the device code; exported so CPU-only tests can pin it against libm */
+float ps_cuda_host_expf_ref(float x);
+float ps_cuda_host_v_expf(float x);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PS_CUDA_H */

@@ -1,0 +1,50 @@
+"""Build libps_cuda.so (hand-written sm_100a kernels + the C ABI) in-tree with nvcc.  No torch involved.
+
+    python -m powerserve_b200.build [--force]
+
+nvcc cross-compiles for sm_100a without a GPU; the resulting .so sits next to this file (git-ignored, but it
+travels to the GPU box with gpurun).
+"""
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIB = os.path.join(HERE, "libps_cuda.so")
+SOURCES = ["ps_cuda.cu"]
+HEADERS = ["ps_kernels.cuh", "ps_math.cuh", os.path.join("..", "..", "include", "ps_cuda.h")]
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+    "--fmad=false",            # never contract a*b+c: FMAs appear only where the reference has them (ps_math.cuh)
+    "-prec-div=true", "-prec-sqrt=true", "-ftz=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off,-O2", "-shared", "-cudart", "shared",
+]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB):
+        return True
+    t = os.path.getmtime(LIB)
+    deps = [os.path.join(CSRC, f) for f in SOURCES + HEADERS] + [os.path.abspath(__file__)]
+    return any(os.path.getmtime(os.path.normpath(d)) > t for d in deps if os.path.exists(os.path.normpath(d)))
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+    if not force and not needs_build():
+        return LIB
+    nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)
+    if verbose:
+        print(r.stdout + r.stderr)
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,321 @@
+"""ctypes binding of libps_cuda.so (include/ps_cuda.h) — the same entry points a PowerServe `CUDABackend` C++ class
+binds.  Python is only the test / bench harness here: every call below crosses the C ABI, nothing
+is computed in Python, and there is NO fallback — a missing library or device raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import json
+import os
+from typing import Dict, List, Optional, Sequence
+
+import numpy as np
+
+from . import gguf
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libps_cuda.so")
+
+F32, Q4_0, Q8_0, Q4_K, Q6_K = 0, 2, 8, 12, 14
+
+
+class PsCudaError(RuntimeError):
+    pass
+
+
+class ModelDesc(C.Structure):
+    _fields_ = [(n, C.c_int32) for n in ("dim", "ffn_dim", "n_layers", "n_heads", "n_kv_heads", "head_size", "vocab_size", "n_ctx")] + [
+        ("norm_eps", C.c_float), ("rope_n_dims", C.c_int32), ("rope_type", C.c_int32), ("rope_freq_base", C.c_float),
+        ("rope_freq_scale", C.c_float), ("rope_attn_factor", C.c_float), ("qkv_bias", C.c_int32), ("max_batch", C.c_int32),
+        ("tp_rank", C.c_int32), ("tp_size", C.c_int32)]
+
+
+class Tensor(C.Structure):
+    _fields_ = [("host", C.c_void_p), ("type", C.c_int32), ("_pad", C.c_int32)]
+
+
+class LayerWeights(C.Structure):
+    _fields_ = [(n, Tensor) for n in ("attn_norm", "ffn_norm", "attn_q", "attn_k", "attn_v", "attn_output", "ffn_gate", "ffn_up",
+                                      "ffn_down", "attn_q_bias", "attn_k_bias", "attn_v_bias")]
+
+
+class ModelWeights(C.Structure):
+    _fields_ = [("token_embd", Tensor), ("output_norm", Tensor), ("output", Tensor), ("layers", C.POINTER(LayerWeights))]
+
+
+_lib: Optional[C.CDLL] = None
+
+
+def load_library() -> C.CDLL:
+    """Load libps_cuda.so; raises if it has not been built (python -m powerserve_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PsCudaError(f"{LIB_PATH} is missing — build it with `python -m powerserve_b200.build`; there is no CPU fallback")
+    L = C.CDLL(LIB_PATH)
+    vp, i32p, fp, i64, ci, sz = C.c_void_p, C.POINTER(C.c_int32), C.c_void_p, C.c_int64, C.c_int, C.c_size_t
+    sig = {
+        "ps_cuda_abi_version": (ci, []),
+        "ps_cuda_device_count": (ci, []),
+        "ps_cuda_create": (ci, [C.POINTER(vp), ci, C.POINTER(ModelDesc)]),
+        "ps_cuda_destroy": (None, [vp]),
+        "ps_cuda_last_error": (C.c_char_p, [vp]),
+        "ps_cuda_sync": (ci, [vp]),
+        "ps_cuda_stream": (vp, [vp]),
+        "ps_cuda_malloc": (ci, [vp, sz, C.POINTER(vp)]),
+        "ps_cuda_free": (ci, [vp, vp]),
+        "ps_cuda_memcpy_h2d": (ci, [vp, vp, vp, sz]),
+        "ps_cuda_memcpy_d2h": (ci, [vp, vp, vp, sz]),
+        "ps_cuda_register_weight": (ci, [vp, vp, ci, i64, i64, C.POINTER(vp)]),
+        "ps_cuda_lookup_weight": (vp, [vp, vp]),
+        "ps_cuda_get_embedding": (ci, [vp, fp, vp, ci, i64, i32p, i64]),
+        "ps_cuda_rmsnorm": (ci, [vp, fp, fp, fp, i64, i64, C.c_float]),
+        "ps_cuda_matmul": (ci, [vp, fp, vp, ci, i64, i64, fp, i64]),
+        "ps_cuda_rope": (ci, [vp, fp, fp, i64, i64, i64, i32p]),
+        "ps_cuda_add": (ci, [vp, fp, fp, fp, i64, i64]),
+        "ps_cuda_silu_hadamard": (ci, [vp, fp, fp, fp, i64]),
+        "ps_cuda_get_mask": (ci, [vp, fp, i64, i64, i32p]),
+        "ps_cuda_softmax_ext": (ci, [vp, fp, fp, fp, i64, i64, i64, C.c_float]),
+        "ps_cuda_attn_scores": (ci, [vp, fp, fp, fp, i64, i64, i64, i64, i64]),
+        "ps_cuda_attn_pv": (ci, [vp, fp, fp, fp, i64, i64, i64, i64, i64, i64]),
+        "ps_cuda_copy_2d": (ci, [vp, vp, i64, i64, vp, i64, i64, i64, i64]),
+        "ps_cuda_kv_position": (ci, [vp]),
+        "ps_cuda_kv_reset": (ci, [vp]),
+        "ps_cuda_kv_truncate": (ci, [vp, ci]),
+        "ps_cuda_kv_rollback": (ci, [vp, ci]),
+        "ps_cuda_kv_advance": (ci, [vp, ci]),
+        "ps_cuda_kv_k": (vp, [vp, ci]),
+        "ps_cuda_kv_v": (vp, [vp, ci]),
+        "ps_cuda_bind_model": (ci, [vp, C.POINTER(ModelWeights)]),
+        "ps_cuda_forward": (ci, [vp, i32p, i32p, ci, ci, C.c_void_p]),
+        "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
+        "ps_cuda_logits_dev": (vp, [vp]),
+        "ps_cuda_set_option": (ci, [vp, C.c_char_p, ci]),
+        "ps_cuda_get_counter": (i64, [vp, C.c_char_p]),
+        "ps_cuda_host_expf_ref": (C.c_float, [C.c_float]),
+        "ps_cuda_host_v_expf": (C.c_float, [C.c_float]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(L, name)   # AttributeError here == the library does not export what include/ps_cuda.h declares
+        fn.restype = res
+        fn.argtypes = args
+    L._ps_signatures = sig
+    _lib = L
+    return L
+
+
+def exported_symbols() -> List[str]:
+    return list(load_library()._ps_signatures.keys())
+
+
+def _i32(a: Sequence[int]) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(a, dtype=np.int32))
+
+
+class DeviceBuffer:
+    """A CUDABuffer: device memory owned by a context (ps_cuda_malloc / ps_cuda_free)."""
+
+    def __init__(self, be: "CudaBackend", nbytes: int):
+        self.be, self.nbytes = be, int(nbytes)
+        p = C.c_void_p()
+        be._ck(be.L.ps_cuda_malloc(be.h, self.nbytes, C.byref(p)))
+        self.ptr = p.value
+
+    @classmethod
+    def from_numpy(cls, be: "CudaBackend", a: np.ndarray) -> "DeviceBuffer":
+        a = np.ascontiguousarray(a)
+        b = cls(be, a.nbytes)
+        be._ck(be.L.ps_cuda_memcpy_h2d(be.h, b.ptr, a.ctypes.data, a.nbytes))
+        return b
+
+    def numpy(self, dtype=np.float32, shape=None) -> np.ndarray:
+        out = np.empty(self.nbytes // np.dtype(dtype).itemsize, dtype=dtype)
+        self.be._ck(self.be.L.ps_cuda_memcpy_d2h(self.be.h, out.ctypes.data, self.ptr, out.nbytes))
+        return out.reshape(shape) if shape is not None else out
+
+    def free(self):
+        if self.ptr:
+            self.be.L.ps_cuda_free(self.be.h, self.ptr)
+            self.ptr = None
+
+
+class CudaBackend:
+    """Mirror of `powerserve::ggml::GGMLBackend`'s operator table (src/backend/ggml/ggml.hpp:216-244) over the C ABI.
+    Method names, argument meaning and error behaviour follow the reference; tensors are DeviceBuffers."""
+
+    def __init__(self, desc: ModelDesc, device: int = 0):
+        self.L = load_library()
+        self.desc = desc
+        h = C.c_void_p()
+        rc = self.L.ps_cuda_create(C.byref(h), device, C.byref(desc))
+        if rc != 0:
+            raise PsCudaError(f"ps_cuda_create failed ({rc}): {self.L.ps_cuda_last_error(None).decode()}")
+        self.h = h
+
+    def _ck(self, rc: int):
+        if rc != 0:
+            raise PsCudaError(f"libps_cuda error {rc}: {self.L.ps_cuda_last_error(self.h).decode()}")
+
+    def close(self):
+        if self.h:
+            self.L.ps_cuda_destroy(self.h)
+            self.h = None
+
+    # ---- memory
+    def empty(self, n_floats: int) -> DeviceBuffer:
+        return DeviceBuffer(self, 4 * int(n_floats))
+
+    def upload(self, a: np.ndarray) -> DeviceBuffer:
+        return DeviceBuffer.from_numpy(self, a)
+
+    def register_weight(self, host: np.ndarray, ggml_type: int, ne0: int, ne1: int) -> int:
+        p = C.c_void_p()
+        self._ck(self.L.ps_cuda_register_weight(self.h, host.ctypes.data, ggml_type, ne0, ne1, C.byref(p)))
+        return p.value
+
+    def sync(self):
+        self._ck(self.L.ps_cuda_sync(self.h))
+
+    def counter(self, name: str) -> int:
+        return int(self.L.ps_cuda_get_counter(self.h, name.encode()))
+
+    def set_option(self, name: str, value: int):
+        self._ck(self.L.ps_cuda_set_option(self.h, name.encode(), int(value)))
+
+    # ---- operator table
+    def get_embedding(self, dst, weight_dev, wtype, dim, tokens):
+        t = _i32(tokens)
+        self._ck(self.L.ps_cuda_get_embedding(self.h, dst.ptr, weight_dev, wtype, dim, t.ctypes.data_as(C.POINTER(C.c_int32)), len(t)))
+
+    def rmsnorm(self, out, x, weight, dim, bs, eps):
+        self._ck(self.L.ps_cuda_rmsnorm(self.h, out.ptr, x.ptr, weight.ptr, dim, bs, eps))
+
+    def matmul(self, dst, weight_dev, wtype, K, N, x, bs):
+        self._ck(self.L.ps_cuda_matmul(self.h, dst.ptr, weight_dev, wtype, K, N, x.ptr, bs))
+
+    def rope(self, out, src, head_size, n_heads, bs, pos):
+        p = _i32(pos)
+        self._ck(self.L.ps_cuda_rope(self.h, out.ptr, src.ptr, head_size, n_heads, bs, p.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def add(self, dst, a, b, n, nb):
+        self._ck(self.L.ps_cuda_add(self.h, dst.ptr, a.ptr, b.ptr, n, nb))
+
+    def silu_hadamard(self, out, hb, hb2, n):
+        self._ck(self.L.ps_cuda_silu_hadamard(self.h, out.ptr, hb.ptr, hb2.ptr, n))
+
+    def get_mask(self, mask, n_kv, bs, pos):
+        p = _i32(pos)
+        self._ck(self.L.ps_cuda_get_mask(self.h, mask.ptr, n_kv, bs, p.ctypes.data_as(C.POINTER(C.c_int32))))
+
+    def softmax_ext(self, out, x, mask, ne0, ne1, ne2, scale):
+        self._ck(self.L.ps_cuda_softmax_ext(self.h, out.ptr, x.ptr, mask.ptr, ne0, ne1, ne2, scale))
+
+    def attn_scores(self, kq, k_cache, q, hs, n_heads, n_kv_heads, n_kv, bs):
+        self._ck(self.L.ps_cuda_attn_scores(self.h, kq.ptr, k_cache.ptr, q.ptr, hs, n_heads, n_kv_heads, n_kv, bs))
+
+    def attn_pv(self, out, v_cache_t, p, hs, n_heads, n_kv_heads, n_kv, n_ctx, bs):
+        self._ck(self.L.ps_cuda_attn_pv(self.h, out.ptr, v_cache_t.ptr, p.ptr, hs, n_heads, n_kv_heads, n_kv, n_ctx, bs))
+
+    # ---- kv
+    @property
+    def kv_position(self) -> int:
+        return self.L.ps_cuda_kv_position(self.h)
+
+    def reset_kv(self):
+        self._ck(self.L.ps_cuda_kv_reset(self.h))
+
+    def kv_rollback(self, n: int):
+        self._ck(self.L.ps_cuda_kv_rollback(self.h, n))
+
+    def kv_truncate(self, n: int):
+        self._ck(self.L.ps_cuda_kv_truncate(self.h, n))
+
+
+def desc_from_model_json(cfg: dict, max_batch: int = 128, n_ctx: Optional[int] = None, qkv_bias: bool = False) -> ModelDesc:
+    llm, rope = cfg["llm_config"], cfg["llm_config"]["rope_config"]
+    return ModelDesc(llm["embed_dim"], llm["ffn_dim"], llm["n_layers"], llm["n_attn_heads"], llm["n_attn_kv_heads"], llm["head_size"],
+                     llm["vocab_size"], n_ctx or llm["n_ctx"], llm["norm_eps"], rope["rope_dim"], rope["rope_type"],
+                     rope["rope_freq_base"], rope["rope_freq_scale"], rope["rope_attn_factor"], int(qkv_bias), max_batch, 0, 1)
+
+
+class CudaModel:
+    """A PowerServe model directory (model.json + ggml/weights.gguf) bound to the CUDA backend.
+    forward / decode follow LlamaModel::forward / decode (src/model/llama/llama_model.cpp:52-132)."""
+
+    def __init__(self, path: Optional[str] = None, *, desc: Optional[ModelDesc] = None,
+                 tensors: Optional[Dict[str, gguf.GGUFTensor]] = None, max_batch: int = 128, device: int = 0):
+        if path is not None:
+            cfg = json.load(open(os.path.join(path, "model.json")))
+            self._gguf = gguf.GGUFFile(os.path.join(path, "ggml", "weights.gguf"))
+            tensors = self._gguf.tensors
+            desc = desc_from_model_json(cfg, max_batch=max_batch, qkv_bias="blk.0.attn_q.bias" in tensors)
+        assert desc is not None and tensors is not None
+        self.desc, self.tensors = desc, tensors
+        self.vocab = desc.vocab_size
+        self.be = CudaBackend(desc, device)
+        L = self.be.L
+
+        def T(name: Optional[str]) -> Tensor:
+            if name is None:
+                return Tensor(None, 0, 0)
+            t = tensors[name]
+            return Tensor(t.host_ptr, t.ggml_type, 0)
+
+        bias = bool(desc.qkv_bias)
+        self._layers = (LayerWeights * desc.n_layers)()
+        for i in range(desc.n_layers):
+            p = f"blk.{i}."
+            self._layers[i] = LayerWeights(T(p + "attn_norm.weight"), T(p + "ffn_norm.weight"), T(p + "attn_q.weight"),
+                                           T(p + "attn_k.weight"), T(p + "attn_v.weight"), T(p + "attn_output.weight"),
+                                           T(p + "ffn_gate.weight"), T(p + "ffn_up.weight"), T(p + "ffn_down.weight"),
+                                           T(p + "attn_q.bias" if bias else None), T(p + "attn_k.bias" if bias else None),
+                                           T(p + "attn_v.bias" if bias else None))
+        out = "output.weight" if "output.weight" in tensors else "token_embd.weight"  # weights.hpp:67
+        self._w = ModelWeights(T("token_embd.weight"), T("output_norm.weight"), T(out), self._layers)
+        self.be._ck(L.ps_cuda_bind_model(self.be.h, C.byref(self._w)))
+
+    @property
+    def position(self) -> int:
+        return self.be.kv_position
+
+    def reset(self):
+        self.be.reset_kv()
+
+    def forward(self, tokens, pos=None, lm_head: bool = True) -> Optional[np.ndarray]:
+        t = _i32(tokens)
+        bs = len(t)
+        p = _i32(pos) if pos is not None else np.arange(self.position, self.position + bs, dtype=np.int32)
+        logits = np.empty((bs, self.vocab), np.float32) if lm_head else None
+        self.be._ck(self.be.L.ps_cuda_forward(self.be.h, t.ctypes.data_as(C.POINTER(C.c_int32)), p.ctypes.data_as(C.POINTER(C.c_int32)),
+                                              bs, int(lm_head), logits.ctypes.data if lm_head else None))
+        return logits
+
+    def decode_greedy(self, first_token: int, n_steps: int) -> np.ndarray:
+        ids = np.zeros(n_steps, np.int32)
+        self.be._ck(self.be.L.ps_cuda_decode_greedy(self.be.h, int(first_token), n_steps, ids.ctypes.data_as(C.POINTER(C.c_int32))))
+        return ids
+
+    def prefill(self, prompt, batch_size: int = 128):
+        """ModelTokenIterator's prefill loop (src/model/model.hpp:147-160): prompt[:-1] in chunks, lm_head = false."""
+        prompt = list(map(int, prompt))
+        i = 0
+        while i < len(prompt) - 1:
+            bs = min(batch_size, len(prompt) - 1 - i)
+            self.forward(prompt[i:i + bs], lm_head=False)
+            i += bs
+
+    def generate(self, prompt, n_decode: int, batch_size: int = 128, forced=None):
+        self.reset()
+        self.prefill(prompt, batch_size)
+        ids, logits, tok = [], [], int(prompt[-1])
+        for step in range(n_decode):
+            lg = self.forward([tok])[0]
+            best = int(np.argmax(lg))
+            ids.append(best)
+            logits.append(lg)
+            tok = int(forced[step]) if forced is not None and step < len(forced) else best
+        return ids, np.stack(logits)
+
+    def close(self):
+        self.be.close()

@@ -1,0 +1,680 @@
+// ps_cuda.cu — host side of libps_cuda.so: context, weight registry, workspace, KV cache, the operator table and the
+// whole-model forward behind the C ABI declared in include/ps_cuda.h.  No torch, no CPU fallback.
+#include "../../include/ps_cuda.h"
+#include "ps_kernels.cuh"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <mutex>
+#include <string>
+#include <unordered_map>
+#include <vector>
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevWeight {
+    void *dev = nullptr;
+    int type = 0;
+    int64_t ne0 = 0, ne1 = 0;
+};
+
+struct LayerDev {
+    const float *attn_norm, *ffn_norm, *q_bias, *k_bias, *v_bias;
+    const uint8_t *wq, *wk, *wv, *wo, *wgate, *wup, *wdown;
+    int tq, tk, tv, to, tgate, tup, tdown;
+};
+
+} // namespace
+
+struct ps_cuda_ctx {
+    int device = 0;
+    cudaStream_t stream = nullptr;
+    ps_cuda_model_desc d{};
+    std::string err;
+    std::mutex mu; // one in-flight generation per context (SURVEY 8b "Threading")
+    std::unordered_map<const void *, DevWeight> weights;
+    std::vector<void *> owned; // every cudaMalloc we must free
+    // model binding
+    bool bound = false;
+    const uint8_t *w_embd = nullptr, *w_out = nullptr;
+    int t_embd = 0, t_out = 0;
+    const float *w_out_norm = nullptr;
+    std::vector<LayerDev> layers;
+    // kv cache
+    std::vector<float *> kc, vct;
+    int position = 0;
+    // rope table
+    float *rope_table = nullptr;
+    // workspace
+    int64_t maxK = 0;
+    float *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *qr = nullptr, *kr = nullptr, *att = nullptr;
+    float *g = nullptr, *u = nullptr, *kq = nullptr, *logits = nullptr;
+    uint32_t *aqs = nullptr, *absp = nullptr;
+    float *ad = nullptr;
+    int32_t *tokens_dev = nullptr, *pos_dev = nullptr, *ids_dev = nullptr;
+    int32_t *h_tokens = nullptr, *h_pos = nullptr, *h_ids = nullptr; // pinned staging
+    float *h_logits = nullptr;                                          // pinned staging for logits
+    size_t h_logits_cap = 0;
+    // options / counters
+    int opt_graph = 0, opt_fused = 0;
+    int64_t n_launch = 0, n_graph = 0, h2d = 0, d2h = 0;
+};
+
+namespace {
+
+int fail(ps_cuda_ctx *c, int code, const char *fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    if (c) c->err = buf;
+    else g_create_error = buf;
+    return code;
+}
+
+#define PS_CK(call)                                                                                          \
+    do {                                                                                                     \
+        cudaError_t e_ = (call);                                                                             \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, PS_CUDA_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+#define PS_LAUNCH_CK()                                                                                       \
+    do {                                                                                                     \
+        ctx->n_launch++;                                                                                     \
+        cudaError_t e_ = cudaGetLastError();                                                                 \
+        if (e_ != cudaSuccess)                                                                               \
+            return fail(ctx, PS_CUDA_ERR_CUDA, "kernel launch failed: %s (%s:%d)", cudaGetErrorString(e_), __FILE__, __LINE__); \
+    } while (0)
+
+int dev_alloc(ps_cuda_ctx *ctx, void **p, size_t bytes) {
+    if (bytes == 0) bytes = 16;
+    cudaError_t e = cudaMalloc(p, bytes);
+    if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+    ctx->owned.push_back(*p);
+    return 0;
+}
+
+bool type_ok(int t) { return t == 0 || t == 2 || t == 8 || t == 12 || t == 14; }
+int blk_elems(int t) { return (t == 12 || t == 14) ? 256 : (t == 0 ? 1 : 32); }
+
+// ggml_rope_cache_init (libs/ggml/src/ggml.c:15342-15356) + rope_yarn (:15319-15336) at ext_factor == 0,
+// freq_factors == NULL (src/backend/ggml/ggml_wrapper.cpp:104-106), evaluated with the platform libm for
+// every position once.
+void build_rope_table(const ps_cuda_model_desc &d, std::vector<float> &t) {
+    const int hs = d.head_size;
+    t.resize((size_t)d.n_ctx * hs);
+    const float theta_scale = powf(d.rope_freq_base, -2.0f / d.rope_n_dims);
+    for (int p = 0; p < d.n_ctx; p++) {
+        volatile float theta = (float)(int64_t)p;
+        float *cache = t.data() + (size_t)p * hs;
+        for (int i0 = 0; i0 < hs; i0 += 2) {
+            volatile float th = d.rope_freq_scale * theta;
+            volatile float c = cosf(th) * d.rope_attn_factor;
+            volatile float s = sinf(th) * d.rope_attn_factor;
+            s = s * 1.0f;
+            cache[i0] = c;
+            cache[i0 + 1] = s;
+            theta = theta * theta_scale;
+        }
+    }
+}
+
+template <int TYPE, int C> size_t mm_smem(int64_t K) {
+    const int64_t nb = K / PsBlk<TYPE>::ELEMS;
+    return (size_t)C * (size_t)(K + nb * 4 + (PsBlk<TYPE>::ELEMS == 256 ? nb * 16 : 0));
+}
+
+template <int TYPE, int C>
+int launch_mm(ps_cuda_ctx *ctx, float *dst, const uint8_t *w, int64_t K, int64_t N, int64_t bs, const float *bias, const float *residual) {
+    static bool attr_set[64] = {};
+    const size_t smem = mm_smem<TYPE, C>(K);
+    if (smem > 48 * 1024 && !attr_set[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_matmul_q<TYPE, C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr_set[ctx->device] = true;
+    }
+    dim3 grid((unsigned)((N + 7) / 8), (unsigned)((bs + C - 1) / C));
+    ps_k_matmul_q<TYPE, C><<<grid, 256, smem, ctx->stream>>>(w, K, N, bs, ctx->aqs, ctx->ad, ctx->absp, dst, bias, residual);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+template <int TYPE>
+int launch_mm_t(ps_cuda_ctx *ctx, float *dst, const uint8_t *w, int64_t K, int64_t N, int64_t bs, const float *bias, const float *residual) {
+    if (bs == 1) return launch_mm<TYPE, 1>(ctx, dst, w, K, N, bs, bias, residual);
+    if (bs == 2) return launch_mm<TYPE, 2>(ctx, dst, w, K, N, bs, bias, residual);
+    if (bs <= 4) return launch_mm<TYPE, 4>(ctx, dst, w, K, N, bs, bias, residual);
+    return launch_mm<TYPE, 8>(ctx, dst, w, K, N, bs, bias, residual);
+}
+
+// quantise bs activation columns of K elements into the context's scratch (type of the WEIGHT decides the format)
+int quantize_act(ps_cuda_ctx *ctx, int wtype, const float *x, int64_t K, int64_t bs) {
+    if (K > ctx->maxK || bs > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "activation %lldx%lld exceeds workspace", (long long)K, (long long)bs);
+    if (wtype == 12 || wtype == 14) {
+        if (K % 256) return fail(ctx, PS_CUDA_ERR_INVALID, "K=%lld is not a multiple of 256", (long long)K);
+        dim3 grid((unsigned)((K / 256 + 3) / 4), (unsigned)bs);
+        ps_k_quantize_q8k<<<grid, 128, 0, ctx->stream>>>(x, K, ctx->aqs, ctx->ad, ctx->absp);
+    } else {
+        if (K % 32) return fail(ctx, PS_CUDA_ERR_INVALID, "K=%lld is not a multiple of 32", (long long)K);
+        dim3 grid((unsigned)((K / 32 + 15) / 16), (unsigned)bs);
+        ps_k_quantize_q80<<<grid, 128, 0, ctx->stream>>>(x, K, ctx->aqs, ctx->ad);
+    }
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+// matmul on already-quantised activations (the reference re-quantises the same input for q, k, v and for gate, up;
+// the bytes are identical, so once is enough)
+int matmul_q(ps_cuda_ctx *ctx, float *dst, const uint8_t *w, int wtype, int64_t K, int64_t N, int64_t bs, const float *bias, const float *residual) {
+    switch (wtype) {
+    case 12: return launch_mm_t<12>(ctx, dst, w, K, N, bs, bias, residual);
+    case 14: return launch_mm_t<14>(ctx, dst, w, K, N, bs, bias, residual);
+    case 2: return launch_mm_t<2>(ctx, dst, w, K, N, bs, bias, residual);
+    case 8: return launch_mm_t<8>(ctx, dst, w, K, N, bs, bias, residual);
+    default: return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "matmul: unsupported weight type %d", wtype);
+    }
+}
+
+int grid1d(int64_t n, int block = 256) { return (int)std::min<int64_t>((n + block - 1) / block, 148 * 8); }
+
+} // namespace
+
+// ====================================================================================================================
+extern "C" {
+
+int ps_cuda_abi_version(void) { return PS_CUDA_ABI_VERSION; }
+
+int ps_cuda_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+const char *ps_cuda_last_error(const ps_cuda_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc) {
+    ps_cuda_ctx *ctx = nullptr;
+    if (!out || !desc) return fail(nullptr, PS_CUDA_ERR_INVALID, "null argument");
+    *out = nullptr;
+    const int ndev = ps_cuda_device_count();
+    if (ndev == 0) return fail(nullptr, PS_CUDA_ERR_NO_DEVICE, "no CUDA device: the PowerServe CUDA backend has no CPU fallback");
+    if (device < 0 || device >= ndev) return fail(nullptr, PS_CUDA_ERR_INVALID, "device %d out of range [0,%d)", device, ndev);
+    const ps_cuda_model_desc &d = *desc;
+    if (d.dim <= 0 || d.n_layers <= 0 || d.n_heads <= 0 || d.n_kv_heads <= 0 || d.head_size <= 0 || d.n_ctx <= 0 || d.vocab_size <= 0 ||
+        d.ffn_dim <= 0 || d.max_batch <= 0)
+        return fail(nullptr, PS_CUDA_ERR_INVALID, "model descriptor has non-positive fields");
+    if (d.n_heads % d.n_kv_heads || d.head_size % 32 || d.head_size > 256 || d.rope_n_dims != d.head_size)
+        return fail(nullptr, PS_CUDA_ERR_UNSUPPORTED, "unsupported head geometry (heads %d/%d, head_size %d, rope dims %d)", d.n_heads,
+                    d.n_kv_heads, d.head_size, d.rope_n_dims);
+    ctx = new ps_cuda_ctx();
+    ctx->device = device;
+    ctx->d = d;
+    auto bail = [&](int rc) {
+        g_create_error = ctx->err;
+        ps_cuda_destroy(ctx);
+        return rc;
+    };
+#define PS_CKC(call)                                                                      \
+    do {                                                                                  \
+        cudaError_t e_ = (call);                                                          \
+        if (e_ != cudaSuccess) {                                                          \
+            fail(ctx, PS_CUDA_ERR_CUDA, "%s failed: %s", #call, cudaGetErrorString(e_)); \
+            return bail(PS_CUDA_ERR_CUDA);                                                \
+        }                                                                                 \
+    } while (0)
+#define PS_AL(ptr, bytes)                                         \
+    do {                                                          \
+        int rc_ = dev_alloc(ctx, (void **)&(ptr), (size_t)(bytes)); \
+        if (rc_) return bail(rc_);                                \
+    } while (0)
+    PS_CKC(cudaSetDevice(device));
+    PS_CKC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+    const int64_t B = d.max_batch, dim = d.dim, qdim = (int64_t)d.n_heads * d.head_size, kvd = (int64_t)d.n_kv_heads * d.head_size;
+    ctx->maxK = std::max<int64_t>(std::max<int64_t>(dim, qdim), d.ffn_dim);
+    PS_AL(ctx->x, 4 * dim * B);
+    PS_AL(ctx->xn, 4 * dim * B);
+    PS_AL(ctx->q, 4 * qdim * B);
+    PS_AL(ctx->k, 4 * kvd * B);
+    PS_AL(ctx->v, 4 * kvd * B);
+    PS_AL(ctx->qr, 4 * qdim * B);
+    PS_AL(ctx->kr, 4 * kvd * B);
+    PS_AL(ctx->att, 4 * qdim * B);
+    PS_AL(ctx->g, 4 * (int64_t)d.ffn_dim * B);
+    PS_AL(ctx->u, 4 * (int64_t)d.ffn_dim * B);
+    PS_AL(ctx->kq, 4 * (int64_t)d.n_heads * B * d.n_ctx);
+    PS_AL(ctx->logits, 4 * (int64_t)d.vocab_size * B);
+    PS_AL(ctx->aqs, ctx->maxK * B);
+    PS_AL(ctx->ad, 4 * (ctx->maxK / 32) * B);
+    PS_AL(ctx->absp, 4 * (ctx->maxK / 256 + 1) * 4 * B);
+    PS_AL(ctx->tokens_dev, 4 * B);
+    PS_AL(ctx->pos_dev, 4 * B);
+    PS_AL(ctx->ids_dev, 4 * 4096);
+    ctx->kc.resize(d.n_layers);
+    ctx->vct.resize(d.n_layers);
+    for (int L = 0; L < d.n_layers; L++) {
+        PS_AL(ctx->kc[L], 4 * kvd * d.n_ctx);
+        PS_AL(ctx->vct[L], 4 * kvd * d.n_ctx);
+        PS_CKC(cudaMemsetAsync(ctx->kc[L], 0, 4 * kvd * d.n_ctx, ctx->stream));
+        PS_CKC(cudaMemsetAsync(ctx->vct[L], 0, 4 * kvd * d.n_ctx, ctx->stream));
+    }
+    {
+        std::vector<float> t;
+        build_rope_table(d, t);
+        PS_AL(ctx->rope_table, t.size() * 4);
+        PS_CKC(cudaMemcpy(ctx->rope_table, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    }
+    PS_CKC(cudaMallocHost(&ctx->h_tokens, 4 * B));
+    PS_CKC(cudaMallocHost(&ctx->h_pos, 4 * B));
+    PS_CKC(cudaMallocHost(&ctx->h_ids, 4 * 8192));
+    PS_CKC(cudaStreamSynchronize(ctx->stream));
+#undef PS_CKC
+#undef PS_AL
+    *out = ctx;
+    return 0;
+}
+
+void ps_cuda_destroy(ps_cuda_ctx *ctx) {
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->owned) cudaFree(p);
+    if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
+    if (ctx->h_pos) cudaFreeHost(ctx->h_pos);
+    if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
+    if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+    if (ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+int ps_cuda_sync(ps_cuda_ctx *ctx) {
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    return 0;
+}
+
+void *ps_cuda_stream(ps_cuda_ctx *ctx) { return (void *)ctx->stream; }
+
+// ---------------------------------------------------------------------------------------------- memory
+int ps_cuda_malloc(ps_cuda_ctx *ctx, size_t bytes, void **dev) {
+    PS_CK(cudaSetDevice(ctx->device));
+    return dev_alloc(ctx, dev, bytes);
+}
+
+int ps_cuda_free(ps_cuda_ctx *ctx, void *dev) {
+    for (size_t i = 0; i < ctx->owned.size(); i++)
+        if (ctx->owned[i] == dev) {
+            PS_CK(cudaStreamSynchronize(ctx->stream));
+            PS_CK(cudaFree(dev));
+            ctx->owned.erase(ctx->owned.begin() + i);
+            return 0;
+        }
+    return fail(ctx, PS_CUDA_ERR_INVALID, "ps_cuda_free: pointer not owned by this context");
+}
+
+int ps_cuda_memcpy_h2d(ps_cuda_ctx *ctx, void *dev, const void *host, size_t bytes) {
+    PS_CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaStreamSynchronize(ctx->stream)); // pageable source: make the call safe to return from
+    ctx->h2d += (int64_t)bytes;
+    return 0;
+}
+
+int ps_cuda_memcpy_d2h(ps_cuda_ctx *ctx, void *host, const void *dev, size_t bytes) {
+    PS_CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->d2h += (int64_t)bytes;
+    return 0;
+}
+
+int ps_cuda_register_weight(ps_cuda_ctx *ctx, const void *host, int type, int64_t ne0, int64_t ne1, void **dev) {
+    if (!host || !type_ok(type) || ne0 <= 0 || ne1 <= 0 || ne0 % blk_elems(type))
+        return fail(ctx, PS_CUDA_ERR_INVALID, "register_weight: bad tensor (type %d, %lld x %lld)", type, (long long)ne0, (long long)ne1);
+    auto it = ctx->weights.find(host);
+    if (it != ctx->weights.end()) {
+        if (it->second.type != type || it->second.ne0 != ne0 || it->second.ne1 != ne1)
+            return fail(ctx, PS_CUDA_ERR_INVALID, "register_weight: host pointer already registered with another shape");
+        if (dev) *dev = it->second.dev;
+        return 0;
+    }
+    PS_CK(cudaSetDevice(ctx->device));
+    const size_t bytes = (size_t)ps_row_bytes(type, ne0) * (size_t)ne1;
+    DevWeight w;
+    w.type = type; w.ne0 = ne0; w.ne1 = ne1;
+    int rc = dev_alloc(ctx, &w.dev, bytes + 16);
+    if (rc) return rc;
+    PS_CK(cudaMemcpy(w.dev, host, bytes, cudaMemcpyHostToDevice));
+    ctx->h2d += (int64_t)bytes;
+    ctx->weights[host] = w;
+    if (dev) *dev = w.dev;
+    return 0;
+}
+
+void *ps_cuda_lookup_weight(ps_cuda_ctx *ctx, const void *host) {
+    auto it = ctx->weights.find(host);
+    return it == ctx->weights.end() ? nullptr : it->second.dev;
+}
+
+// ---------------------------------------------------------------------------------------------- operator table
+static int stage_ints(ps_cuda_ctx *ctx, int32_t *dev, int32_t *pinned, const int32_t *host, int64_t n) {
+    if (n > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "batch %lld exceeds max_batch %d", (long long)n, ctx->d.max_batch);
+    PS_CK(cudaStreamSynchronize(ctx->stream)); // the pinned staging buffer may still be in flight
+    memcpy(pinned, host, (size_t)n * 4);
+    PS_CK(cudaMemcpyAsync(dev, pinned, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += n * 4;
+    return 0;
+}
+
+int ps_cuda_get_embedding(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype, int64_t dim, const int32_t *tokens, int64_t bs) {
+    if (!type_ok(wtype) || dim % blk_elems(wtype)) return fail(ctx, PS_CUDA_ERR_INVALID, "get_embedding: bad type/dim");
+    int rc = stage_ints(ctx, ctx->tokens_dev, ctx->h_tokens, tokens, bs);
+    if (rc) return rc;
+    ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(dst, (const uint8_t *)w, wtype, dim, ctx->tokens_dev);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_rmsnorm(ps_cuda_ctx *ctx, float *dst, const float *x, const float *w, int64_t dim, int64_t bs, float eps) {
+    if (!(eps > 0.0f)) return fail(ctx, PS_CUDA_ERR_INVALID, "rmsnorm: eps must be > 0 (GGML_ASSERT, ggml.c:12684)");
+    ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(dst, x, w, dim, eps);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_matmul(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype, int64_t K, int64_t N, const float *x, int64_t bs) {
+    if (bs <= 0 || N <= 0) return fail(ctx, PS_CUDA_ERR_INVALID, "matmul: empty shape");
+    int rc = quantize_act(ctx, wtype, x, K, bs);
+    if (rc) return rc;
+    return matmul_q(ctx, dst, (const uint8_t *)w, wtype, K, N, bs, nullptr, nullptr);
+}
+
+int ps_cuda_rope(ps_cuda_ctx *ctx, float *dst, const float *src, int64_t head_size, int64_t n_heads, int64_t bs, const int32_t *pos) {
+    if (head_size != ctx->d.head_size) return fail(ctx, PS_CUDA_ERR_INVALID, "rope: head_size %lld != model head_size %d", (long long)head_size, ctx->d.head_size);
+    for (int64_t i = 0; i < bs; i++)
+        if (pos[i] < 0 || pos[i] >= ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_INVALID, "rope: position %d outside [0,%d)", pos[i], ctx->d.n_ctx);
+    int rc = stage_ints(ctx, ctx->pos_dev, ctx->h_pos, pos, bs);
+    if (rc) return rc;
+    ps_k_rope<<<dim3((unsigned)n_heads, (unsigned)bs), 64, 0, ctx->stream>>>(dst, src, (int)head_size, ctx->d.rope_n_dims, ctx->d.rope_type & 2,
+                                                                              ctx->pos_dev, ctx->rope_table);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_add(ps_cuda_ctx *ctx, float *dst, const float *a, const float *b, int64_t n, int64_t nb) {
+    if (nb <= 0 || n % nb) return fail(ctx, PS_CUDA_ERR_INVALID, "add: broadcast size %lld does not divide %lld", (long long)nb, (long long)n);
+    ps_k_add<<<grid1d(n), 256, 0, ctx->stream>>>(dst, a, b, n, nb);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_silu_hadamard(ps_cuda_ctx *ctx, float *dst, const float *gate, const float *up, int64_t n) {
+    ps_k_silu_hadamard<<<grid1d(n), 256, 0, ctx->stream>>>(dst, gate, up, n);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_get_mask(ps_cuda_ctx *ctx, float *mask, int64_t n_kv, int64_t bs, const int32_t *pos) {
+    int rc = stage_ints(ctx, ctx->pos_dev, ctx->h_pos, pos, bs);
+    if (rc) return rc;
+    ps_k_get_mask<<<dim3((unsigned)std::min<int64_t>((n_kv + 255) / 256, 64), (unsigned)bs), 256, 0, ctx->stream>>>(mask, n_kv, ctx->pos_dev);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_softmax_ext(ps_cuda_ctx *ctx, float *dst, const float *x, const float *mask, int64_t ne0, int64_t ne1, int64_t ne2, float scale) {
+    if (!mask) return fail(ctx, PS_CUDA_ERR_INVALID, "softmax_ext: mask is required (use get_mask)");
+    if (ne0 * 4 > 160 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "softmax_ext: row of %lld exceeds shared memory", (long long)ne0);
+    static bool attr = false;
+    if (!attr) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    ps_k_softmax_ext<<<(unsigned)(ne1 * ne2), 256, (size_t)ne0 * 4, ctx->stream>>>(dst, x, mask, nullptr, ne0, ne1, scale);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_attn_scores(ps_cuda_ctx *ctx, float *kq, const float *k_cache, const float *q, int64_t hs, int64_t n_heads, int64_t n_kv_heads,
+                        int64_t n_kv, int64_t bs) {
+    if (hs % 32 || hs > 256 || n_heads % n_kv_heads) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "attn_scores: head geometry");
+    ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)n_kv_heads), 128, 0, ctx->stream>>>(kq, k_cache, q, (int)hs, (int)n_heads,
+                                                                                                     (int)n_kv_heads, n_kv, (int)bs);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_attn_pv(ps_cuda_ctx *ctx, float *out, const float *v_cache_t, const float *p, int64_t hs, int64_t n_heads, int64_t n_kv_heads,
+                    int64_t n_kv, int64_t n_ctx, int64_t bs) {
+    if (hs % 32 || n_heads % n_kv_heads) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "attn_pv: head geometry");
+    ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)n_kv_heads), 128, 0, ctx->stream>>>(out, v_cache_t, p, (int)hs, (int)n_heads,
+                                                                                               (int)n_kv_heads, n_kv, n_ctx, (int)bs);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_copy_2d(ps_cuda_ctx *ctx, void *dst, int64_t ds0, int64_t ds1, const void *src, int64_t ss0, int64_t ss1, int64_t ne0, int64_t ne1) {
+    ps_k_copy_2d<<<grid1d(ne0 * ne1), 256, 0, ctx->stream>>>((uint8_t *)dst, ds0, ds1, (const uint8_t *)src, ss0, ss1, ne0, ne1);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- KV cache
+int ps_cuda_kv_position(ps_cuda_ctx *ctx) { return ctx->position; }
+int ps_cuda_kv_reset(ps_cuda_ctx *ctx) { ctx->position = 0; return 0; }
+int ps_cuda_kv_truncate(ps_cuda_ctx *ctx, int n) {
+    if (n < 0) return fail(ctx, PS_CUDA_ERR_INVALID, "kv_truncate: negative size");
+    if (n < ctx->position) ctx->position = n; // truncate_tokens, kv_cache.hpp:265-271
+    return 0;
+}
+int ps_cuda_kv_rollback(ps_cuda_ctx *ctx, int n) {
+    if (n < 0 || n > ctx->position) return fail(ctx, PS_CUDA_ERR_INVALID, "kv_rollback: %d > position %d (POWERSERVE_ASSERT_KVCACHE)", n, ctx->position);
+    ctx->position -= n;
+    return 0;
+}
+int ps_cuda_kv_advance(ps_cuda_ctx *ctx, int n) {
+    if (n < 0 || ctx->position + n > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
+    ctx->position += n;
+    return 0;
+}
+float *ps_cuda_kv_k(ps_cuda_ctx *ctx, int layer) { return (layer >= 0 && layer < ctx->d.n_layers) ? ctx->kc[layer] : nullptr; }
+float *ps_cuda_kv_v(ps_cuda_ctx *ctx, int layer) { return (layer >= 0 && layer < ctx->d.n_layers) ? ctx->vct[layer] : nullptr; }
+
+// ---------------------------------------------------------------------------------------------- whole model
+int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int64_t qdim = (int64_t)d.n_heads * d.head_size, kvd = (int64_t)d.n_kv_heads * d.head_size;
+    auto reg = [&](const ps_cuda_tensor &t, int64_t ne0, int64_t ne1, const void **dev, int *type) -> int {
+        if (!t.host) return fail(ctx, PS_CUDA_ERR_INVALID, "bind_model: missing tensor");
+        void *p = nullptr;
+        int rc = ps_cuda_register_weight(ctx, t.host, t.type, ne0, ne1, &p);
+        if (rc) return rc;
+        *dev = p;
+        if (type) *type = t.type;
+        return 0;
+    };
+#define REG(t, ne0, ne1, dev, type)                                   \
+    do {                                                              \
+        int rc_ = reg(t, ne0, ne1, (const void **)&(dev), type);      \
+        if (rc_) return rc_;                                          \
+    } while (0)
+    REG(w->token_embd, d.dim, d.vocab_size, ctx->w_embd, &ctx->t_embd);
+    REG(w->output, d.dim, d.vocab_size, ctx->w_out, &ctx->t_out);
+    REG(w->output_norm, d.dim, 1, ctx->w_out_norm, nullptr);
+    if (w->output_norm.type != 0) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "norm weights must be F32");
+    ctx->layers.assign(d.n_layers, LayerDev{});
+    for (int L = 0; L < d.n_layers; L++) {
+        const ps_cuda_layer_weights &lw = w->layers[L];
+        LayerDev &ld = ctx->layers[L];
+        if (lw.attn_norm.type != 0 || lw.ffn_norm.type != 0) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "norm weights must be F32");
+        REG(lw.attn_norm, d.dim, 1, ld.attn_norm, nullptr);
+        REG(lw.ffn_norm, d.dim, 1, ld.ffn_norm, nullptr);
+        REG(lw.attn_q, d.dim, qdim, ld.wq, &ld.tq);
+        REG(lw.attn_k, d.dim, kvd, ld.wk, &ld.tk);
+        REG(lw.attn_v, d.dim, kvd, ld.wv, &ld.tv);
+        REG(lw.attn_output, qdim, d.dim, ld.wo, &ld.to);
+        REG(lw.ffn_gate, d.dim, d.ffn_dim, ld.wgate, &ld.tgate);
+        REG(lw.ffn_up, d.dim, d.ffn_dim, ld.wup, &ld.tup);
+        REG(lw.ffn_down, d.ffn_dim, d.dim, ld.wdown, &ld.tdown);
+        if (d.qkv_bias) {
+            if (lw.attn_q_bias.type != 0 || lw.attn_k_bias.type != 0 || lw.attn_v_bias.type != 0)
+                return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "bias tensors must be F32");
+            REG(lw.attn_q_bias, qdim, 1, ld.q_bias, nullptr);
+            REG(lw.attn_k_bias, kvd, 1, ld.k_bias, nullptr);
+            REG(lw.attn_v_bias, kvd, 1, ld.v_bias, nullptr);
+        }
+        // q/k/v (and gate/up) share one quantised activation: their vec_dot_type must agree
+        auto kq = [](int t) { return t == 12 || t == 14; };
+        if (kq(ld.tq) != kq(ld.tk) || kq(ld.tq) != kq(ld.tv) || kq(ld.tgate) != kq(ld.tup))
+            return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "layer %d mixes K-quant and 32-block weights on one input", L);
+    }
+#undef REG
+    ctx->bound = true;
+    return 0;
+}
+
+// LlamaModel::forward / Qwen2Model::forward on the device, one kernel per table op (the fused / graph-replayed decode
+// path lives in ps_decode.cuh and is bit-identical).
+static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
+    const int64_t n_kv = (int64_t)pos0 + bs; // pos.back() + 1
+    const float kq_scale = 1.0f / sqrtf((float)hs);
+    int rc;
+    ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
+    PS_LAUNCH_CK();
+    static bool attr = false;
+    if (!attr) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    for (int L = 0; L < d.n_layers; L++) {
+        const LayerDev &ld = ctx->layers[L];
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tq, ctx->xn, dim, bs))) return rc;
+        if ((rc = matmul_q(ctx, ctx->q, ld.wq, ld.tq, dim, qdim, bs, d.qkv_bias ? ld.q_bias : nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->k, ld.wk, ld.tk, dim, kvd, bs, d.qkv_bias ? ld.k_bias : nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->v, ld.wv, ld.tv, dim, kvd, bs, d.qkv_bias ? ld.v_bias : nullptr, nullptr))) return rc;
+        ps_k_rope<<<dim3((unsigned)nh, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->qr, ctx->q, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_rope<<<dim3((unsigned)nkv, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
+        PS_LAUNCH_CK();
+        ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
+        PS_LAUNCH_CK();
+        ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
+        PS_LAUNCH_CK();
+        ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.to, ctx->att, qdim, bs))) return rc;
+        if ((rc = matmul_q(ctx, ctx->x, ld.wo, ld.to, qdim, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wo.att
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.ffn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tgate, ctx->xn, dim, bs))) return rc;
+        if ((rc = matmul_q(ctx, ctx->g, ld.wgate, ld.tgate, dim, ffn, bs, nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->u, ld.wup, ld.tup, dim, ffn, bs, nullptr, nullptr))) return rc;
+        ps_k_silu_hadamard<<<grid1d(ffn * bs), 256, 0, ctx->stream>>>(ctx->g, ctx->g, ctx->u, ffn * bs);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tdown, ctx->g, ffn, bs))) return rc;
+        if ((rc = matmul_q(ctx, ctx->x, ld.wdown, ld.tdown, ffn, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wdown.h
+    }
+    if (lm_head) {
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ctx->w_out_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ctx->t_out, ctx->xn, dim, bs))) return rc;
+        if ((rc = matmul_q(ctx, ctx->logits, ctx->w_out, ctx->t_out, dim, d.vocab_size, bs, nullptr, nullptr))) return rc;
+    }
+    return 0;
+}
+
+static int check_forward_args(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs) {
+    if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: no model bound");
+    if (bs <= 0 || bs > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: batch %d outside [1,%d]", bs, ctx->d.max_batch);
+    for (int i = 0; i < bs; i++) {
+        if (tokens[i] < 0 || tokens[i] >= ctx->d.vocab_size) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: token %d outside the vocabulary", tokens[i]);
+        if (pos[i] != pos[0] + i) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward: positions must be consecutive (the CPU path ignores tree masks, SURVEY F7)");
+    }
+    if (pos[0] < 0 || pos[0] + bs > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
+    return 0;
+}
+
+int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, int lm_head, float *logits_host) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    int rc = check_forward_args(ctx, tokens, pos, bs);
+    if (rc) return rc;
+    if (lm_head && !logits_host) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: lm_head requested without a logits buffer");
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_tokens, tokens, (size_t)bs * 4);
+    memcpy(ctx->h_pos, pos, (size_t)bs * 4);
+    PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += (int64_t)bs * 8;
+    if ((rc = forward_ops(ctx, bs, lm_head, pos[0]))) return rc;
+    if (lm_head) {
+        const size_t bytes = (size_t)bs * ctx->d.vocab_size * 4;
+        if (bytes > ctx->h_logits_cap) {
+            if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+            ctx->h_logits = nullptr;
+            ctx->h_logits_cap = 0;
+            PS_CK(cudaMallocHost(&ctx->h_logits, bytes));
+            ctx->h_logits_cap = bytes;
+        }
+        PS_CK(cudaMemcpyAsync(ctx->h_logits, ctx->logits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        PS_CK(cudaStreamSynchronize(ctx->stream));
+        memcpy(logits_host, ctx->h_logits, bytes);
+        ctx->d2h += (int64_t)bytes;
+    } else {
+        PS_CK(cudaStreamSynchronize(ctx->stream));
+    }
+    ctx->position = pos[0] + bs; // m_kv->advance(batch_size), llama_model.cpp:109
+    return 0;
+}
+
+int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, int32_t *ids_host) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "decode_greedy: no model bound");
+    if (n_steps <= 0 || n_steps > 4096) return fail(ctx, PS_CUDA_ERR_INVALID, "decode_greedy: n_steps %d outside [1,4096]", n_steps);
+    if (first_token < 0 || first_token >= ctx->d.vocab_size) return fail(ctx, PS_CUDA_ERR_INVALID, "decode_greedy: bad token");
+    if (ctx->position + n_steps > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    ctx->h_tokens[0] = first_token;
+    PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, 4, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += 4;
+    for (int s = 0; s < n_steps; s++) {
+        const int pos = ctx->position + s;
+        int32_t *slot = &ctx->h_ids[4096 + s]; // one pinned slot per step: the async copies never race with the host writes
+        *slot = pos;
+        PS_CK(cudaMemcpyAsync(ctx->pos_dev, slot, 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d += 4;
+        int rc = forward_ops(ctx, 1, 1, pos);
+        if (rc) return rc;
+        ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits, ctx->d.vocab_size, ctx->ids_dev + s, ctx->tokens_dev);
+        PS_LAUNCH_CK();
+    }
+    PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
+    ctx->d2h += (int64_t)n_steps * 4;
+    ctx->position += n_steps;
+    return 0;
+}
+
+const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx) { return ctx->logits; }
+
+int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
+    if (!strcmp(name, "graph")) ctx->opt_graph = value;
+    else if (!strcmp(name, "fused")) ctx->opt_fused = value;
+    else return fail(ctx, PS_CUDA_ERR_INVALID, "unknown option %s", name);
+    return 0;
+}
+
+int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
+    if (!strcmp(name, "kernel_launches")) return ctx->n_launch;
+    if (!strcmp(name, "graph_replays")) return ctx->n_graph;
+    if (!strcmp(name, "h2d_bytes")) return ctx->h2d;
+    if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
+    return -1;
+}
+
+float ps_cuda_host_expf_ref(float x) { return ps_expf_glibc(x); }
+float ps_cuda_host_v_expf(float x) { return ps_v_expf(x); }
+
+} // extern "C"

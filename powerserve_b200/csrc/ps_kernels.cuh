@@ -1,0 +1,650 @@
+// ps_kernels.cuh — hand-written sm_100a kernels for PowerServe's decode / prefill hot path (table-op granularity).
+//
+// Every kernel cites the reference function it replaces (paths relative to /root/reference).  All of them are
+// HBM/L2-bound integer / fp32 work; the data-path rule is the same everywhere: a warp lane owns one "AVX lane"
+// (four consecutive bytes of a 32-byte group == one dp4a), partial sums stay integer until the reference converts
+// them, and the fp32 accumulation chains are replayed in the reference's order (see ps_math.cuh).
+#pragma once
+#include "ps_math.cuh"
+
+#define PS_FULL 0xffffffffu
+
+// ggml block sizes in bytes (libs/ggml/src/ggml-common.h:158-162, 200-204, 299-310, 335-340)
+#define PS_Q4_0_BYTES 18
+#define PS_Q8_0_BYTES 34
+#define PS_Q4_K_BYTES 144
+#define PS_Q6_K_BYTES 210
+
+__host__ __device__ inline int64_t ps_row_bytes(int type, int64_t k) {
+    switch (type) {
+    case 0: return k * 4;
+    case 2: return k / 32 * PS_Q4_0_BYTES;
+    case 8: return k / 32 * PS_Q8_0_BYTES;
+    case 12: return k / 256 * PS_Q4_K_BYTES;
+    case 14: return k / 256 * PS_Q6_K_BYTES;
+    default: return 0;
+    }
+}
+
+PS_D float ps_half_bits_to_float(uint32_t h16) { return __half2float(__ushort_as_half((unsigned short)h16)); }
+PS_D uint32_t ps_ld_u32_a2(const uint8_t *p) { // 4 bytes from a 2-byte-aligned address
+    const unsigned short *q = reinterpret_cast<const unsigned short *>(p);
+    return (uint32_t)q[0] | ((uint32_t)q[1] << 16);
+}
+
+// hsum_float_8 (libs/ggml/src/ggml-quants.c:62-68) over the values held by lanes 0..7 of the warp; all lanes call.
+PS_D float ps_hsum8_lanes(float v) {
+    float x[8];
+#pragma unroll
+    for (int l = 0; l < 8; l++) x[l] = __shfl_sync(PS_FULL, v, l);
+    const float r0 = __fadd_rn(x[4], x[0]), r1 = __fadd_rn(x[5], x[1]), r2 = __fadd_rn(x[6], x[2]), r3 = __fadd_rn(x[7], x[3]);
+    return __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+}
+
+// GGML_F32x8_REDUCE (libs/ggml/src/ggml.c:1354-1372) when lane t = 8*j + l holds sum[j][l]: the five butterfly
+// steps below are exactly x0+=x2, x1+=x3; x0+=x1; lo128+hi128; hadd; hadd (fp add is commutative, so every lane ends
+// with the same value the reference leaves in element 0).
+PS_D float ps_f32x8_reduce(float v) {
+    v = __fadd_rn(v, __shfl_xor_sync(PS_FULL, v, 16));
+    v = __fadd_rn(v, __shfl_xor_sync(PS_FULL, v, 8));
+    v = __fadd_rn(v, __shfl_xor_sync(PS_FULL, v, 4));
+    v = __fadd_rn(v, __shfl_xor_sync(PS_FULL, v, 1));
+    v = __fadd_rn(v, __shfl_xor_sync(PS_FULL, v, 2));
+    return v;
+}
+
+// ====================================================================================================================
+// Activation quantisers  (replaces the from_float step of powerserve_compute_forward_mul_mat, ggml.c:13502-13530)
+// ====================================================================================================================
+// Device layout of a Q8_K-quantised activation column (K elements, nb = K/256 blocks) — "lane-major" so that the
+// matvec's lane l reads its eight dp4a operands of block i with two 16-byte shared-memory loads:
+//   qs  [nb][2][8] uint4 : word (h, l, w) = bytes of elements 32*(4h+w) + 4l .. +3      (K bytes)
+//   d   [nb] float       : block scale (block_q8_K::d)
+//   bsp [nb][4] uint32   : int16 pair (s_{2k}, s_{2k+1}), s_j = sum of the 32 quants of sub-block j
+//                          (== hadd_epi16 of block_q8_K::bsums, ggml-quants.c:7829-7830)
+
+// quantize_row_q8_K_ref (libs/ggml/src/ggml-quants.c:3799-3837).  One warp per 256-block.
+__global__ void __launch_bounds__(128) ps_k_quantize_q8k(const float *__restrict__ x, int64_t K, uint32_t *__restrict__ qs,
+                                                         float *__restrict__ dq, uint32_t *__restrict__ bsp) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nb = K / 256;
+    const int64_t i = (int64_t)blockIdx.x * 4 + warp;
+    const int64_t col = blockIdx.y;
+    if (i >= nb) return;
+    const int l = lane & 7, jj = lane >> 3;
+    const float *xb = x + col * K + i * 256;
+    const float4 v0 = *reinterpret_cast<const float4 *>(xb + 32 * jj + 4 * l);
+    const float4 v1 = *reinterpret_cast<const float4 *>(xb + 32 * (jj + 4) + 4 * l);
+    const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+    const int idx0 = 32 * jj + 4 * l, idx1 = 32 * (jj + 4) + 4 * l;
+    float amax = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; t++) amax = fmaxf(amax, fabsf(e[t]));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(PS_FULL, amax, o));
+    // `if (ax > amax) { amax = ax; max = x[j]; }` keeps the FIRST element that attains the maximum magnitude
+    int first = 1 << 20;
+#pragma unroll
+    for (int t = 7; t >= 0; t--)
+        if (fabsf(e[t]) == amax) first = (t < 4 ? idx0 + t : idx1 + t - 4);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(PS_FULL, first, o));
+    float mx = 0.f;
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+        if ((t < 4 ? idx0 + t : idx1 + t - 4) == first) mx = e[t];
+    {   // broadcast the signed maximum from its owner
+        const unsigned owner = __ballot_sync(PS_FULL, (first >= idx0 && first < idx0 + 4) || (first >= idx1 && first < idx1 + 4));
+        mx = __shfl_sync(PS_FULL, mx, __ffs(owner) - 1);
+    }
+    uint32_t *qcol = qs + (col * nb + i) * 64; // 64 words per block
+    if (amax == 0.f) {
+        qcol[(0 * 8 + l) * 4 + jj] = 0;
+        qcol[(1 * 8 + l) * 4 + jj] = 0;
+        if (lane == 0) dq[col * nb + i] = 0.f;
+        if (lane < 4) bsp[(col * nb + i) * 4 + lane] = 0;
+        return;
+    }
+    const float iscale = __fdiv_rn(-127.f, mx);
+    int q[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const float val = __fadd_rn(__fmul_rn(iscale, e[t]), 12582912.f); // nearest_int, ggml-quants.c:1653-1658
+        const int v = (int)(ps_f2u(val) & 0x007fffffu) - 0x00400000;
+        q[t] = min(127, v);
+    }
+    const uint32_t w0 = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
+    const uint32_t w1 = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
+    qcol[(0 * 8 + l) * 4 + jj] = w0; // sub-block j = jj      -> half 0, word jj
+    qcol[(1 * 8 + l) * 4 + jj] = w1; // sub-block j = jj + 4  -> half 1, word jj
+    int s0 = q[0] + q[1] + q[2] + q[3], s1 = q[4] + q[5] + q[6] + q[7];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+        s0 += __shfl_xor_sync(PS_FULL, s0, o);
+        s1 += __shfl_xor_sync(PS_FULL, s1, o);
+    }
+    // lane (jj, l=0) holds s_jj and s_{jj+4}; pair k packs (s_{2k}, s_{2k+1})
+    int sj[8];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        sj[j] = __shfl_sync(PS_FULL, s0, j * 8);
+        sj[j + 4] = __shfl_sync(PS_FULL, s1, j * 8);
+    }
+    if (lane < 4) bsp[(col * nb + i) * 4 + lane] = ((uint32_t)sj[2 * lane] & 0xffffu) | ((uint32_t)sj[2 * lane + 1] << 16);
+    if (lane == 0) dq[col * nb + i] = __fdiv_rn(1.f, iscale);
+}
+
+// quantize_row_q8_0, AVX2 branch (libs/ggml/src/ggml-quants.c:957-1017): d = max|x| / 127 stored as fp16,
+// id = 127 / max|x|, round-half-to-even.  One warp handles four 32-blocks (lane = 8*b + l owns word l of block b).
+// Layout: qs [nb32][8] uint32 natural order, d [nb32] float holding fp16(d) widened back (what the dot product reads).
+__global__ void __launch_bounds__(128) ps_k_quantize_q80(const float *__restrict__ x, int64_t K, uint32_t *__restrict__ qs,
+                                                         float *__restrict__ dq) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nb = K / 32;
+    const int64_t i = ((int64_t)blockIdx.x * 4 + warp) * 4 + (lane >> 3);
+    const int64_t col = blockIdx.y;
+    const int l = lane & 7;
+    const bool valid = i < nb;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (valid) v = *reinterpret_cast<const float4 *>(x + col * K + i * 32 + 4 * l);
+    float amax = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) amax = fmaxf(amax, __shfl_xor_sync(PS_FULL, amax, o));
+    if (!valid) return;
+    const float d = __fdiv_rn(amax, 127.f);
+    const float id = (amax != 0.0f) ? __fdiv_rn(127.f, amax) : 0.0f;
+    const int q0 = __float2int_rn(__fmul_rn(v.x, id)), q1 = __float2int_rn(__fmul_rn(v.y, id));
+    const int q2 = __float2int_rn(__fmul_rn(v.z, id)), q3 = __float2int_rn(__fmul_rn(v.w, id));
+    qs[(col * nb + i) * 8 + l] = (uint32_t)(q0 & 0xff) | ((uint32_t)(q1 & 0xff) << 8) | ((uint32_t)(q2 & 0xff) << 16) | ((uint32_t)(q3 & 0xff) << 24);
+    if (l == 0) dq[col * nb + i] = __half2float(__float2half_rn(d));
+}
+
+// ====================================================================================================================
+// Quantised weight x quantised activation  (replaces powerserve_compute_forward_mul_mat -> vec_dot, ggml.c:13344-13432)
+// ====================================================================================================================
+// Lane t = 8*b + l of a warp owns AVX lane l of block (4*it + b) of the row: its integer partial S (and, for Q4_K, the
+// mins product P) are what one lane of the reference's __m256i sumi / __m128i prod holds after the block.  The fp32
+// accumulators acc[l] (and acc_m[k]) are then advanced block by block IN ROW ORDER with one FMA each, the values
+// travelling between lanes by shuffle, and reduced once at the end in hsum_float_8 order.
+
+struct PsActQ8K { const uint4 *qs; const float *d; const uint32_t *bsp; };  // shared-memory views of one column
+struct PsActQ80 { const uint32_t *qs; const float *d; };
+
+template <int TYPE> struct PsBlk;
+
+// ggml_vec_dot_q4_K_q8_K, AVX2 branch (libs/ggml/src/ggml-quants.c:7809-7872)
+template <> struct PsBlk<12> {
+    static constexpr int BYTES = PS_Q4_K_BYTES, ELEMS = 256;
+    static constexpr bool HAS_MIN = true;
+    uint32_t q4[4], scA, scB, mA, mB;
+    float xd, xmin;
+    PS_D void load(const uint8_t *blk, int l) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(blk);
+        xd = ps_half_bits_to_float(h.x & 0xffffu);
+        xmin = ps_half_bits_to_float(h.x >> 16);
+        // the utmp / kmask shuffle of :7816-7826 (== get_scale_min_k4 for all eight j)
+        const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
+        mB = ((h.w >> 4) & k2) | (((h.z >> 6) & k3) << 4);
+        mA = h.z & k1;
+        scB = (h.w & k2) | (((h.y >> 6) & k3) << 4);
+        scA = h.y & k1;
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(blk + 16) + l;
+#pragma unroll
+        for (int j = 0; j < 4; j++) q4[j] = q[8 * j];
+    }
+    PS_D void partial(const PsActQ8K &a, int64_t i, int l, int &S, float &d, int &P, float &dm) const {
+        const uint4 lo = a.qs[(i * 2 + 0) * 8 + l], hi = a.qs[(i * 2 + 1) * 8 + l];
+        const int q8[8] = {(int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w, (int)hi.x, (int)hi.y, (int)hi.z, (int)hi.w};
+        S = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const int p0 = __dp4a((int)(q4[j] & 0x0f0f0f0fu), q8[2 * j], 0);
+            const int p1 = __dp4a((int)((q4[j] >> 4) & 0x0f0f0f0fu), q8[2 * j + 1], 0);
+            const uint32_t scw = (j < 2) ? scA : scB;
+            const int s0 = (scw >> (16 * (j & 1))) & 0xff, s1 = (scw >> (16 * (j & 1) + 8)) & 0xff;
+            S += s0 * p0 + s1 * p1;
+        }
+        const float yd = a.d[i];
+        d = __fmul_rn(yd, xd);
+        dm = __fmul_rn(-yd, xmin);
+        // prod lane k = l & 3: m_{2k} * s_{2k} + m_{2k+1} * s_{2k+1}  (madd_epi16 of mins with the hadd'ed bsums)
+        const int k = l & 3;
+        const uint32_t mw = (k < 2) ? mA : mB;
+        const int m0 = (mw >> (16 * (k & 1))) & 0xff, m1 = (mw >> (16 * (k & 1) + 8)) & 0xff;
+        const uint32_t bs = a.bsp[i * 4 + k];
+        P = m0 * (int)(short)(bs & 0xffffu) + m1 * (int)(short)(bs >> 16);
+    }
+};
+
+// ggml_vec_dot_q6_K_q8_K, AVX2 branch (libs/ggml/src/ggml-quants.c:9039-9116)
+template <> struct PsBlk<14> {
+    static constexpr int BYTES = PS_Q6_K_BYTES, ELEMS = 256;
+    static constexpr bool HAS_MIN = false;
+    uint32_t ql[4], qh[2];
+    int sc[8];
+    float xd;
+    PS_D void load(const uint8_t *blk, int l) {
+#pragma unroll
+        for (int jh = 0; jh < 2; jh++) {
+            ql[2 * jh + 0] = ps_ld_u32_a2(blk + 64 * jh + 4 * l);
+            ql[2 * jh + 1] = ps_ld_u32_a2(blk + 64 * jh + 32 + 4 * l);
+            qh[jh] = ps_ld_u32_a2(blk + 128 + 32 * jh + 4 * l);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; j++) sc[j] = (int)(signed char)blk[192 + 2 * j + (l >= 4)];
+        xd = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk + 208));
+    }
+    PS_D void partial(const PsActQ8K &a, int64_t i, int l, int &S, float &d, int &P, float &dm) const {
+        const uint4 lo = a.qs[(i * 2 + 0) * 8 + l], hi = a.qs[(i * 2 + 1) * 8 + l];
+        const int q8[8] = {(int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w, (int)hi.x, (int)hi.y, (int)hi.z, (int)hi.w};
+        S = 0;
+#pragma unroll
+        for (int jh = 0; jh < 2; jh++)
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                const uint32_t lw = ql[2 * jh + (g & 1)];
+                const uint32_t nib = (g < 2) ? (lw & 0x0f0f0f0fu) : ((lw >> 4) & 0x0f0f0f0fu);
+                const uint32_t q = __vsub4(nib | (((qh[jh] >> (2 * g)) & 0x03030303u) << 4), 0x20202020u);
+                S += sc[4 * jh + g] * __dp4a((int)q, q8[4 * jh + g], 0);
+            }
+        d = __fmul_rn(a.d[i], xd);
+        P = 0;
+        dm = 0.f;
+    }
+};
+
+// ggml_vec_dot_q4_0_q8_0, AVX2 branch (libs/ggml/src/ggml-quants.c:4205-4228)
+template <> struct PsBlk<2> {
+    static constexpr int BYTES = PS_Q4_0_BYTES, ELEMS = 32;
+    static constexpr bool HAS_MIN = false;
+    uint32_t q;
+    float xd;
+    PS_D void load(const uint8_t *blk, int l) {
+        const uint32_t w = ps_ld_u32_a2(blk + 2 + 4 * (l & 3));
+        q = __vsub4((l < 4) ? (w & 0x0f0f0f0fu) : ((w >> 4) & 0x0f0f0f0fu), 0x08080808u);
+        xd = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+    }
+    PS_D void partial(const PsActQ80 &a, int64_t i, int l, int &S, float &d, int &P, float &dm) const {
+        S = __dp4a((int)q, (int)a.qs[i * 8 + l], 0);
+        d = __fmul_rn(xd, a.d[i]);
+        P = 0;
+        dm = 0.f;
+    }
+};
+
+// ggml_vec_dot_q8_0_q8_0, AVX2 branch (libs/ggml/src/ggml-quants.c:5761-5782)
+template <> struct PsBlk<8> {
+    static constexpr int BYTES = PS_Q8_0_BYTES, ELEMS = 32;
+    static constexpr bool HAS_MIN = false;
+    uint32_t q;
+    float xd;
+    PS_D void load(const uint8_t *blk, int l) {
+        q = ps_ld_u32_a2(blk + 2 + 4 * l);
+        xd = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+    }
+    PS_D void partial(const PsActQ80 &a, int64_t i, int l, int &S, float &d, int &P, float &dm) const {
+        S = __dp4a((int)q, (int)a.qs[i * 8 + l], 0);
+        d = __fmul_rn(xd, a.d[i]);
+        P = 0;
+        dm = 0.f;
+    }
+};
+
+// dst{N, bs} = W{K, N} . x{K, bs}; one warp per weight row, C activation columns per pass (gridDim.y passes).
+// Shared memory holds the C quantised columns.  Row results are bit-identical for every C (each column has its own
+// chain), which tests/test_gpu_ops.py checks.
+template <int TYPE, int C>
+__global__ void __launch_bounds__(256) ps_k_matmul_q(const uint8_t *__restrict__ w, int64_t K, int64_t N, int64_t bs,
+                                                     const uint32_t *__restrict__ aqs, const float *__restrict__ ad,
+                                                     const uint32_t *__restrict__ absp, float *__restrict__ dst,
+                                                     const float *__restrict__ bias, const float *__restrict__ residual) {
+    using B = PsBlk<TYPE>;
+    constexpr bool KQ = (B::ELEMS == 256);
+    extern __shared__ __align__(16) uint8_t smem[];
+    const int64_t nb = K / B::ELEMS;
+    const int64_t col0 = (int64_t)blockIdx.y * C;
+    const int ncol = (int)min((int64_t)C, bs - col0);
+    // ---- stage the quantised activation columns
+    const int64_t qwords = K / 4;                       // words of quants per column
+    uint32_t *s_qs = reinterpret_cast<uint32_t *>(smem);                      // [C][K/4]
+    float *s_d = reinterpret_cast<float *>(s_qs + (int64_t)C * qwords);       // [C][nb]
+    uint32_t *s_bsp = reinterpret_cast<uint32_t *>(s_d + (int64_t)C * nb);    // [C][nb*4] (K-quants only)
+    for (int c = 0; c < ncol; c++) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(aqs + (col0 + c) * qwords);
+        uint4 *dstq = reinterpret_cast<uint4 *>(s_qs + c * qwords);
+        for (int64_t t = threadIdx.x; t < qwords / 4; t += blockDim.x) dstq[t] = src[t];
+        for (int64_t t = threadIdx.x; t < nb; t += blockDim.x) s_d[c * nb + t] = ad[(col0 + c) * nb + t];
+        if (KQ)
+            for (int64_t t = threadIdx.x; t < nb * 4; t += blockDim.x) s_bsp[c * nb * 4 + t] = absp[(col0 + c) * nb * 4 + t];
+    }
+    __syncthreads();
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, l = lane & 7, b = lane >> 3;
+    const int64_t n = (int64_t)blockIdx.x * 8 + warp;
+    if (n >= N) return;
+    const uint8_t *wrow = w + n * nb * B::BYTES;
+    float acc[C], accm[C];
+#pragma unroll
+    for (int c = 0; c < C; c++) { acc[c] = 0.f; accm[c] = 0.f; }
+    for (int64_t i0 = 0; i0 < nb; i0 += 4) {
+        const int64_t i = i0 + b;
+        const bool valid = i < nb;
+        B blk;
+        if (valid) blk.load(wrow + i * B::BYTES, l);
+        const int nvalid = (int)min((int64_t)4, nb - i0);
+#pragma unroll
+        for (int c = 0; c < C; c++) {
+            if (c < ncol) {
+                int S = 0, P = 0;
+                float d = 0.f, dm = 0.f;
+                if (valid) {
+                    if constexpr (KQ) {
+                        PsActQ8K a{reinterpret_cast<const uint4 *>(s_qs + c * qwords), s_d + c * nb, s_bsp + c * nb * 4};
+                        blk.partial(a, i, l, S, d, P, dm);
+                    } else {
+                        PsActQ80 a{s_qs + c * qwords, s_d + c * nb};
+                        blk.partial(a, i, l, S, d, P, dm);
+                    }
+                }
+                // advance the 8 (+4) accumulator chains over the (up to) four blocks of this step, in row order
+                for (int bb = 0; bb < nvalid; bb++) {
+                    const int Sb = __shfl_sync(PS_FULL, S, bb * 8 + l);
+                    const float db = __shfl_sync(PS_FULL, d, bb * 8 + l);
+                    acc[c] = __fmaf_rn(db, __int2float_rn(Sb), acc[c]);
+                    if constexpr (B::HAS_MIN) {
+                        const int Pb = __shfl_sync(PS_FULL, P, bb * 8 + (l & 3));
+                        const float dmb = __shfl_sync(PS_FULL, dm, bb * 8 + l);
+                        accm[c] = __fmaf_rn(dmb, __int2float_rn(Pb), accm[c]);
+                    }
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int c = 0; c < C; c++) {
+        if (c < ncol) {
+            float r = ps_hsum8_lanes(acc[c]);
+            if constexpr (B::HAS_MIN) {
+                // acc_m = add(acc_m, movehl(acc_m)); add_ss(acc_m, movehdup(acc_m))   (ggml-quants.c:7868-7871)
+                const float m0 = __shfl_sync(PS_FULL, accm[c], 0), m1 = __shfl_sync(PS_FULL, accm[c], 1);
+                const float m2 = __shfl_sync(PS_FULL, accm[c], 2), m3 = __shfl_sync(PS_FULL, accm[c], 3);
+                r = __fadd_rn(r, __fadd_rn(__fadd_rn(m0, m2), __fadd_rn(m1, m3)));
+            }
+            if (lane == 0) {
+                const int64_t o = (col0 + c) * N + n;
+                if (bias) r = __fadd_rn(r, bias[n]);          // GGMLBackend::add with row broadcast (Qwen2 q/k/v bias)
+                if (residual) r = __fadd_rn(residual[o], r);  // residual add: x + W.h  (powerserve_compute_forward_add)
+                dst[o] = r;
+            }
+        }
+    }
+}
+
+// ====================================================================================================================
+// Small fp32 operators
+// ====================================================================================================================
+// GGMLBackend::get_embedding (src/backend/ggml/ggml_wrapper.cpp:181-211) + dequantize_row_* (ggml-quants.c:1536,
+// 1630, 2569, 2991).  One CTA per token row.
+__global__ void __launch_bounds__(256) ps_k_get_embedding(float *__restrict__ dst, const uint8_t *__restrict__ w, int type,
+                                                          int64_t dim, const int32_t *__restrict__ tokens) {
+    const int64_t tok = tokens[blockIdx.x];
+    const uint8_t *row = w + tok * ps_row_bytes(type, dim);
+    float *y = dst + (int64_t)blockIdx.x * dim;
+    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) {
+        float v;
+        if (type == 0) {
+            v = reinterpret_cast<const float *>(row)[e];
+        } else if (type == 2) {
+            const uint8_t *blk = row + (e / 32) * PS_Q4_0_BYTES;
+            const float d = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+            const int j = (int)(e % 32);
+            const int q = (j < 16) ? (blk[2 + j] & 0x0F) - 8 : (blk[2 + j - 16] >> 4) - 8;
+            v = __fmul_rn((float)q, d);
+        } else if (type == 8) {
+            const uint8_t *blk = row + (e / 32) * PS_Q8_0_BYTES;
+            const float d = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+            v = __fmul_rn((float)(int)(signed char)blk[2 + e % 32], d);
+        } else if (type == 12) {
+            const uint8_t *blk = row + (e / 256) * PS_Q4_K_BYTES;
+            const int r = (int)(e % 256), j = r / 32, el = r % 32;
+            const float d = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+            const float mn = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk + 2));
+            const uint8_t *sc = blk + 4;
+            int s, m; // get_scale_min_k4, ggml-quants.c:1912-1919
+            if (j < 4) { s = sc[j] & 63; m = sc[j + 4] & 63; }
+            else { s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
+            const uint8_t qb = blk[16 + 32 * (j / 2) + el];
+            const int q = (j & 1) ? (qb >> 4) : (qb & 0xF);
+            // `d1 * q - m1` is one FMA in the reference build (gcc -O3 -mfma contracts it)
+            v = __fmaf_rn(__fmul_rn(d, (float)s), (float)q, -__fmul_rn(mn, (float)m));
+        } else { // 14: Q6_K
+            const uint8_t *blk = row + (e / 256) * PS_Q6_K_BYTES;
+            const int r = (int)(e % 256), half = r / 128, rr = r % 128, g = rr / 32, lq = rr % 32;
+            const float d = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk + 208));
+            const uint8_t lb = blk[64 * half + (g & 1) * 32 + lq], hb = blk[128 + 32 * half + lq];
+            const int q = (int)(signed char)(((g < 2) ? (lb & 0xF) : (lb >> 4)) | (((hb >> (2 * g)) & 3) << 4)) - 32;
+            const int s = (int)(signed char)blk[192 + 8 * half + 2 * g + lq / 16];
+            v = __fmul_rn(__fmul_rn(d, (float)s), (float)q);
+        }
+        y[e] = v;
+    }
+}
+
+// block-wide sum of doubles (tree order; see DESIGN.md "double-precision sums")
+PS_D double ps_block_sum_double(double v, double *sh) {
+#pragma unroll
+    for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(PS_FULL, v, o);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    double t = (threadIdx.x < nw) ? sh[threadIdx.x] : 0.0;
+    if (warp == 0) {
+#pragma unroll
+        for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(PS_FULL, t, o);
+        if (lane == 0) sh[0] = t;
+    }
+    __syncthreads();
+    return sh[0];
+}
+
+// powerserve_compute_forward_rms_norm_f32 (libs/ggml/src/ggml.c:12667-12721): y = x * (w * 1/sqrtf(mean(x^2)+eps)),
+// the sum of fp32 squares accumulated in double.  One CTA per row.
+__global__ void __launch_bounds__(256) ps_k_rmsnorm(float *__restrict__ dst, const float *__restrict__ x, const float *__restrict__ w,
+                                                    int64_t dim, float eps) {
+    __shared__ double sh[32];
+    const float *xr = x + (int64_t)blockIdx.x * dim;
+    float *yr = dst + (int64_t)blockIdx.x * dim;
+    double s = 0.0;
+    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) s += (double)__fmul_rn(xr[e], xr[e]);
+    const double sum = ps_block_sum_double(s, sh);
+    const float mean = (float)(sum / (double)dim);
+    const float scale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, eps)));
+    for (int64_t e = threadIdx.x; e < dim; e += blockDim.x) yr[e] = __fmul_rn(xr[e], __fmul_rn(w[e], scale));
+}
+
+// ggml_compute_forward_rope_f32 (libs/ggml/src/ggml.c:15368-15497) with the cos/sin cache of ggml_rope_cache_init
+// (:15342-15356) precomputed for every position by the host (ps_cuda.cu: build_rope_table) — table[pos][i0] = cos,
+// table[pos][i0+1] = sin.  src/dst {head_size, n_heads, bs}; grid (n_heads, bs).
+__global__ void ps_k_rope(float *__restrict__ dst, const float *__restrict__ src, int head_size, int n_dims, int neox,
+                          const int32_t *__restrict__ pos, const float *__restrict__ table) {
+    const int64_t row = (int64_t)blockIdx.y * gridDim.x + blockIdx.x;
+    const float *s = src + row * head_size;
+    float *d = dst + row * head_size;
+    const float *cache = table + (int64_t)pos[blockIdx.y] * head_size;
+    for (int p = threadIdx.x; p < head_size / 2; p += blockDim.x) {
+        const int i0 = 2 * p;
+        if (i0 < n_dims) {
+            const float c = cache[i0], sn = cache[i0 + 1];
+            const int a = neox ? p : i0, bidx = neox ? p + n_dims / 2 : i0 + 1;
+            const float x0 = s[a], x1 = s[bidx];
+            d[a] = __fadd_rn(__fmul_rn(x0, c), -__fmul_rn(x1, sn));    // x0*c - x1*s  (not fused in the reference)
+            d[bidx] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));  // x0*s + x1*c
+        } else {
+            d[i0] = s[i0];
+            d[i0 + 1] = s[i0 + 1];
+        }
+    }
+}
+
+// KV store: the two COPY ops of NormAttention::build (src/model/module/norm_attention.cpp:79-105).
+// K cache [n_ctx][kv_dim] <- rope(k) rows at pos0..; V cache TRANSPOSED [kv_dim][n_ctx] <- v columns at pos0..
+__global__ void ps_k_kv_store(float *__restrict__ kc, float *__restrict__ vct, const float *__restrict__ k, const float *__restrict__ v,
+                              int64_t kv_dim, int64_t n_ctx, const int32_t *__restrict__ pos, int64_t bs) {
+    const int64_t pos0 = pos[0];
+    const int64_t total = kv_dim * bs;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / kv_dim, e = t % kv_dim;
+        kc[(pos0 + i) * kv_dim + e] = k[t];
+        vct[e * n_ctx + pos0 + i] = v[t];
+    }
+}
+
+// GET_MASK (src/executor/executor.cpp:210-224)
+__global__ void ps_k_get_mask(float *__restrict__ mask, int64_t n_kv, const int32_t *__restrict__ pos) {
+    const int64_t i = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_kv; j += (int64_t)gridDim.x * blockDim.x)
+        mask[j + i * n_kv] = (j <= (int64_t)pos[i]) ? 0.f : -INFINITY;
+}
+
+// mat_mul(k_view, q) (norm_attention.cpp:115-129) -> ggml_vec_dot_f32 (ggml.c:2092-2131), head_size a multiple of 32.
+// One warp per (cache position j, kv head): the K row is read once and dotted with every q head of the group and
+// every batch column.  kq {n_kv, bs, n_heads}.
+__global__ void __launch_bounds__(128) ps_k_attn_scores(float *__restrict__ kq, const float *__restrict__ kc, const float *__restrict__ q,
+                                                        int hs, int n_heads, int n_kv_heads, int64_t n_kv, int bs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t j = (int64_t)blockIdx.x * 4 + warp;
+    const int g = blockIdx.y;
+    if (j >= n_kv) return;
+    const int r2 = n_heads / n_kv_heads;
+    const float *krow = kc + j * (int64_t)(hs * n_kv_heads) + g * hs;
+    float kv[8];
+    const int steps = hs / 32;
+    for (int s = 0; s < steps; s++) kv[s] = krow[32 * s + lane];
+    for (int i = 0; i < bs; i++)
+        for (int hh = 0; hh < r2; hh++) {
+            const int h = g * r2 + hh;
+            const float *qv = q + ((int64_t)i * n_heads + h) * hs;
+            float sum = 0.f;
+            for (int s = 0; s < steps; s++) sum = __fmaf_rn(kv[s], qv[32 * s + lane], sum);
+            sum = ps_f32x8_reduce(sum);
+            if (lane == 0) kq[((int64_t)h * bs + i) * n_kv + j] = sum;
+        }
+}
+
+// ggml_compute_forward_soft_max_f32 (ggml.c:14846-14940) + ggml_vec_soft_max_f32 AVX2 branch (:2814-2868).
+// One CTA per row of {ne0, ne1, ne2}.  mask == nullptr -> the position mask of GET_MASK is applied from `pos`.
+__global__ void __launch_bounds__(256) ps_k_softmax_ext(float *__restrict__ dst, const float *__restrict__ x, const float *__restrict__ mask,
+                                                        const int32_t *__restrict__ pos, int64_t ne0, int64_t ne1, float scale) {
+    extern __shared__ float wp[];
+    __shared__ double sh[32];
+    __shared__ float shf[32];
+    const int64_t row = blockIdx.x, i1 = row % ne1;
+    const float *sp = x + row * ne0;
+    float *dp = dst + row * ne0;
+    float mx = -INFINITY;
+    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) {
+        const float m = mask ? mask[i1 * ne0 + j] : ((j <= (int64_t)pos[i1]) ? 0.f : -INFINITY);
+        const float v = __fadd_rn(__fmul_rn(sp[j], scale), m); // ggml_vec_scale_f32 then `wp[i] += slope*mp[i]`, slope == 1
+        wp[j] = v;
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
+    if ((threadIdx.x & 31) == 0) shf[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = shf[0];
+    for (int t = 1; t < (int)((blockDim.x + 31) >> 5); t++) mx = fmaxf(mx, shf[t]);
+    const int64_t n8 = ne0 & ~(int64_t)7;
+    double s = 0.0;
+    for (int64_t gi = threadIdx.x; gi < n8 / 8; gi += blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            v[l] = ps_v_expf(__fadd_rn(wp[gi * 8 + l], -mx));
+            dp[gi * 8 + l] = v[l];
+        }
+        const float r0 = __fadd_rn(v[4], v[0]), r1 = __fadd_rn(v[5], v[1]), r2 = __fadd_rn(v[6], v[2]), r3 = __fadd_rn(v[7], v[3]);
+        s += (double)__fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+    }
+    for (int64_t j = n8 + threadIdx.x; j < ne0; j += blockDim.x) { // scalar tail: libm expf
+        const float v = ps_expf_glibc(__fadd_rn(wp[j], -mx));
+        dp[j] = v;
+        s += (double)v;
+    }
+    const double sum = ps_block_sum_double(s, sh);
+    const float inv = (float)(1.0 / sum);
+    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) dp[j] = __fmul_rn(dp[j], inv);
+}
+
+// mat_mul(v_view, kq) + permute + cont (norm_attention.cpp:138-151): out[i][h*hs + d] = vec_dot_f32(n_kv, Vt row, P row).
+// One warp per (kv head g, d): the V^T row is streamed once for all heads of the group and all columns.
+__global__ void __launch_bounds__(128) ps_k_attn_pv(float *__restrict__ out, const float *__restrict__ vct, const float *__restrict__ p,
+                                                    int hs, int n_heads, int n_kv_heads, int64_t n_kv, int64_t n_ctx, int bs) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int d = blockIdx.x * 4 + warp, g = blockIdx.y;
+    if (d >= hs) return;
+    const int r2 = n_heads / n_kv_heads;
+    const float *vrow = vct + ((int64_t)g * hs + d) * n_ctx;
+    const int64_t np = n_kv & ~(int64_t)31;
+    for (int i = 0; i < bs; i++)
+        for (int hh = 0; hh < r2; hh++) {
+            const int h = g * r2 + hh;
+            const float *pr = p + ((int64_t)h * bs + i) * n_kv;
+            float sum = 0.f;
+            for (int64_t s = 0; s < np; s += 32) sum = __fmaf_rn(vrow[s + lane], pr[s + lane], sum);
+            sum = ps_f32x8_reduce(sum);
+            if (lane == 0) {
+                for (int64_t j = np; j < n_kv; j++) sum = __fadd_rn(sum, __fmul_rn(vrow[j], pr[j])); // leftovers: mul, then add
+                out[((int64_t)i * n_heads + h) * hs + d] = sum;
+            }
+        }
+}
+
+// GGMLBackend::silu_hadamard (src/backend/ggml/ggml.cpp:115-129)
+__global__ void ps_k_silu_hadamard(float *__restrict__ dst, const float *__restrict__ g, const float *__restrict__ u, int64_t n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = ps_silu_mul(g[t], u[t]);
+}
+
+// powerserve_compute_forward_add_f32 (libs/ggml/src/ggml.c:10042-10112), src1 row-broadcast
+__global__ void ps_k_add(float *__restrict__ dst, const float *__restrict__ a, const float *__restrict__ b, int64_t n, int64_t nb) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = __fadd_rn(a[t], b[t % nb]);
+}
+
+// powerserve_compute_forward_dup (ggml.c:9519-9558) for 2-D fp32 views with byte strides
+__global__ void ps_k_copy_2d(uint8_t *__restrict__ dst, int64_t ds0, int64_t ds1, const uint8_t *__restrict__ src, int64_t ss0, int64_t ss1,
+                             int64_t ne0, int64_t ne1) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ne0 * ne1; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i0 = t % ne0, i1 = t / ne0;
+        *reinterpret_cast<float *>(dst + i0 * ds0 + i1 * ds1) = *reinterpret_cast<const float *>(src + i0 * ss0 + i1 * ss1);
+    }
+}
+
+// greedy pick (Model::decode with top_k = 1: ProbArray + greedy_sample, src/model/llama/llama_model.cpp:124-128):
+// first maximum wins.  One CTA; writes the id to `out[step]` and to `next_token` (device feedback for the next step).
+__global__ void __launch_bounds__(1024) ps_k_argmax(const float *__restrict__ logits, int64_t n, int32_t *__restrict__ out, int32_t *__restrict__ next_token) {
+    __shared__ float sv[32];
+    __shared__ int si[32];
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
+        const float v = logits[t];
+        if (v > best || (v == best && (int)t < bi)) { best = v; bi = (int)t; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(PS_FULL, best, o);
+        const int oi = __shfl_xor_sync(PS_FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < (int)(blockDim.x >> 5); t++)
+            if (sv[t] > best || (sv[t] == best && si[t] < bi)) { best = sv[t]; bi = si[t]; }
+        if (bi == 0x7fffffff) bi = 0;
+        *out = bi;
+        *next_token = bi;
+    }
+}
