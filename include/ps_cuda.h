@@ -86,6 +86,7 @@ int   ps_cuda_memcpy_h2d(ps_cuda_ctx *ctx, void *dev, const void *host, size_t b
 int   ps_cuda_memcpy_d2h(ps_cuda_ctx *ctx, void *host, const void *dev, size_t bytes);  /* synchronises */
 int   ps_cuda_register_weight(ps_cuda_ctx *ctx, const void *host, int type, int64_t ne0, int64_t ne1, void **dev);
 void *ps_cuda_lookup_weight(ps_cuda_ctx *ctx, const void *host);
+int   ps_cuda_unregister_weight(ps_cuda_ctx *ctx, const void *host); /* frees the device copy (model unload) */
 
 /* ---------------------------------------------------------------------------------------------- operator table
  * One entry per GGMLBackend method on the hot path (ggml.hpp:216-244); all pointers are DEVICE pointers except

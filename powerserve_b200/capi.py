@@ -69,6 +69,7 @@ def load_library() -> C.CDLL:
         "ps_cuda_memcpy_d2h": (ci, [vp, vp, vp, sz]),
         "ps_cuda_register_weight": (ci, [vp, vp, ci, i64, i64, C.POINTER(vp)]),
         "ps_cuda_lookup_weight": (vp, [vp, vp]),
+        "ps_cuda_unregister_weight": (ci, [vp, vp]),
         "ps_cuda_get_embedding": (ci, [vp, fp, vp, ci, i64, i32p, i64]),
         "ps_cuda_rmsnorm": (ci, [vp, fp, fp, fp, i64, i64, C.c_float]),
         "ps_cuda_matmul": (ci, [vp, fp, vp, ci, i64, i64, fp, i64]),
@@ -173,6 +174,9 @@ class CudaBackend:
         p = C.c_void_p()
         self._ck(self.L.ps_cuda_register_weight(self.h, host.ctypes.data, ggml_type, ne0, ne1, C.byref(p)))
         return p.value
+
+    def unregister_weight(self, host: np.ndarray):
+        self._ck(self.L.ps_cuda_unregister_weight(self.h, host.ctypes.data))
 
     def sync(self):
         self._ck(self.L.ps_cuda_sync(self.h))

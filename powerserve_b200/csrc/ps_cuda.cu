@@ -356,6 +356,14 @@ void *ps_cuda_lookup_weight(ps_cuda_ctx *ctx, const void *host) {
     return it == ctx->weights.end() ? nullptr : it->second.dev;
 }
 
+int ps_cuda_unregister_weight(ps_cuda_ctx *ctx, const void *host) {
+    auto it = ctx->weights.find(host);
+    if (it == ctx->weights.end()) return fail(ctx, PS_CUDA_ERR_INVALID, "unregister_weight: unknown host pointer");
+    void *dev = it->second.dev;
+    ctx->weights.erase(it);
+    return ps_cuda_free(ctx, dev);
+}
+
 // ---------------------------------------------------------------------------------------------- operator table
 static int stage_ints(ps_cuda_ctx *ctx, int32_t *dev, int32_t *pinned, const int32_t *host, int64_t n) {
     if (n > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "batch %lld exceeds max_batch %d", (long long)n, ctx->d.max_batch);

@@ -53,7 +53,7 @@ def test_matmul_bit_exact(be, t, blk, bs, kind):
         xd, dd = be.upload(x), be.empty(N * bs)
         be.matmul(dd, wd, t, K, N, xd, bs)
         L.assert_bit_equal(dd.numpy(), ref, f"matmul type={t} K={K} N={N} bs={bs}")
-        xd.free(); dd.free()
+        xd.free(); dd.free(); be.unregister_weight(w)
 
 
 def test_matmul_real_shapes_q4k(be):
@@ -72,7 +72,7 @@ def test_matmul_real_shapes_q4k(be):
         ref = np.zeros(64, np.float32)
         o.ps_or_matmul(L.Q4_K, L.vptr(sub), K, 64, L.fptr(x), 1, L.fptr(ref))
         L.assert_bit_equal(got[rows], ref, f"matmul {K}x{N}")
-        xd.free(); dd.free()
+        xd.free(); dd.free(); be.unregister_weight(w.reshape(-1))
 
 
 @pytest.mark.parametrize("dim,bs", [(64, 1), (896, 3), (4096, 2), (100, 5), (14336, 1)])
@@ -163,6 +163,7 @@ def test_get_embedding(be, t, blk):
     dd = be.empty(dim * 5)
     be.get_embedding(dd, wd, t, dim, toks)
     L.assert_bit_equal(dd.numpy(), ref, "get_embedding")
+    be.unregister_weight(w)
 
 
 @pytest.mark.parametrize("hs,nh,nkv,n_kv,bs", [(64, 4, 2, 1, 1), (64, 8, 2, 37, 1), (128, 8, 2, 100, 3), (64, 14, 2, 65, 2), (128, 32, 8, 2048, 1)])
