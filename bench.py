@@ -1,0 +1,252 @@
+#!/usr/bin/env python
+"""bench.py — BASELINE.json metric: "Llama-3.1-8B Q4_K decode tok/s & prefill tok/s @1 GPU; HBM GB/s vs peak".
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA backend (through the C ABI)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference's own ggml CPU path (oracle/_ref)
+
+A "step" is ONE DECODED TOKEN of the named model with `--prompt` tokens of context already in the KV cache
+(BASELINE.json configs[2]: Llama-3.1-8B Q4_K, prefill 2048 + decode).  `value` is decode tokens/s with everything
+resident in HBM, timed with CUDA events on the backend's stream; `e2e` is the same metric through the reference-
+facing call (`ps_cuda_forward`: HOST token ids in, HOST logits out, every step); prefill tokens/s is reported in
+`prefill`.  Weights are synthetic random Q4_K blocks (no model files / network on the box); they are 4.2 GB per
+token, far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
+
+Multi-GPU (N > 1): until the tensor-parallel path lands the N ranks run independent replicas (weak scaling, no
+collective on the data path) and `value` is the sum over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from powerserve_b200 import gguf, synth  # noqa: E402
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def weight_bytes_per_token(shape: synth.ModelShape) -> int:
+    """Algorithmic bytes of one decoded token: every matmul weight block as stored in the GGUF, read once
+    (SURVEY.md section 8(d)): 7 matrices per layer + lm_head."""
+    n = 0
+    for name, t, shp, _ in synth.tensor_plan(shape):
+        if t != gguf.GGML_F32 and name != "token_embd.weight":
+            n += gguf.tensor_bytes(t, shp)
+    if shape.tied:  # lm_head re-reads the embedding table
+        n += gguf.tensor_bytes(shape.embd_type or shape.wtype, (shape.dim, shape.vocab_size))
+    return n
+
+
+class ClockSampler:
+    """nvidia-smi SM clock / throttle reasons sampled DURING the timed region."""
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.rows, self._stop, self._t = gpu_index, [], threading.Event(), None
+
+    def __enter__(self):
+        def run():
+            q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+            while not self._stop.is_set():
+                try:
+                    r = subprocess.run(["nvidia-smi", f"--id={self.idx}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                       capture_output=True, text=True, timeout=5)
+                    if r.returncode == 0 and r.stdout.strip():
+                        self.rows.append([c.strip() for c in r.stdout.strip().split(",")])
+                except Exception:
+                    pass
+                self._stop.wait(0.1)
+        self._t = threading.Thread(target=run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[2 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
+
+
+def cpu_reference_run(shape, tensors, prompt, n_decode, n_threads, batch_size=128):
+    """Time the reference's own CPU implementation (oracle/_ref/ps_ref_run) on the SAME weights; falls back to the
+    oracle port when the compiled reference did not travel.  Returns (dict, kind)."""
+    ref_exe = os.path.join(ROOT, "oracle", "_ref", "ps_ref_run")
+    if os.path.exists(ref_exe):
+        with tempfile.TemporaryDirectory(dir=os.environ.get("PS_BENCH_TMP", None)) as td:
+            os.makedirs(os.path.join(td, "ggml"))
+            json.dump(synth.model_json(shape), open(os.path.join(td, "model.json"), "w"))
+            gguf.write_gguf(os.path.join(td, "ggml", "weights.gguf"), tensors, arch=shape.arch)
+            pf = os.path.join(td, "prompt.txt")
+            open(pf, "w").write(" ".join(str(int(t)) for t in prompt))
+            r = subprocess.run([ref_exe, td, str(n_threads), str(batch_size), pf, str(n_decode), os.path.join(td, "out")],
+                               capture_output=True, text=True, timeout=3000)
+            if r.returncode != 0:
+                raise RuntimeError("ps_ref_run failed: " + r.stderr[-1000:])
+            tm = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+            ids = [int(x) for x in open(os.path.join(td, "out.ids")).read().split()]
+            return {"decode_tok_s": tm["decode_tok_s"], "prefill_tok_s": tm["prefill_tok_s"], "ids": ids}, "reference"
+    # port: the oracle restatement (single process, its own thread pool)
+    sys.path.insert(0, ROOT)
+    from tests import _model as M  # noqa: F401  (test infrastructure; allowed for the cpu_baseline leg only)
+    raise RuntimeError("oracle/_ref not present and in-memory oracle baseline not wired for bench; run `make -C oracle ref`")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=128)
+    ap.add_argument("--warmup", type=int, default=8)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--model", default="llama-3.1-8b")
+    ap.add_argument("--prompt", type=int, default=2048, help="tokens of context before the timed decode steps")
+    ap.add_argument("--prefill-batch", type=int, default=128)
+    ap.add_argument("--cpu-threads", type=int, default=0)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--seed", type=int, default=0)
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    shape = synth.PRESETS[args.model]
+    shape.n_ctx = max(shape.n_ctx, 4096)
+    hbm_peak, peak_src = peaks()
+    wbytes = weight_bytes_per_token(shape)
+    n_cpu = os.cpu_count() or 2
+    cpu_threads = args.cpu_threads or max(1, min(n_cpu - 1, 32))
+    cfg = {"workload": f"{args.model} Q4_K synthetic: decode 1 token/step at context {args.prompt}+ (BASELINE configs[2]: prefill {args.prompt} + decode)",
+           "context": args.prompt, "prefill_batch": args.prefill_batch, "weight_bytes_per_token": wbytes,
+           "l2": "weights (>= 0.7 GB/token) exceed the 126 MB L2; no explicit flush", "parallelism": f"replicas x{world}" if world > 1 else "1 GPU"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        tensors = synth.generate_tensors(shape, args.seed)
+        prompt = synth.random_prompt(shape.vocab_size, 17, seed=1234)
+        n_dec = max(2, min(args.steps, 9))
+        t0 = time.time()
+        res, kind = cpu_reference_run(shape, tensors, prompt, n_dec + min(args.warmup, 1), cpu_threads)
+        out = {"impl": "reference", "metric": "decode_tok_s", "value": res["decode_tok_s"], "unit": "tok/s", "n_gpus": args.gpus,
+               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / max(res["decode_tok_s"], 1e-9),
+               "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint4 dot, fp32 accumulate", "data": "synthetic",
+               "config": cfg, "prefill": {"value": res["prefill_tok_s"], "unit": "tok/s", "tokens": len(prompt) - 1},
+               "cpu_baseline": {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": kind,
+                                "sample": f"{len(prompt)}-token prompt + {n_dec} greedy decode tokens of the full model, wall clock like app/run/run.cpp:96-154"},
+               "e2e": {"value": res["decode_tok_s"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+               "wall_s": time.time() - t0}
+        print(json.dumps(out))
+        return 0
+
+    # ------------------------------------------------------------------ our arm (CUDA, through the C ABI)
+    import torch
+    import torch.distributed as dist
+
+    from powerserve_b200 import build, capi
+
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    build.build()
+    tensors = synth.generate_tensors(shape, args.seed + 1000 * rank)
+    tmap = {n: gguf.GGUFTensor(n, t, tuple(s), np.ascontiguousarray(d).view(np.uint8).reshape(-1)) for n, t, s, d in tensors}
+    desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=args.prefill_batch, n_ctx=shape.n_ctx, qkv_bias=shape.qkv_bias)
+    model = capi.CudaModel(desc=desc, tensors=tmap, device=local_rank)
+    prompt = synth.random_prompt(shape.vocab_size, args.prompt + 1, seed=1234)
+
+    # prefill (ModelTokenIterator loop: prompt[:-1] in chunks, lm_head=false), wall clock through the C ABI
+    model.reset()
+    t0 = time.perf_counter()
+    model.prefill(prompt, args.prefill_batch)
+    prefill_s = time.perf_counter() - t0
+    tok = int(prompt[-1])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # --- value: device-resident decode (token id fed back on the device), CUDA events on the backend stream
+    model.decode_greedy(tok, args.warmup)
+    barrier()
+    l0 = model.be.counter("kernel_launches")
+    with ClockSampler(local_rank) as clk:
+        ids = model.decode_greedy(tok, args.steps)
+        dev_ms = model.be.counter("last_device_ns") / 1e6
+    launches = model.be.counter("kernel_launches") - l0
+    barrier()
+    # --- e2e: host token -> ps_cuda_forward -> host logits, every step
+    model.be.kv_rollback(args.steps)
+    h0, d0 = model.be.counter("h2d_bytes"), model.be.counter("d2h_bytes")
+    t0 = time.perf_counter()
+    t = tok
+    for _ in range(args.steps):
+        lg = model.forward([t])[0]
+        t = int(np.argmax(lg))
+    e2e_s = time.perf_counter() - t0
+    h2d = (model.be.counter("h2d_bytes") - h0) / args.steps
+    d2h = (model.be.counter("d2h_bytes") - d0) / args.steps
+    barrier()
+
+    ms_dev, e2e_ms = dev_ms, e2e_s * 1e3
+    if world > 1:
+        tt = torch.tensor([ms_dev, e2e_ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        ms_dev, e2e_ms = tt.tolist()
+    value = world * args.steps / (ms_dev / 1e3)
+    e2e_value = world * args.steps / (e2e_ms / 1e3)
+    achieved = wbytes * args.steps / (ms_dev / 1e3) / 1e9  # per GPU
+    out = {"metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "int8xint4 dot, fp32 accumulate (bit-exact with the ggml CPU reference)", "data": "synthetic", "config": cfg,
+           "prefill": {"value": world * (len(prompt) - 1) / prefill_s, "unit": "tok/s", "tokens": len(prompt) - 1, "timing": "wall clock through ps_cuda_forward"},
+           "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+           "gpu_launches": int(launches),
+           "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": None, "peak_source": peak_src,
+                        "what": "decode step: algorithmic weight bytes per token / CUDA-event step time"},
+           "clocks": clk.summary(), "greedy_ids_head": [int(x) for x in ids[:8]]}
+    if rank == 0 and not args.no_cpu_baseline:
+        try:
+            cp = synth.random_prompt(shape.vocab_size, 17, seed=1234)
+            res, kind = cpu_reference_run(shape, tensors, cp, 9, cpu_threads)
+            out["cpu_baseline"] = {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": kind,
+                                   "sample": "17-token prompt + 9 greedy decode tokens of the full model (same weights)",
+                                   "prefill_tok_s": res["prefill_tok_s"]}
+            # parity spot check on the same weights: the GPU must produce the same greedy ids as the CPU reference
+            model.reset()
+            model.prefill(cp, 128)
+            gi = [int(x) for x in model.decode_greedy(int(cp[-1]), 9)]
+            out["cpu_baseline"]["greedy_ids_match"] = gi == res["ids"]
+        except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
+            out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": cpu_threads, "kind": "unavailable", "sample": str(e)[:200]}
+    model.close()
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

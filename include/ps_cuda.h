@@ -136,7 +136,8 @@ const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
 /* execution switches (0/1): "graph" = replay the decode step as a captured CUDA graph, "fused" = fused decode
  * kernels instead of one kernel per table op.  Both produce bit-identical results; they exist so tests can prove it. */
 int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
-/* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes" */
+/* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes",
+ * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call) */
 int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name);
 
 /* host-side restatement of glibc expf used by the device code; exported so CPU-only tests can pin it against libm */

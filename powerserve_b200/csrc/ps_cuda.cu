@@ -1,7 +1,7 @@
 // ps_cuda.cu — host side of libps_cuda.so: context, weight registry, workspace, KV cache, the operator table and the
 // whole-model forward behind the C ABI declared in include/ps_cuda.h.  No torch, no CPU fallback.
 #include "../../include/ps_cuda.h"
-#include "ps_kernels.cuh"
+#include "ps_decode.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -59,8 +59,14 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 0, opt_fused = 0;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1;
+    bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
+    int n_sm = 148;
+    int32_t *ctr_dev = nullptr;
+    cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
     int64_t n_launch = 0, n_graph = 0, h2d = 0, d2h = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr; // device timing of the last forward / decode call (stream events)
+    double last_ms = 0.0;
 };
 
 namespace {
@@ -184,6 +190,139 @@ int grid1d(int64_t n, int block = 256) { return (int)std::min<int64_t>((n + bloc
 } // namespace
 
 // ====================================================================================================================
+// Fused decode step (bs = 1): EMBED, 32 x {QKV, ATTN1, ATTN2, WO, GATE/UP, DOWN}, LM_HEAD, (ARGMAX) — 195 launches for
+// Llama-3.1-8B instead of ~650, chained with programmatic dependent launch and replayed as one CUDA graph.
+// ====================================================================================================================
+namespace {
+
+template <typename... KArgs, typename... Args>
+int launch_k(ps_cuda_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args... args) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
+    ctx->n_launch++;
+    if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+size_t mv_smem_bytes(int K, int R) {
+    const int nb = K / 256;
+    return (size_t)PS_MV_STAGES * R * nb * PS_Q4_K_BYTES + (size_t)K + (size_t)((nb + 3) & ~3) * 4 + (size_t)nb * 16 +
+           (size_t)R * (nb * 16 + 16) * 4 + (size_t)((R + 3) & ~3) * 4 + 2 * PS_MV_STAGES * 8;
+}
+
+int launch_matvec(ps_cuda_ctx *ctx, PsMvArgs a) {
+    const int nb = a.K / 256;
+    int R = PS_MV_COMPUTE / nb;
+    if (R > 16) R = 16;
+    if (a.epi == PS_EPI_SILU) R &= ~1;
+    if (R < (a.epi == PS_EPI_SILU ? 2 : 1)) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused matvec: K=%d too large", a.K);
+    a.R = R;
+    int tiles = 0;
+    if (a.epi == PS_EPI_SILU) {
+        tiles = (a.seg[0].n_rows + R / 2 - 1) / (R / 2);
+    } else {
+        for (int s = 0; s < a.n_seg; s++) {
+            a.seg[s].tile0 = tiles;
+            tiles += (a.seg[s].n_rows + R - 1) / R;
+        }
+    }
+    a.n_tiles = tiles;
+    const size_t smem = mv_smem_bytes(a.K, R);
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_matvec_q4k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr[ctx->device] = true;
+    }
+    if (smem > 220 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused matvec: %zu bytes of shared memory needed", smem);
+    const int grid = std::min(tiles, ctx->n_sm);
+    return launch_k(ctx, ps_k_matvec_q4k_tma, dim3(grid), dim3(PS_MV_THREADS), smem, a);
+}
+
+// one decode step on the token in tokens_dev[0] at position pos_dev[0]; `pick`: run the greedy pick + bookkeeping
+int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
+    const float kq_scale = 1.0f / sqrtf((float)hs);
+    int rc;
+    if ((rc = launch_k(ctx, ps_k_embed_dev, dim3(std::max(1, dim / 256)), dim3(256), 0, ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev))) return rc;
+    for (int L = 0; L < d.n_layers; L++) {
+        const LayerDev &ld = ctx->layers[L];
+        PsMvArgs a{};
+        a.n_seg = 3;
+        a.seg[0] = {ld.wq, ctx->q, d.qkv_bias ? ld.q_bias : nullptr, qdim, 0};
+        a.seg[1] = {ld.wk, ctx->k, d.qkv_bias ? ld.k_bias : nullptr, kvd, 0};
+        a.seg[2] = {ld.wv, ctx->v, d.qkv_bias ? ld.v_bias : nullptr, kvd, 0};
+        a.K = dim; a.x = ctx->x; a.norm_w = ld.attn_norm; a.eps = d.norm_eps; a.epi = PS_EPI_STORE;
+        if ((rc = launch_matvec(ctx, a))) return rc;
+        if ((rc = launch_k(ctx, ps_k_attn1, dim3((unsigned)((d.n_ctx + 31) / 32), (unsigned)nkv), dim3(128), 0, ctx->kq, ctx->kc[L], ctx->vct[L],
+                           (const float *)ctx->q, (const float *)ctx->k, (const float *)ctx->v, (const int32_t *)ctx->pos_dev,
+                           (const float *)ctx->rope_table, hs, nh, nkv, d.n_ctx, d.rope_type & 2, kq_scale))) return rc;
+        const size_t a2smem = (size_t)(nh / nkv) * (size_t)((d.n_ctx + 31) & ~31) * 4;
+        if ((rc = launch_k(ctx, ps_k_attn2, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
+                           (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, nh, nkv, d.n_ctx))) return rc;
+        PsMvArgs o{};
+        o.n_seg = 1; o.seg[0] = {ld.wo, ctx->x, nullptr, dim, 0};
+        o.K = qdim; o.x = ctx->att; o.norm_w = nullptr; o.residual = ctx->x; o.epi = PS_EPI_RESIDUAL;
+        if ((rc = launch_matvec(ctx, o))) return rc;
+        PsMvArgs gu{};
+        gu.n_seg = 2; gu.seg[0] = {ld.wgate, ctx->g, nullptr, ffn, 0}; gu.seg[1] = {ld.wup, nullptr, nullptr, ffn, 0};
+        gu.K = dim; gu.x = ctx->x; gu.norm_w = ld.ffn_norm; gu.eps = d.norm_eps; gu.epi = PS_EPI_SILU;
+        if ((rc = launch_matvec(ctx, gu))) return rc;
+        PsMvArgs dn{};
+        dn.n_seg = 1; dn.seg[0] = {ld.wdown, ctx->x, nullptr, dim, 0};
+        dn.K = ffn; dn.x = ctx->g; dn.norm_w = nullptr; dn.residual = ctx->x; dn.epi = PS_EPI_RESIDUAL;
+        if ((rc = launch_matvec(ctx, dn))) return rc;
+    }
+    if (lm_head) {
+        PsMvArgs lm{};
+        lm.n_seg = 1; lm.seg[0] = {ctx->w_out, ctx->logits, nullptr, d.vocab_size, 0};
+        lm.K = dim; lm.x = ctx->x; lm.norm_w = ctx->w_out_norm; lm.eps = d.norm_eps; lm.epi = PS_EPI_STORE;
+        if ((rc = launch_matvec(ctx, lm))) return rc;
+        if (pick) {
+            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(1024), 0, (const float *)ctx->logits, (int64_t)d.vocab_size, ctx->ids_dev,
+                               ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev))) return rc;
+        }
+    }
+    return 0;
+}
+
+// capture one step into a graph (lazily), then replay it
+int run_step(ps_cuda_ctx *ctx, bool pick) {
+    if (!ctx->opt_graph) return decode_step_fused(ctx, true, pick);
+    cudaGraphExec_t &ge = pick ? ctx->g_step : ctx->g_fwd;
+    if (!ge) {
+        cudaGraph_t graph = nullptr;
+        const int64_t n0 = ctx->n_launch;
+        PS_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+        int rc = decode_step_fused(ctx, true, pick);
+        cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        ctx->n_launch = n0; // capture enqueued nothing
+        if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+        if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+        e = cudaGraphInstantiate(&ge, graph, 0);
+        cudaGraphDestroy(graph);
+        if (e != cudaSuccess) { ge = nullptr; return fail(ctx, PS_CUDA_ERR_CUDA, "graph instantiate failed: %s", cudaGetErrorString(e)); }
+    }
+    PS_CK(cudaGraphLaunch(ge, ctx->stream));
+    ctx->n_graph++;
+    ctx->n_launch += 1 + 6 * ctx->d.n_layers + 1 + (pick ? 1 : 0); // kernels inside the replayed graph
+    return 0;
+}
+
+} // namespace
+
+
+// ====================================================================================================================
 extern "C" {
 
 int ps_cuda_abi_version(void) { return PS_CUDA_ABI_VERSION; }
@@ -253,6 +392,8 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->tokens_dev, 4 * B);
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
+    PS_AL(ctx->ctr_dev, 16);
+    { int v = 148; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) ctx->n_sm = v; }
     ctx->kc.resize(d.n_layers);
     ctx->vct.resize(d.n_layers);
     for (int L = 0; L < d.n_layers; L++) {
@@ -270,6 +411,8 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_CKC(cudaMallocHost(&ctx->h_tokens, 4 * B));
     PS_CKC(cudaMallocHost(&ctx->h_pos, 4 * B));
     PS_CKC(cudaMallocHost(&ctx->h_ids, 4 * 8192));
+    PS_CKC(cudaEventCreate(&ctx->ev0));
+    PS_CKC(cudaEventCreate(&ctx->ev1));
     PS_CKC(cudaStreamSynchronize(ctx->stream));
 #undef PS_CKC
 #undef PS_AL
@@ -286,6 +429,10 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_pos) cudaFreeHost(ctx->h_pos);
     if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+    if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
+    if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
+    if (ctx->ev0) cudaEventDestroy(ctx->ev0);
+    if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
     delete ctx;
 }
@@ -534,6 +681,13 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
             return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "layer %d mixes K-quant and 32-block weights on one input", L);
     }
 #undef REG
+    ctx->fused_ok = (ctx->t_embd == 12 && ctx->t_out == 12);
+    for (const LayerDev &ld : ctx->layers)
+        if (ld.tq != 12 || ld.tk != 12 || ld.tv != 12 || ld.to != 12 || ld.tgate != 12 || ld.tup != 12 || ld.tdown != 12) ctx->fused_ok = false;
+    if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 128 || d.ffn_dim / 256 > 128 || d.n_heads / d.n_kv_heads > 8)
+        ctx->fused_ok = false;
+    if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
+    if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
     ctx->bound = true;
     return 0;
 }
@@ -591,6 +745,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
     return 0;
 }
 
+
 static int check_forward_args(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs) {
     if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: no model bound");
     if (bs <= 0 || bs > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: batch %d outside [1,%d]", bs, ctx->d.max_batch);
@@ -614,7 +769,15 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
     PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += (int64_t)bs * 8;
-    if ((rc = forward_ops(ctx, bs, lm_head, pos[0]))) return rc;
+    PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
+        if (lm_head) rc = run_step(ctx, false);
+        else rc = decode_step_fused(ctx, false, false);
+    } else {
+        rc = forward_ops(ctx, bs, lm_head, pos[0]);
+    }
+    if (rc) return rc;
+    PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     if (lm_head) {
         const size_t bytes = (size_t)bs * ctx->d.vocab_size * 4;
         if (bytes > ctx->h_logits_cap) {
@@ -631,6 +794,7 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     } else {
         PS_CK(cudaStreamSynchronize(ctx->stream));
     }
+    { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     ctx->position = pos[0] + bs; // m_kv->advance(batch_size), llama_model.cpp:109
     return 0;
 }
@@ -646,6 +810,28 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     ctx->h_tokens[0] = first_token;
     PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += 4;
+    if (ctx->opt_fused && ctx->fused_ok) {
+        int32_t *slot = &ctx->h_ids[4096];
+        slot[0] = ctx->position;
+        slot[1] = 0;
+        PS_CK(cudaMemcpyAsync(ctx->pos_dev, &slot[0], 4, cudaMemcpyHostToDevice, ctx->stream));
+        PS_CK(cudaMemcpyAsync(ctx->ctr_dev, &slot[1], 4, cudaMemcpyHostToDevice, ctx->stream));
+        ctx->h2d += 8;
+        PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+        for (int s = 0; s < n_steps; s++) {
+            int rc = run_step(ctx, true);
+            if (rc) return rc;
+        }
+        PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+        PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        PS_CK(cudaStreamSynchronize(ctx->stream));
+        { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
+        memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
+        ctx->d2h += (int64_t)n_steps * 4;
+        ctx->position += n_steps;
+        return 0;
+    }
+    PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     for (int s = 0; s < n_steps; s++) {
         const int pos = ctx->position + s;
         int32_t *slot = &ctx->h_ids[4096 + s]; // one pinned slot per step: the async copies never race with the host writes
@@ -657,8 +843,10 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits, ctx->d.vocab_size, ctx->ids_dev + s, ctx->tokens_dev);
         PS_LAUNCH_CK();
     }
+    PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
     PS_CK(cudaStreamSynchronize(ctx->stream));
+    { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
     ctx->d2h += (int64_t)n_steps * 4;
     ctx->position += n_steps;
@@ -668,8 +856,11 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
 const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx) { return ctx->logits; }
 
 int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
+    if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
+    if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
+    else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else return fail(ctx, PS_CUDA_ERR_INVALID, "unknown option %s", name);
     return 0;
 }
@@ -679,6 +870,7 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "graph_replays")) return ctx->n_graph;
     if (!strcmp(name, "h2d_bytes")) return ctx->h2d;
     if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
+    if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6); // CUDA-event time of the last forward / decode
     return -1;
 }
 

@@ -60,6 +60,9 @@ PRESETS: Dict[str, ModelShape] = {
     "tiny-llama-hs128": ModelShape("tiny-llama-hs128", "llama", 512, 1024, 2, 4, 2, 128, 768, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=384),
     "tiny-qwen2": ModelShape("tiny-qwen2", "qwen2", 256, 608, 2, 4, 2, 64, 512, True, 2, 1e6, 1e-6, GGML_Q4_0, n_ctx=256, qkv_bias=True),
     "tiny-q8": ModelShape("tiny-q8", "llama", 256, 512, 2, 4, 4, 64, 512, False, 0, 1e4, 1e-5, GGML_Q8_0, n_ctx=256),
+    # real per-layer shapes of the BASELINE models with few layers / small vocab (exercise nb = 8/32 and 16/56 paths)
+    "slice-1b": ModelShape("slice-1b", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),
+    "slice-8b": ModelShape("slice-8b", "llama", 4096, 14336, 1, 32, 8, 128, 2048, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),
     "tiny-mixed": ModelShape("tiny-mixed", "llama", 512, 1024, 2, 8, 4, 64, 768, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256,
                              output_type=GGML_Q6_K),
 }
@@ -77,38 +80,37 @@ def random_blocks(rng: np.random.Generator, ggml_type: int, n_rows: int, k: int,
     blk, nbytes = gguf.TYPE_INFO[ggml_type]
     assert k % blk == 0, (k, blk)
     nb = n_rows * (k // blk)
-    out = np.empty((nb, nbytes), dtype=np.uint8)
-    jitter = rng.uniform(0.6, 1.4, size=nb).astype(np.float32)
+    # One pass of raw random bytes fills the whole tensor (fast path of the bit generator); the few structured
+    # fields (fp16 scales, 6-bit sub-block scales) are then overwritten using bit tricks on those same bytes.
+    out = rng.integers(0, 256, size=(nb, nbytes), dtype=np.uint8)
+    jitter = 0.6 + 0.8 * (rng.integers(0, 256, size=nb, dtype=np.uint8).astype(np.float32) / 255.0)
     if ggml_type == GGML_Q4_0:
         # w = (q - 8) * d ; q uniform 0..15 -> std(q-8) ~ 4.63
         out[:, 0:2] = _f16_bytes(std / 4.63 * jitter)
-        out[:, 2:] = rng.integers(0, 256, size=(nb, 16), dtype=np.uint8)
     elif ggml_type == GGML_Q8_0:
-        # w = q * d ; q uniform -127..127 -> std ~ 73.3
-        out[:, 0:2] = _f16_bytes(std / 73.3 * jitter)
-        out[:, 2:] = rng.integers(-127, 128, size=(nb, 32), dtype=np.int8).view(np.uint8)
+        # w = q * d ; q uniform int8 (-128 remapped to -127, the quantiser never emits -128) -> std ~ 73.6
+        out[:, 0:2] = _f16_bytes(std / 73.6 * jitter)
+        q = out[:, 2:]
+        q[q == 0x80] = 0x81
     elif ggml_type == GGML_Q4_K:
-        # w = d*sc_j*q - dmin*m_j.  Draw sc_j in [16,63], m_j near 7.5*sc_j*(d/dmin) with dmin = 8 d so that every
-        # sub-block is (nearly) zero-mean; std(w) ~ d * sqrt(E[sc^2]) * 4.61 ~ 193 d.
-        d = std / 193.0 * jitter
+        # w = d*sc_j*q - dmin*m_j.  sc_j in [16,62], m_j ~ 7.5*sc_j*(d/dmin) with dmin = 8 d so that every sub-block is
+        # (nearly) zero-mean; std(w) ~ d * sqrt(E[sc^2]) * 4.61 ~ 190 d.
+        d = std / 190.0 * jitter
+        r = out[:, 4:12].copy()                                   # 8 random bytes per block drive the 8 (sc, m) pairs
+        sc = (16 + (r & 31) + ((r >> 5) & 7) * 2).astype(np.uint8)             # 16 .. 61
+        m = np.minimum(63, ((sc.astype(np.uint16) * 15 + 8) >> 4) + ((r >> 3) & 3)).astype(np.uint8) - 1
         out[:, 0:2] = _f16_bytes(d)
         out[:, 2:4] = _f16_bytes(8.0 * d)
-        sc = rng.integers(16, 64, size=(nb, 8), dtype=np.uint8)
-        m = np.clip(np.rint(sc * (7.5 / 8.0)) + rng.integers(-2, 3, size=(nb, 8)), 0, 63).astype(np.uint8)
-        scales = np.empty((nb, 12), dtype=np.uint8)
         # inverse of get_scale_min_k4 (ggml-quants.c:1912-1919)
-        scales[:, 0:4] = (sc[:, 0:4] & 63) | ((sc[:, 4:8] >> 4) << 6)
-        scales[:, 4:8] = (m[:, 0:4] & 63) | ((m[:, 4:8] >> 4) << 6)
-        scales[:, 8:12] = (sc[:, 4:8] & 0xF) | ((m[:, 4:8] & 0xF) << 4)
-        out[:, 4:16] = scales
-        out[:, 16:] = rng.integers(0, 256, size=(nb, 128), dtype=np.uint8)
+        out[:, 4:8] = (sc[:, 0:4] & 63) | ((sc[:, 4:8] >> 4) << 6)
+        out[:, 8:12] = (m[:, 0:4] & 63) | ((m[:, 4:8] >> 4) << 6)
+        out[:, 12:16] = (sc[:, 4:8] & 0xF) | ((m[:, 4:8] & 0xF) << 4)
     elif ggml_type == GGML_Q6_K:
-        # w = d * sc_j * (q - 32), q 6-bit uniform -> std(q-32) ~ 18.5 ; sc int8 in [-90, 90] \ small
-        out[:, 0:192] = rng.integers(0, 256, size=(nb, 192), dtype=np.uint8)   # ql[128] + qh[64]
-        sc = rng.integers(24, 100, size=(nb, 16)).astype(np.int8)
-        sc *= rng.choice(np.array([-1, 1], dtype=np.int8), size=(nb, 16))
-        out[:, 192:208] = sc.view(np.uint8)
-        out[:, 208:210] = _f16_bytes(std / (18.5 * 66.0) * jitter)
+        # w = d * sc_j * (q - 32), q 6-bit uniform -> std(q-32) ~ 18.5 ; |sc| in [24, 87], random sign
+        r = out[:, 192:208]
+        mag = (24 + (r & 63)).astype(np.int8)
+        out[:, 192:208] = np.where(r & 0x80, -mag, mag).astype(np.int8).view(np.uint8)
+        out[:, 208:210] = _f16_bytes(std / (18.5 * 58.0) * jitter)
     else:
         raise ValueError(f"no random generator for ggml type {ggml_type}")
     return out.reshape(n_rows, (k // blk) * nbytes)
@@ -164,20 +166,28 @@ def tensor_plan(shape: ModelShape) -> List[Tuple[str, int, Tuple[int, ...], floa
     return plan
 
 
-def generate_tensors(shape: ModelShape, seed: int = 0) -> List[Tuple[str, int, Tuple[int, ...], np.ndarray]]:
-    """Materialise every tensor of `shape` (deterministic in `seed`; each tensor has its own sub-stream)."""
-    out = []
-    for idx, (name, t, shp, std) in enumerate(tensor_plan(shape)):
-        rng = np.random.default_rng([seed, idx])
-        if t == GGML_F32:
-            if name.endswith("norm.weight"):
-                data = (1.0 + 0.1 * rng.standard_normal(shp[0])).astype(np.float32)
-            else:
-                data = (std * rng.standard_normal(shp[0])).astype(np.float32)
-            out.append((name, t, shp, data.view(np.uint8)))
+def _make_tensor(shape_seed):
+    seed, idx, name, t, shp, std = shape_seed
+    rng = np.random.Generator(np.random.SFC64([seed, idx]))   # one independent stream per tensor
+    if t == GGML_F32:
+        if name.endswith("norm.weight"):
+            data = (1.0 + 0.1 * rng.standard_normal(shp[0])).astype(np.float32)
         else:
-            out.append((name, t, shp, random_blocks(rng, t, shp[1], shp[0], std).reshape(-1)))
-    return out
+            data = (std * rng.standard_normal(shp[0])).astype(np.float32)
+        return (name, t, shp, data.view(np.uint8))
+    return (name, t, shp, random_blocks(rng, t, shp[1], shp[0], std).reshape(-1))
+
+
+def generate_tensors(shape: ModelShape, seed: int = 0, workers: Optional[int] = None) -> List[Tuple[str, int, Tuple[int, ...], np.ndarray]]:
+    """Materialise every tensor of `shape`.  Deterministic in `seed` (each tensor has its own random stream, so the
+    result does not depend on `workers`); numpy releases the GIL in the generators, so threads scale."""
+    jobs = [(seed, idx, name, t, shp, std) for idx, (name, t, shp, std) in enumerate(tensor_plan(shape))]
+    workers = workers or min(32, os.cpu_count() or 1)
+    if workers <= 1 or len(jobs) < 4:
+        return [_make_tensor(j) for j in jobs]
+    from concurrent.futures import ThreadPoolExecutor
+    with ThreadPoolExecutor(workers) as ex:
+        return list(ex.map(_make_tensor, jobs))
 
 
 def write_model_dir(path: str, shape: ModelShape, seed: int = 0, model_id: Optional[str] = None) -> str:
@@ -192,4 +202,4 @@ def write_model_dir(path: str, shape: ModelShape, seed: int = 0, model_id: Optio
 
 def random_prompt(vocab_size: int, n: int, seed: int = 1234) -> np.ndarray:
     """Token ids uniform in [0, vocab) — SURVEY.md section 8(d) 'synthetic prompts'."""
-    return np.random.default_rng(seed).integers(0, vocab_size, size=n, dtype=np.int32)
+    return np.random.Generator(np.random.SFC64(seed)).integers(0, vocab_size, size=n, dtype=np.int32)
