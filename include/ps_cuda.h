@@ -140,6 +140,10 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
  * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call) */
 int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name);
 
+/* debug: with option "trace" = 1 the fused mat-vec records per-CTA globaltimer stamps (16 per CTA, 148 CTAs, ring of
+ * 256 launches); read them back here.  Not used in production. */
+int ps_cuda_read_trace(ps_cuda_ctx *ctx, long long *host, int n_launches);
+
 /* host-side restatement of glibc expf used by the device code; exported so CPU-only tests can pin it against libm */
 float ps_cuda_host_expf_ref(float x);
 float ps_cuda_host_v_expf(float x);

@@ -94,6 +94,7 @@ def load_library() -> C.CDLL:
         "ps_cuda_logits_dev": (vp, [vp]),
         "ps_cuda_set_option": (ci, [vp, C.c_char_p, ci]),
         "ps_cuda_get_counter": (i64, [vp, C.c_char_p]),
+        "ps_cuda_read_trace": (ci, [vp, C.c_void_p, ci]),
         "ps_cuda_host_expf_ref": (C.c_float, [C.c_float]),
         "ps_cuda_host_v_expf": (C.c_float, [C.c_float]),
     }

@@ -64,6 +64,8 @@ struct ps_cuda_ctx {
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
+    long long *trace_dev = nullptr; // debug: per-launch CTA timestamps of the fused matvec (option "trace")
+    int trace_launch = 0;
     int64_t n_launch = 0, n_graph = 0, h2d = 0, d2h = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; // device timing of the last forward / decode call (stream events)
     double last_ms = 0.0;
@@ -216,7 +218,7 @@ int launch_k(ps_cuda_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, si
 size_t mv_smem_bytes(int K, int R) {
     const int nb = K / 256;
     return (size_t)PS_MV_STAGES * R * nb * PS_Q4_K_BYTES + (size_t)K + (size_t)((nb + 3) & ~3) * 4 + (size_t)nb * 16 +
-           (size_t)R * (nb * 16 + 16) * 4 + (size_t)((R + 3) & ~3) * 4 + 2 * PS_MV_STAGES * 8;
+           (size_t)2 * R * (nb * 16 + 16) * 4 + (size_t)((R + 3) & ~3) * 4 + 2 * PS_MV_STAGES * 8;
 }
 
 int launch_matvec(ps_cuda_ctx *ctx, PsMvArgs a) {
@@ -236,6 +238,7 @@ int launch_matvec(ps_cuda_ctx *ctx, PsMvArgs a) {
         }
     }
     a.n_tiles = tiles;
+    a.trace = ctx->trace_dev ? ctx->trace_dev + (size_t)(ctx->trace_launch++ % 256) * 148 * 16 : nullptr;
     const size_t smem = mv_smem_bytes(a.K, R);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
@@ -861,6 +864,14 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "trace")) {
+        if (value && !ctx->trace_dev) {
+            int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * 256 * 148 * 16);
+            if (rc) return rc;
+            PS_CK(cudaMemset(ctx->trace_dev, 0, sizeof(long long) * 256 * 148 * 16));
+        }
+        ctx->trace_launch = 0;
+    }
     else return fail(ctx, PS_CUDA_ERR_INVALID, "unknown option %s", name);
     return 0;
 }
@@ -872,6 +883,13 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
     if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6); // CUDA-event time of the last forward / decode
     return -1;
+}
+
+int ps_cuda_read_trace(ps_cuda_ctx *ctx, long long *host, int n_launches) {
+    if (!ctx->trace_dev) return fail(ctx, PS_CUDA_ERR_INVALID, "trace is off");
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    PS_CK(cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * (size_t)n_launches * 148 * 16, cudaMemcpyDeviceToHost));
+    return 0;
 }
 
 float ps_cuda_host_expf_ref(float x) { return ps_expf_glibc(x); }

@@ -42,6 +42,7 @@ struct PsMvArgs {
     float eps;
     const float *residual; // PS_EPI_RESIDUAL: dst[n] = residual[n] + r
     int epi;
+    long long *trace;      // optional per-CTA timestamps (globaltimer ns), 16 slots per CTA; nullptr in production
 };
 
 // ---------------------------------------------------------------------------------------------------- PTX helpers
@@ -76,6 +77,15 @@ PS_D void ps_fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cl
 PS_D void ps_grid_dep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 PS_D void ps_grid_dep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 PS_D void ps_bar_sync(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
+PS_D long long ps_globaltimer() {
+    long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+#define PS_TRACE(slot)                                                                   \
+    do {                                                                                 \
+        if (a.trace && (threadIdx.x & 31) == 0 && (threadIdx.x >> 5) == 0) a.trace[blockIdx.x * 16 + (slot)] = ps_globaltimer(); \
+    } while (0)
 PS_D int ps_dp4a_us(uint32_t a, int b, int c) { // unsigned bytes of a  x  signed bytes of b
     int d;
     asm("dp4a.u32.s32 %0, %1, %2, %3;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
@@ -142,7 +152,7 @@ PS_D void ps_quant_block_q8k_warp(const float e[8], int lane, uint32_t *qs_words
 //   [stages]   PS_MV_STAGES x stage_bytes, stage_bytes = R * nb * 144 (PS_EPI_SILU: R/2 gate rows then R/2 up rows)
 //   [q8]       K                                   quantised activation, natural word order
 //   [yd]       nb x 4, [bsp] nb x 16
-//   [chain]    R x (nb*16 + 16) x 4                per block: S[8], P[4], d, dmin, pad x2
+//   [chain]    2 x R x (nb*16 + 16) x 4            per block: S[8], P[4], d, dmin, pad x2 (double-buffered hand-off)
 //   [res]      R x 4
 //   [bars]     2 x PS_MV_STAGES x 8
 __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const PsMvArgs a) {
@@ -157,7 +167,7 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
     uint32_t *s_bsp = reinterpret_cast<uint32_t *>(s_yd + ((nb + 3) & ~3));
     const int chain_row = nb * 16 + 16;
     uint32_t *s_chain = s_bsp + nb * 4;                                       // 16-byte aligned: every term above is
-    float *s_res = reinterpret_cast<float *>(s_chain + (size_t)R * chain_row);
+    float *s_res = reinterpret_cast<float *>(s_chain + (size_t)2 * R * chain_row);             // two hand-off buffers
     uint64_t *s_full = reinterpret_cast<uint64_t *>(s_res + ((R + 3) & ~3));
     uint64_t *s_empty = s_full + PS_MV_STAGES;
     __shared__ double sh_red[32];
@@ -199,6 +209,7 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
         }
     };
 
+    PS_TRACE(0);
     if (tid == 0) {
         for (int s = 0; s < PS_MV_STAGES; s++) {
             ps_mbar_init(&s_full[s], 1);
@@ -223,7 +234,9 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
     }
 
     // ===== compute warps
-    ps_grid_dep_wait();        // activations come from the previous kernel in the stream / graph
+    PS_TRACE(1);
+    ps_grid_dep_wait();
+    PS_TRACE(2);        // activations come from the previous kernel in the stream / graph
     ps_grid_dep_launch();      // let the next kernel's CTAs start their weight prefetch as SMs free up
     // ---- prologue: (RMSNorm) + Q8_K quantisation of the activation vector, redundantly per CTA (K <= 14336 floats)
     float nscale = 1.f;
@@ -256,6 +269,7 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
     }
     ps_bar_sync(1, PS_MV_COMPUTE);
 
+    PS_TRACE(3);
     // ---- this thread's fixed (row-in-tile, block) slot and its activation block in registers
     const int r_slot = tid / nb, i_blk = tid % nb;
     const bool active = tid < R * nb;
@@ -274,13 +288,63 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
         for (int k = 0; k < 4; k++) bsp[k] = s_bsp[i_blk * 4 + k];
     }
 
+    // chain + epilogue of tile #kk of this CTA (reads hand-off buffer kk & 1).  16 lanes per chain group: roles 0-7 are
+    // the acc lanes, 8-11 the acc_m lanes.  STORE / RESIDUAL: group c owns row slot c.  SILU: group c owns the gate slot c
+    // and the up slot half + c, so the group leader ends up holding both values and no second barrier is needed.
+    auto chain_tile = [&](int kk) {
+        const int tile = (int)blockIdx.x + kk * (int)gridDim.x;
+        int seg, row0, nrows;
+        tile_info(tile, seg, row0, nrows);
+        const int grp = tid >> 4, role = tid & 15;
+        const uint32_t *cbuf = s_chain + (size_t)(kk & 1) * R * chain_row;
+        const int base = lane & 16;
+        const bool g_ok = grp < nrows;
+        float res[2] = {0.f, 0.f};
+        const int nchains = (a.epi == PS_EPI_SILU) ? 2 : 1;
+        for (int c = 0; c < nchains; c++) {
+            float acc = 0.f;
+            if (g_ok && role < 12) {
+                const uint32_t *cb = cbuf + (size_t)(grp + c * half) * chain_row;
+                const int dsel = (role < 8) ? 12 : 13;
+                int i = 0;
+                for (; i + 8 <= nb; i += 8) {
+                    int v[8];
+                    float dd[8];
+#pragma unroll
+                    for (int u = 0; u < 8; u++) { v[u] = (int)cb[(i + u) * 16 + role]; dd[u] = __uint_as_float(cb[(i + u) * 16 + dsel]); }
+#pragma unroll
+                    for (int u = 0; u < 8; u++) acc = __fmaf_rn(dd[u], __int2float_rn(v[u]), acc);
+                }
+                for (; i < nb; i++) acc = __fmaf_rn(__uint_as_float(cb[i * 16 + dsel]), __int2float_rn((int)cb[i * 16 + role]), acc);
+            }
+            float x[12];
+#pragma unroll
+            for (int t = 0; t < 12; t++) x[t] = __shfl_sync(PS_FULL, acc, base + t);
+            const float r0 = __fadd_rn(x[4], x[0]), r1 = __fadd_rn(x[5], x[1]), r2 = __fadd_rn(x[6], x[2]), r3 = __fadd_rn(x[7], x[3]);
+            const float hsum = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+            res[c] = __fadd_rn(hsum, __fadd_rn(__fadd_rn(x[8], x[10]), __fadd_rn(x[9], x[11])));
+        }
+        if (g_ok && role == 0) {
+            const int n = row0 + grp;
+            if (a.epi == PS_EPI_SILU) {
+                a.seg[0].dst[n] = ps_silu_mul(res[0], res[1]);
+            } else {
+                float r = res[0];
+                if (a.seg[seg].bias) r = __fadd_rn(r, a.seg[seg].bias[n]);
+                if (a.epi == PS_EPI_RESIDUAL) r = __fadd_rn(a.residual[n], r);
+                a.seg[seg].dst[n] = r;
+            }
+        }
+    };
+
     for (int k = 0; k < my_tiles; k++) {
         const int tile = (int)blockIdx.x + k * (int)gridDim.x;
         const int st = k % PS_MV_STAGES;
         int seg, row0, nrows;
         tile_info(tile, seg, row0, nrows);
-        const int rows_here = (a.epi == PS_EPI_SILU) ? half + nrows : nrows; // slots [0,nrows) and [half, half+nrows)
+        if (k < 4) PS_TRACE(4 + 2 * k);
         ps_mbar_wait(&s_full[st], (k / PS_MV_STAGES) & 1);
+        if (k < 4) PS_TRACE(5 + 2 * k);
         // ---------------- integer phase: one thread, one block
         const bool row_ok = active && ((a.epi == PS_EPI_SILU) ? (r_slot < nrows || (r_slot >= half && r_slot < half + nrows)) : (r_slot < nrows));
         if (row_ok) {
@@ -310,14 +374,12 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
                     }
                 }
             }
-            uint32_t *cb = s_chain + (size_t)r_slot * chain_row + i_blk * 16;
-            uint4 o0, o1, o2;
+            uint4 o0, o1, o2, o3;
             o0.x = (uint32_t)(S[0] + (Sh[0] >> 4)); o0.y = (uint32_t)(S[1] + (Sh[1] >> 4));
             o0.z = (uint32_t)(S[2] + (Sh[2] >> 4)); o0.w = (uint32_t)(S[3] + (Sh[3] >> 4));
             o1.x = (uint32_t)(S[4] + (Sh[4] >> 4)); o1.y = (uint32_t)(S[5] + (Sh[5] >> 4));
             o1.z = (uint32_t)(S[6] + (Sh[6] >> 4)); o1.w = (uint32_t)(S[7] + (Sh[7] >> 4));
-            // prod lanes: m_{2k} s_{2k} + m_{2k+1} s_{2k+1}
-            int P[4];
+            int P[4]; // prod lanes: m_{2k} s_{2k} + m_{2k+1} s_{2k+1}
 #pragma unroll
             for (int kk = 0; kk < 4; kk++) {
                 const uint32_t mw = (kk < 2) ? mA : mB;
@@ -326,55 +388,21 @@ __global__ void __launch_bounds__(PS_MV_THREADS, 1) ps_k_matvec_q4k_tma(const Ps
             }
             o2.x = (uint32_t)P[0]; o2.y = (uint32_t)P[1]; o2.z = (uint32_t)P[2]; o2.w = (uint32_t)P[3];
             const float xd = ps_half_bits_to_float(h.x & 0xffffu), xmin = ps_half_bits_to_float(h.x >> 16);
-            uint4 o3;
             o3.x = __float_as_uint(__fmul_rn(yd, xd));
             o3.y = __float_as_uint(__fmul_rn(-yd, xmin));
             o3.z = 0; o3.w = 0;
-            uint4 *cbv = reinterpret_cast<uint4 *>(cb);
+            uint4 *cbv = reinterpret_cast<uint4 *>(s_chain + (size_t)(k & 1) * R * chain_row + (size_t)r_slot * chain_row + i_blk * 16);
             cbv[0] = o0; cbv[1] = o1; cbv[2] = o2; cbv[3] = o3;
         }
         __syncwarp();
         if (lane == 0) ps_mbar_arrive(&s_empty[st]); // the weight bytes of this stage are consumed
+        // the fp32 chains of the PREVIOUS tile run here, interleaved (across warps) with this tile's integer work
+        if (k > 0) chain_tile(k - 1);
         ps_bar_sync(1, PS_MV_COMPUTE);
-        // ---------------- chain phase: 16 threads per row slot (8 acc lanes, 4 acc_m lanes, 4 idle)
-        {
-            const int crow = tid >> 4, role = tid & 15;
-            const bool c_ok = (a.epi == PS_EPI_SILU) ? (crow < nrows || (crow >= half && crow < half + nrows)) : (crow < nrows);
-            float acc = 0.f;
-            if (crow < R && c_ok && role < 12) {
-                const uint32_t *cb = s_chain + (size_t)crow * chain_row;
-                const int dsel = (role < 8) ? 12 : 13;
-                for (int i = 0; i < nb; i++) {
-                    const int v = (int)cb[i * 16 + role];
-                    const float dd = __uint_as_float(cb[i * 16 + dsel]);
-                    acc = __fmaf_rn(dd, __int2float_rn(v), acc);
-                }
-            }
-            // hsum_float_8(acc) + ((m0+m2)+(m1+m3)) within the 16-lane group
-            const int base = lane & 16;
-            float x[12];
-#pragma unroll
-            for (int t = 0; t < 12; t++) x[t] = __shfl_sync(PS_FULL, acc, base + t);
-            const float r0 = __fadd_rn(x[4], x[0]), r1 = __fadd_rn(x[5], x[1]), r2 = __fadd_rn(x[6], x[2]), r3 = __fadd_rn(x[7], x[3]);
-            const float hs = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-            const float ms = __fadd_rn(__fadd_rn(x[8], x[10]), __fadd_rn(x[9], x[11]));
-            if (role == 0 && crow < R) s_res[crow] = __fadd_rn(hs, ms);
-        }
-        ps_bar_sync(1, PS_MV_COMPUTE);
-        // ---------------- epilogue
-        if (tid < nrows) {
-            const int n = row0 + tid;
-            if (a.epi == PS_EPI_SILU) {
-                a.seg[0].dst[n] = ps_silu_mul(s_res[tid], s_res[half + tid]);
-            } else {
-                float r = s_res[tid];
-                if (a.seg[seg].bias) r = __fadd_rn(r, a.seg[seg].bias[n]);
-                if (a.epi == PS_EPI_RESIDUAL) r = __fadd_rn(a.residual[n], r);
-                a.seg[seg].dst[n] = r;
-            }
-        }
-        (void)rows_here;
     }
+    PS_TRACE(12);
+    if (my_tiles > 0) chain_tile(my_tiles - 1);
+    PS_TRACE(13);
 }
 
 // ====================================================================================================================
@@ -420,21 +448,30 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, float 
         }
     }
     const int steps = hs / 32;
+    // all (<= 8) K rows of this warp are requested before any is used: the loop is latency- not bandwidth-bound
+    float kv[8][8];
+    const int64_t j0 = (int64_t)chunk * 32 + warp * 8;
+#pragma unroll
     for (int t = 0; t < 8; t++) {
-        const int64_t j = (int64_t)chunk * 32 + warp * 8 + t;
-        if (j >= n_kv) break;
-        float kv[8];
-        if (j == pos) {
-            for (int s = 0; s < steps; s++) kv[s] = s_k[32 * s + lane];
-        } else {
-            const float *krow = kc + j * (int64_t)(hs * n_kv_heads) + g * hs;
-            for (int s = 0; s < steps; s++) kv[s] = krow[32 * s + lane];
+        const int64_t j = j0 + t;
+#pragma unroll
+        for (int s = 0; s < 8; s++) {
+            kv[t][s] = 0.f;
+            if (s < steps && j < n_kv) kv[t][s] = (j == pos) ? s_k[32 * s + lane] : kc[j * (int64_t)(hs * n_kv_heads) + g * hs + 32 * s + lane];
         }
-        for (int hh = 0; hh < r2; hh++) {
-            float sum = 0.f;
-            for (int s = 0; s < steps; s++) sum = __fmaf_rn(kv[s], s_q[hh][32 * s + lane], sum);
-            sum = ps_f32x8_reduce(sum);
-            if (lane == 0) sc[(int64_t)(g * r2 + hh) * n_ctx + j] = __fadd_rn(__fmul_rn(sum, scale), 0.0f);
+    }
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int64_t j = j0 + t;
+        if (j < n_kv) {
+            for (int hh = 0; hh < r2; hh++) {
+                float sum = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < steps) sum = __fmaf_rn(kv[t][s], s_q[hh][32 * s + lane], sum);
+                sum = ps_f32x8_reduce(sum);
+                if (lane == 0) sc[(int64_t)(g * r2 + hh) * n_ctx + j] = __fadd_rn(__fmul_rn(sum, scale), 0.0f);
+            }
         }
     }
 }
@@ -498,7 +535,18 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
     float sum[8];
 #pragma unroll
     for (int hh = 0; hh < 8; hh++) sum[hh] = 0.f;
-    for (int64_t s0 = 0; s0 < np; s0 += 32) {
+    int64_t s0 = 0;
+    for (; s0 + 256 <= np; s0 += 256) { // 8 independent V loads in flight per lane; the FMA chains stay in position order
+        float vv[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) vv[u] = vrow[s0 + 32 * u + lane];
+#pragma unroll
+        for (int u = 0; u < 8; u++)
+#pragma unroll
+            for (int hh = 0; hh < 8; hh++)
+                if (hh < r2) sum[hh] = __fmaf_rn(vv[u], s_p[hh * stride + s0 + 32 * u + lane], sum[hh]);
+    }
+    for (; s0 < np; s0 += 32) {
         const float vv = vrow[s0 + lane];
 #pragma unroll
         for (int hh = 0; hh < 8; hh++)
