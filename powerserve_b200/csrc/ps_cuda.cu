@@ -2,6 +2,7 @@
 // whole-model forward behind the C ABI declared in include/ps_cuda.h.  No torch, no CPU fallback.
 #include "../../include/ps_cuda.h"
 #include "ps_decode.cuh"
+#include "ps_rw.cuh"
 
 #include <cstdarg>
 #include <cstdio>
@@ -10,6 +11,8 @@
 #include <string>
 #include <unordered_map>
 #include <vector>
+
+#define PS_TL_SLOTS 512
 
 namespace {
 
@@ -25,6 +28,8 @@ struct LayerDev {
     const float *attn_norm, *ffn_norm, *q_bias, *k_bias, *v_bias;
     const uint8_t *wq, *wk, *wv, *wo, *wgate, *wup, *wdown;
     int tq, tk, tv, to, tgate, tup, tdown;
+    // octet-interleaved copies for the row-walker mat-vec (ps_rw.cuh): q|k|v rows, o, gate|up slots, down
+    uint8_t *rw_qkv = nullptr, *rw_o = nullptr, *rw_gu = nullptr, *rw_down = nullptr;
 };
 
 } // namespace
@@ -60,11 +65,12 @@ struct ps_cuda_ctx {
     size_t h_logits_cap = 0;
     // options / counters
     int opt_graph = 1, opt_fused = 1, opt_pdl = 1;
+    uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
-    long long *trace_dev = nullptr; // debug: per-launch CTA timestamps of the fused matvec (option "trace")
+    long long *trace_dev = nullptr; // debug: per-launch timeline of the fused decode step (option "trace"), PS_TL_SLOTS x 4
     int trace_launch = 0;
     int64_t n_launch = 0, n_graph = 0, h2d = 0, d2h = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr; // device timing of the last forward / decode call (stream events)
@@ -215,85 +221,104 @@ int launch_k(ps_cuda_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, si
     return 0;
 }
 
-size_t mv_smem_bytes(int K, int R) {
-    const int nb = K / 256;
-    return (size_t)PS_MV_STAGES * R * nb * PS_Q4_K_BYTES + (size_t)K + (size_t)((nb + 3) & ~3) * 4 + (size_t)nb * 16 +
-           (size_t)2 * R * (nb * 16 + 16) * 4 + (size_t)((R + 3) & ~3) * 4 + 2 * PS_MV_STAGES * 8;
+// timeline slot of the next fused-path launch (nullptr when option "trace" is off)
+long long *tl_slot(ps_cuda_ctx *ctx) {
+    if (!ctx->trace_dev) return nullptr;
+    return ctx->trace_dev + (size_t)(ctx->trace_launch++ % PS_TL_SLOTS) * 4;
 }
 
-int launch_matvec(ps_cuda_ctx *ctx, PsMvArgs a) {
-    const int nb = a.K / 256;
-    int R = PS_MV_COMPUTE / nb;
-    if (R > 16) R = 16;
-    if (a.epi == PS_EPI_SILU) R &= ~1;
-    if (R < (a.epi == PS_EPI_SILU ? 2 : 1)) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused matvec: K=%d too large", a.K);
-    a.R = R;
-    int tiles = 0;
-    if (a.epi == PS_EPI_SILU) {
-        tiles = (a.seg[0].n_rows + R / 2 - 1) / (R / 2);
-    } else {
-        for (int s = 0; s < a.n_seg; s++) {
-            a.seg[s].tile0 = tiles;
-            tiles += (a.seg[s].n_rows + R - 1) / R;
-        }
-    }
-    a.n_tiles = tiles;
-    a.trace = ctx->trace_dev ? ctx->trace_dev + (size_t)(ctx->trace_launch++ % 256) * 148 * 16 : nullptr;
-    const size_t smem = mv_smem_bytes(a.K, R);
+// ---- row-walker mat-vec (ps_rw.cuh)
+int rw_repack(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int64_t n_rows, int64_t K, int64_t oct0, int slot, int n_slots) {
+    const int64_t chunks = ((n_rows + 7) / 8) * (K / 256) * 72;
+    ps_k_rw_repack<<<(unsigned)std::min<int64_t>((chunks + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(dst, src, n_rows, K / 256, oct0, slot, n_slots);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
+    a.tl = tl_slot(ctx);
+    const int nb = a.K / 256, rpt = (epi == PS_EPI_SILU) ? 2 : 1;
+    if (nb > 4 * PS_RW_WARPS) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: K=%d too large", a.K);
+    int kb = (rpt == 2) ? 2 : 4;
+    while (nb % kb) kb >>= 1;
+    const int grid = std::min(ctx->n_sm, a.n_oct);
+    const int per_cta = (a.n_oct + grid - 1) / grid;
+    a.kb = kb;
+    a.n_act = std::min(PS_RW_WARPS, per_cta);
+    const size_t stage = (size_t)kb * rpt * PS_RW_OCTET_BLOCK, fixed = (size_t)a.K + (size_t)nb * 32;
+    const size_t budget = 200 * 1024;
+    int ns = (int)((budget - fixed) / ((size_t)a.n_act * (stage + 8)));
+    ns = std::min(ns, PS_RW_MAX_NS);
+    if (ns < 2) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
+    a.ns = ns;
+    const size_t smem = fixed + (size_t)a.n_act * ns * (stage + 8);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
-        PS_CK(cudaFuncSetAttribute(ps_k_matvec_q4k_tma, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         PS_CK(cudaFuncSetAttribute(ps_k_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr[ctx->device] = true;
     }
-    if (smem > 220 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused matvec: %zu bytes of shared memory needed", smem);
-    const int grid = std::min(tiles, ctx->n_sm);
-    return launch_k(ctx, ps_k_matvec_q4k_tma, dim3(grid), dim3(PS_MV_THREADS), smem, a);
+    if (epi == PS_EPI_SILU) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_SILU>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
+    if (epi == PS_EPI_RESIDUAL) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_RESIDUAL>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
+    return launch_k(ctx, ps_k_rw_matvec<PS_EPI_STORE>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
+}
+
+// the four mat-vecs of a layer + lm_head on the row-walker kernel
+int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int qdim = d.n_heads * d.head_size, kvd = d.n_kv_heads * d.head_size;
+    PsRwArgs a{};
+    a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
+    a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim};
+    a.seg[1] = {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd};
+    a.seg[2] = {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, qdim + kvd, qdim + 2 * kvd};
+    a.x = ctx->x; a.norm_w = ld.attn_norm; a.eps = d.norm_eps;
+    return launch_rw(ctx, a, PS_EPI_STORE);
+}
+int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual) {
+    PsRwArgs a{};
+    a.w = w; a.n_oct = (n_rows + 7) / 8; a.K = K; a.n_seg = 1;
+    a.seg[0] = {dst, nullptr, 0, n_rows};
+    a.x = x; a.norm_w = norm_w; a.eps = ctx->d.norm_eps; a.residual = residual;
+    return launch_rw(ctx, a, residual ? PS_EPI_RESIDUAL : PS_EPI_STORE);
+}
+int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
+    const ps_cuda_model_desc &d = ctx->d;
+    PsRwArgs a{};
+    a.w = ld.rw_gu; a.n_oct = (d.ffn_dim + 7) / 8; a.K = d.dim; a.n_seg = 1;
+    a.seg[0] = {ctx->g, nullptr, 0, d.ffn_dim};
+    a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
+    return launch_rw(ctx, a, PS_EPI_SILU);
 }
 
 // one decode step on the token in tokens_dev[0] at position pos_dev[0]; `pick`: run the greedy pick + bookkeeping
 int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     const ps_cuda_model_desc &d = ctx->d;
-    const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
+    const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, qdim = nh * hs, ffn = d.ffn_dim;
     const float kq_scale = 1.0f / sqrtf((float)hs);
     int rc;
-    if ((rc = launch_k(ctx, ps_k_embed_dev, dim3(std::max(1, dim / 256)), dim3(256), 0, ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev))) return rc;
+    ctx->trace_launch = 0;
+    if ((rc = launch_k(ctx, ps_k_embed_dev, dim3(std::max(1, dim / 256)), dim3(256), 0, ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev, tl_slot(ctx)))) return rc;
     for (int L = 0; L < d.n_layers; L++) {
         const LayerDev &ld = ctx->layers[L];
-        PsMvArgs a{};
-        a.n_seg = 3;
-        a.seg[0] = {ld.wq, ctx->q, d.qkv_bias ? ld.q_bias : nullptr, qdim, 0};
-        a.seg[1] = {ld.wk, ctx->k, d.qkv_bias ? ld.k_bias : nullptr, kvd, 0};
-        a.seg[2] = {ld.wv, ctx->v, d.qkv_bias ? ld.v_bias : nullptr, kvd, 0};
-        a.K = dim; a.x = ctx->x; a.norm_w = ld.attn_norm; a.eps = d.norm_eps; a.epi = PS_EPI_STORE;
-        if ((rc = launch_matvec(ctx, a))) return rc;
+        if ((rc = rw_qkv(ctx, ld))) return rc;
         if ((rc = launch_k(ctx, ps_k_attn1, dim3((unsigned)((d.n_ctx + 31) / 32), (unsigned)nkv), dim3(128), 0, ctx->kq, ctx->kc[L], ctx->vct[L],
                            (const float *)ctx->q, (const float *)ctx->k, (const float *)ctx->v, (const int32_t *)ctx->pos_dev,
-                           (const float *)ctx->rope_table, hs, nh, nkv, d.n_ctx, d.rope_type & 2, kq_scale))) return rc;
+                           (const float *)ctx->rope_table, hs, nh, nkv, d.n_ctx, d.rope_type & 2, kq_scale, tl_slot(ctx)))) return rc;
         const size_t a2smem = (size_t)(nh / nkv) * (size_t)((d.n_ctx + 31) & ~31) * 4;
         if ((rc = launch_k(ctx, ps_k_attn2, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
-                           (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, nh, nkv, d.n_ctx))) return rc;
-        PsMvArgs o{};
-        o.n_seg = 1; o.seg[0] = {ld.wo, ctx->x, nullptr, dim, 0};
-        o.K = qdim; o.x = ctx->att; o.norm_w = nullptr; o.residual = ctx->x; o.epi = PS_EPI_RESIDUAL;
-        if ((rc = launch_matvec(ctx, o))) return rc;
-        PsMvArgs gu{};
-        gu.n_seg = 2; gu.seg[0] = {ld.wgate, ctx->g, nullptr, ffn, 0}; gu.seg[1] = {ld.wup, nullptr, nullptr, ffn, 0};
-        gu.K = dim; gu.x = ctx->x; gu.norm_w = ld.ffn_norm; gu.eps = d.norm_eps; gu.epi = PS_EPI_SILU;
-        if ((rc = launch_matvec(ctx, gu))) return rc;
-        PsMvArgs dn{};
-        dn.n_seg = 1; dn.seg[0] = {ld.wdown, ctx->x, nullptr, dim, 0};
-        dn.K = ffn; dn.x = ctx->g; dn.norm_w = nullptr; dn.residual = ctx->x; dn.epi = PS_EPI_RESIDUAL;
-        if ((rc = launch_matvec(ctx, dn))) return rc;
+                           (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, nh, nkv, d.n_ctx, tl_slot(ctx)))) return rc;
+        if ((rc = rw_single(ctx, ld.rw_o, dim, qdim, ctx->x, ctx->att, nullptr, ctx->x))) return rc;      // x += Wo . att
+        if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
+        if ((rc = rw_single(ctx, ld.rw_down, dim, ffn, ctx->x, ctx->g, nullptr, ctx->x))) return rc;      // x += Wdown . g
     }
     if (lm_head) {
-        PsMvArgs lm{};
-        lm.n_seg = 1; lm.seg[0] = {ctx->w_out, ctx->logits, nullptr, d.vocab_size, 0};
-        lm.K = dim; lm.x = ctx->x; lm.norm_w = ctx->w_out_norm; lm.eps = d.norm_eps; lm.epi = PS_EPI_STORE;
-        if ((rc = launch_matvec(ctx, lm))) return rc;
+        if ((rc = rw_single(ctx, ctx->rw_out, d.vocab_size, dim, ctx->logits, ctx->x, ctx->w_out_norm, nullptr))) return rc;
         if (pick) {
             if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(1024), 0, (const float *)ctx->logits, (int64_t)d.vocab_size, ctx->ids_dev,
-                               ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev))) return rc;
+                               ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev, tl_slot(ctx)))) return rc;
         }
     }
     return 0;
@@ -687,8 +712,31 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
     ctx->fused_ok = (ctx->t_embd == 12 && ctx->t_out == 12);
     for (const LayerDev &ld : ctx->layers)
         if (ld.tq != 12 || ld.tk != 12 || ld.tv != 12 || ld.to != 12 || ld.tgate != 12 || ld.tup != 12 || ld.tdown != 12) ctx->fused_ok = false;
-    if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 128 || d.ffn_dim / 256 > 128 || d.n_heads / d.n_kv_heads > 8)
+    if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 64 || d.ffn_dim / 256 > 64 || d.n_heads / d.n_kv_heads > 8 ||
+        ((int64_t)d.n_heads * d.head_size) % 8 || ((int64_t)d.n_kv_heads * d.head_size) % 8)
         ctx->fused_ok = false;
+    if (ctx->fused_ok) {
+        // octet-interleaved copies for the row-walker mat-vec (a permutation of the same bytes; see ps_rw.cuh)
+        const int64_t dim = d.dim, ffn = d.ffn_dim;
+        auto oct_bytes = [](int64_t rows, int64_t K, int slots) { return (size_t)((rows + 7) / 8) * (size_t)(K / 256) * slots * PS_RW_OCTET_BLOCK; };
+        int rc;
+        for (LayerDev &ld : ctx->layers) {
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_qkv, oct_bytes(qdim + 2 * kvd, dim, 1)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_o, oct_bytes(dim, qdim, 1)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_gu, oct_bytes(ffn, dim, 2)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_down, oct_bytes(dim, ffn, 1)))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wq, qdim, dim, 0, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wk, kvd, dim, qdim / 8, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wv, kvd, dim, (qdim + kvd) / 8, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_o, ld.wo, dim, qdim, 0, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wgate, ffn, dim, 0, 0, 2))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wup, ffn, dim, 0, 1, 2))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_down, ld.wdown, dim, ffn, 0, 0, 1))) return rc;
+        }
+        if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(d.vocab_size, dim, 1)))) return rc;
+        if ((rc = rw_repack(ctx, ctx->rw_out, ctx->w_out, d.vocab_size, dim, 0, 0, 1))) return rc;
+        PS_CK(cudaStreamSynchronize(ctx->stream));
+    }
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
     if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
     ctx->bound = true;
@@ -866,9 +914,15 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
-            int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * 256 * 148 * 16);
+            int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 4);
             if (rc) return rc;
-            PS_CK(cudaMemset(ctx->trace_dev, 0, sizeof(long long) * 256 * 148 * 16));
+        }
+        if (!value && ctx->trace_dev) { ps_cuda_free(ctx, ctx->trace_dev); ctx->trace_dev = nullptr; }
+        if (ctx->trace_dev) {
+            std::vector<long long> init((size_t)PS_TL_SLOTS * 4);
+            for (size_t i = 0; i < init.size(); i++) init[i] = (i & 1) ? 0 : 0x7fffffffffffffffLL; // [0],[2] take minima
+            PS_CK(cudaStreamSynchronize(ctx->stream));
+            PS_CK(cudaMemcpy(ctx->trace_dev, init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice));
         }
         ctx->trace_launch = 0;
     }
@@ -887,8 +941,9 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
 
 int ps_cuda_read_trace(ps_cuda_ctx *ctx, long long *host, int n_launches) {
     if (!ctx->trace_dev) return fail(ctx, PS_CUDA_ERR_INVALID, "trace is off");
+    if (n_launches < 0 || n_launches > PS_TL_SLOTS) return fail(ctx, PS_CUDA_ERR_INVALID, "read_trace: at most %d slots", PS_TL_SLOTS);
     PS_CK(cudaStreamSynchronize(ctx->stream));
-    PS_CK(cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * (size_t)n_launches * 148 * 16, cudaMemcpyDeviceToHost));
+    PS_CK(cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * (size_t)n_launches * 4, cudaMemcpyDeviceToHost));
     return 0;
 }
 
