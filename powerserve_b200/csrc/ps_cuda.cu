@@ -64,11 +64,13 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_pre = 1;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
+    float *part_val = nullptr; // per-CTA partial arg-max of the lm_head kernel (greedy pick, stage 1)
+    int *part_idx = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
     long long *trace_dev = nullptr; // debug: per-launch timeline of the fused decode step (option "trace"), PS_TL_SLOTS x 4
     int trace_launch = 0;
@@ -237,6 +239,7 @@ int rw_repack(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int64_t n_rows
 
 int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     a.tl = tl_slot(ctx);
+    a.inv_k = (a.K & (a.K - 1)) == 0 ? 1.0 / (double)a.K : 0.0;
     const int nb = a.K / 256, rpt = (epi == PS_EPI_SILU) ? 2 : 1;
     if (nb > 4 * PS_RW_WARPS) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: K=%d too large", a.K);
     int kb = (rpt == 2) ? 2 : 4;
@@ -251,13 +254,13 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     ns = std::min(ns, PS_RW_MAX_NS);
     if (ns < 2) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
     a.ns = ns;
+    a.pre = std::min(ns, ctx->opt_pre);
     const size_t smem = fixed + (size_t)a.n_act * ns * (stage + 8);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
         PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        PS_CK(cudaFuncSetAttribute(ps_k_attn2, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         attr[ctx->device] = true;
     }
     if (epi == PS_EPI_SILU) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_SILU>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
@@ -266,19 +269,40 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
-int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld) {
+// q, k, v in one launch; the epilogue applies ROPE to q and k and writes k / v straight into the KV cache at pos_dev[0]
+int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     const ps_cuda_model_desc &d = ctx->d;
     const int qdim = d.n_heads * d.head_size, kvd = d.n_kv_heads * d.head_size;
     PsRwArgs a{};
     a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
-    a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim};
-    a.seg[1] = {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd};
-    a.seg[2] = {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, qdim + kvd, qdim + 2 * kvd};
+    a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim, PS_RW_OUT_ROPE};
+    a.seg[1] = {ctx->kc[L], d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd, PS_RW_OUT_ROPE_KCACHE};
+    a.seg[2] = {ctx->vct[L], d.qkv_bias ? ld.v_bias : nullptr, qdim + kvd, qdim + 2 * kvd, PS_RW_OUT_VCACHE_T};
     a.x = ctx->x; a.norm_w = ld.attn_norm; a.eps = d.norm_eps;
+    a.pos_dev = ctx->pos_dev; a.rope_table = ctx->rope_table; a.hs = d.head_size; a.kvd = kvd; a.n_ctx = d.n_ctx;
     return launch_rw(ctx, a, PS_EPI_STORE);
 }
-int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual) {
+
+template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int hs = d.head_size, nkv = d.n_kv_heads;
+    const float kq_scale = 1.0f / sqrtf((float)hs);
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_attn2<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr[ctx->device] = true;
+    }
+    int rc;
+    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * 2)), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], (const float *)ctx->q,
+                       (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx)))) return rc;
+    const size_t a2smem = (size_t)R2 * (size_t)((d.n_ctx + 31) & ~31) * 4;
+    return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
+                    (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx));
+}
+int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
+              bool partial_argmax = false) {
     PsRwArgs a{};
+    if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; }
     a.w = w; a.n_oct = (n_rows + 7) / 8; a.K = K; a.n_seg = 1;
     a.seg[0] = {dst, nullptr, 0, n_rows};
     a.x = x; a.norm_w = norm_w; a.eps = ctx->d.norm_eps; a.residual = residual;
@@ -297,28 +321,29 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
 int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     const ps_cuda_model_desc &d = ctx->d;
     const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, qdim = nh * hs, ffn = d.ffn_dim;
-    const float kq_scale = 1.0f / sqrtf((float)hs);
     int rc;
     ctx->trace_launch = 0;
     if ((rc = launch_k(ctx, ps_k_embed_dev, dim3(std::max(1, dim / 256)), dim3(256), 0, ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev, tl_slot(ctx)))) return rc;
     for (int L = 0; L < d.n_layers; L++) {
         const LayerDev &ld = ctx->layers[L];
-        if ((rc = rw_qkv(ctx, ld))) return rc;
-        if ((rc = launch_k(ctx, ps_k_attn1, dim3((unsigned)((d.n_ctx + 31) / 32), (unsigned)nkv), dim3(128), 0, ctx->kq, ctx->kc[L], ctx->vct[L],
-                           (const float *)ctx->q, (const float *)ctx->k, (const float *)ctx->v, (const int32_t *)ctx->pos_dev,
-                           (const float *)ctx->rope_table, hs, nh, nkv, d.n_ctx, d.rope_type & 2, kq_scale, tl_slot(ctx)))) return rc;
-        const size_t a2smem = (size_t)(nh / nkv) * (size_t)((d.n_ctx + 31) & ~31) * 4;
-        if ((rc = launch_k(ctx, ps_k_attn2, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
-                           (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, nh, nkv, d.n_ctx, tl_slot(ctx)))) return rc;
+        if ((rc = rw_qkv(ctx, ld, L))) return rc;
+        switch (nh / nkv) {
+        case 1: rc = launch_attn<1>(ctx, L); break;
+        case 2: rc = launch_attn<2>(ctx, L); break;
+        case 4: rc = launch_attn<4>(ctx, L); break;
+        default: rc = launch_attn<8>(ctx, L); break;
+        }
+        if (rc) return rc;
         if ((rc = rw_single(ctx, ld.rw_o, dim, qdim, ctx->x, ctx->att, nullptr, ctx->x))) return rc;      // x += Wo . att
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
         if ((rc = rw_single(ctx, ld.rw_down, dim, ffn, ctx->x, ctx->g, nullptr, ctx->x))) return rc;      // x += Wdown . g
     }
     if (lm_head) {
-        if ((rc = rw_single(ctx, ctx->rw_out, d.vocab_size, dim, ctx->logits, ctx->x, ctx->w_out_norm, nullptr))) return rc;
+        if ((rc = rw_single(ctx, ctx->rw_out, d.vocab_size, dim, ctx->logits, ctx->x, ctx->w_out_norm, nullptr, pick))) return rc;
         if (pick) {
-            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(1024), 0, (const float *)ctx->logits, (int64_t)d.vocab_size, ctx->ids_dev,
-                               ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev, tl_slot(ctx)))) return rc;
+            const int n_part = std::min(ctx->n_sm, (d.vocab_size + 7) / 8);
+            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, (const float *)ctx->part_val, (const int *)ctx->part_idx, n_part,
+                               ctx->ids_dev, ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev, tl_slot(ctx)))) return rc;
         }
     }
     return 0;
@@ -421,6 +446,8 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
+    PS_AL(ctx->part_val, 4 * 1024);
+    PS_AL(ctx->part_idx, 4 * 1024);
     { int v = 148; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) ctx->n_sm = v; }
     ctx->kc.resize(d.n_layers);
     ctx->vct.resize(d.n_layers);
@@ -713,7 +740,8 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
     for (const LayerDev &ld : ctx->layers)
         if (ld.tq != 12 || ld.tk != 12 || ld.tv != 12 || ld.to != 12 || ld.tgate != 12 || ld.tup != 12 || ld.tdown != 12) ctx->fused_ok = false;
     if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 64 || d.ffn_dim / 256 > 64 || d.n_heads / d.n_kv_heads > 8 ||
-        ((int64_t)d.n_heads * d.head_size) % 8 || ((int64_t)d.n_kv_heads * d.head_size) % 8)
+        ((int64_t)d.n_heads * d.head_size) % 8 || ((int64_t)d.n_kv_heads * d.head_size) % 8 || (d.rope_type & 2) ||
+        !(d.n_heads / d.n_kv_heads == 1 || d.n_heads / d.n_kv_heads == 2 || d.n_heads / d.n_kv_heads == 4 || d.n_heads / d.n_kv_heads == 8))
         ctx->fused_ok = false;
     if (ctx->fused_ok) {
         // octet-interleaved copies for the row-walker mat-vec (a permutation of the same bytes; see ps_rw.cuh)
@@ -912,6 +940,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "pre")) ctx->opt_pre = value;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
             int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 4);

@@ -128,73 +128,77 @@ PS_D void ps_quant_block_q8k_warp(const float e[8], int lane, uint32_t *qs_words
 }
 
 // ====================================================================================================================
-// Decode attention (bs = 1), two kernels, positions read from device memory so the step can be replayed as a graph
+// Decode attention (bs = 1), two kernels, positions read from device memory so the step can be replayed as a graph.
+// ROPE(q), ROPE(k) and the two KV-cache COPY ops are fused into the QKV mat-vec epilogue (ps_rw.cuh), so by the time
+// these run q is rotated and row `pos` of the K cache / column `pos` of the transposed V cache are in place.
 // ====================================================================================================================
-// ATTN1 = ROPE(q), ROPE(k) + KV store + mat_mul(k_view, q) + scale/mask      (norm_attention.cpp:72-134, first half)
-// One CTA (4 warps) per (32-position chunk, kv head).  Each CTA re-derives rope(q) for the r2 heads of its group (128
-// floats each) instead of running a separate kernel; the CTA whose chunk holds the current position also ropes k,
-// appends it to the K cache, stores v into the transposed V cache, and scores it from registers.
+// the five butterfly steps of GGML_F32x8_REDUCE (see ps_f32x8_reduce) on N independent values, interleaved so the
+// shuffle latencies overlap
+template <int N> PS_D void ps_f32x8_reduce_n(float (&v)[N]) {
+    const int steps[5] = {16, 8, 4, 1, 2};
+#pragma unroll
+    for (int k = 0; k < 5; k++) {
+        float o[N];
+#pragma unroll
+        for (int t = 0; t < N; t++) o[t] = __shfl_xor_sync(PS_FULL, v[t], steps[k]);
+#pragma unroll
+        for (int t = 0; t < N; t++) v[t] = __fadd_rn(v[t], o[t]);
+    }
+}
+
+// ATTN1 = mat_mul(k_view, q) + scale + mask                                   (norm_attention.cpp:115-134, first half)
 //   wp[h][j] = fl(fl(dot_f32(K[j], q_h) * scale) + 0.0f)   written to `sc` ({n_ctx} per head), j < n_kv = pos + 1.
-__global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, float *__restrict__ kc, float *__restrict__ vct,
-                                                  const float *__restrict__ q, const float *__restrict__ k, const float *__restrict__ v,
-                                                  const int32_t *__restrict__ pos_dev, const float *__restrict__ table, int hs, int n_heads,
-                                                  int n_kv_heads, int n_ctx, int neox, float scale, long long *tl) {
-    __shared__ float s_q[8][256];  // roped q of the (<= 8) heads of this group
-    __shared__ float s_k[256];     // roped k of the current position
+// Persistent grid; a work item is (32-position chunk, kv head); a warp scores 8 cache rows against the R2 query heads
+// of the group, with all K loads of the item in flight before anything is consumed.
+template <int R2>
+__global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const float *__restrict__ kc, const float *__restrict__ q,
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_kv_heads, int n_ctx, float scale, long long *tl) {
+    __shared__ float s_q[R2][256];
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(tl, 2);
     const int pos = pos_dev[0];
     const int64_t n_kv = (int64_t)pos + 1;
-    const int chunk = blockIdx.x, g = blockIdx.y;
-    if ((int64_t)chunk * 32 >= n_kv) { ps_tl_max(tl, 1); return; }
-    const int r2 = n_heads / n_kv_heads, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const float *cache = table + (int64_t)pos * hs;
-    const bool has_cur = (pos / 32) == chunk;
-    // rope, pair by pair (ggml.c:15455-15486): d[a] = x0*c - x1*s ; d[b] = x0*s + x1*c, products rounded separately
-    for (int idx = tid; idx < (r2 + (has_cur ? 1 : 0)) * (hs / 2); idx += blockDim.x) {
-        const int hh = idx / (hs / 2), p = idx % (hs / 2);
-        const float *src = (hh < r2) ? q + (int64_t)(g * r2 + hh) * hs : k + (int64_t)g * hs;
-        float *dst = (hh < r2) ? s_q[hh] : s_k;
-        const int i0 = 2 * p;
-        const float c = cache[i0], sn = cache[i0 + 1];
-        const int ia = neox ? p : i0, ib = neox ? p + hs / 2 : i0 + 1;
-        const float x0 = src[ia], x1 = src[ib];
-        dst[ia] = __fadd_rn(__fmul_rn(x0, c), -__fmul_rn(x1, sn));
-        dst[ib] = __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c));
-    }
-    __syncthreads();
-    if (has_cur) { // KV store (norm_attention.cpp:79-105): K row `pos`, V column `pos` of the transposed cache
-        for (int e = tid; e < hs; e += blockDim.x) {
-            kc[(int64_t)pos * (hs * n_kv_heads) + g * hs + e] = s_k[e];
-            vct[((int64_t)g * hs + e) * n_ctx + pos] = v[g * hs + e];
-        }
-    }
-    const int steps = hs / 32;
-    // all (<= 8) K rows of this warp are requested before any is used: the loop is latency- not bandwidth-bound
-    float kv[8][8];
-    const int64_t j0 = (int64_t)chunk * 32 + warp * 8;
+    const int n_items = (int)((n_kv + 31) / 32) * n_kv_heads;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, steps = hs / 32;
+    const int kvd = hs * n_kv_heads;
+    for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
+        const int chunk = item / n_kv_heads, g = item % n_kv_heads;
+        const int64_t j0 = (int64_t)chunk * 32 + warp * 8;
+        float kv[8][8];
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-        const int64_t j = j0 + t;
+        for (int t = 0; t < 8; t++)
 #pragma unroll
-        for (int s = 0; s < 8; s++) {
-            kv[t][s] = 0.f;
-            if (s < steps && j < n_kv) kv[t][s] = (j == pos) ? s_k[32 * s + lane] : kc[j * (int64_t)(hs * n_kv_heads) + g * hs + 32 * s + lane];
-        }
-    }
+            for (int s = 0; s < 8; s++) {
+                kv[t][s] = 0.f;
+                if (s < steps && j0 + t < n_kv) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
+            }
+        __syncthreads(); // the previous item's queries are no longer needed
+        for (int idx = tid; idx < R2 * hs; idx += 128) s_q[idx / hs][idx % hs] = q[(int64_t)g * R2 * hs + idx];
+        __syncthreads();
+        float qv[R2][8];
 #pragma unroll
-    for (int t = 0; t < 8; t++) {
-        const int64_t j = j0 + t;
-        if (j < n_kv) {
-            for (int hh = 0; hh < r2; hh++) {
-                float sum = 0.f;
+        for (int hh = 0; hh < R2; hh++)
+#pragma unroll
+            for (int s = 0; s < 8; s++) qv[hh][s] = (s < steps) ? s_q[hh][32 * s + lane] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float sum[R2];
+#pragma unroll
+            for (int hh = 0; hh < R2; hh++) {
+                sum[hh] = 0.f;
 #pragma unroll
                 for (int s = 0; s < 8; s++)
-                    if (s < steps) sum = __fmaf_rn(kv[t][s], s_q[hh][32 * s + lane], sum);
-                sum = ps_f32x8_reduce(sum);
-                if (lane == 0) sc[(int64_t)(g * r2 + hh) * n_ctx + j] = __fadd_rn(__fmul_rn(sum, scale), 0.0f);
+                    if (s < steps) sum[hh] = __fmaf_rn(kv[t][s], qv[hh][s], sum[hh]); // ggml_vec_dot_f32 lane chain (ggml.c:2092-2131)
+            }
+            ps_f32x8_reduce_n<R2>(sum);
+            if (lane < R2 && j0 + t < n_kv) {
+                float v = sum[0];
+#pragma unroll
+                for (int hh = 1; hh < R2; hh++)
+                    if (lane == hh) v = sum[hh];
+                sc[(int64_t)(g * R2 + lane) * n_ctx + j0 + t] = __fadd_rn(__fmul_rn(v, scale), 0.0f);
             }
         }
     }
@@ -202,40 +206,44 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, float 
 }
 
 // ATTN2 = softmax_ext + mat_mul(v_view, kq) + permute/cont                    (norm_attention.cpp:133-151)
-// One CTA (8 warps) per (group of 8 output dims d, kv head): it rebuilds the soft-max row of each of the r2 heads of the
-// group in shared memory (max, ggml_v_expf / expf tail, double sum, scale: ggml.c:14846-14940, 2814-2868) and then each
-// warp streams one V^T row once for all r2 heads (ggml_vec_dot_f32 lane order, leftovers in order).
+// One CTA (8 warps) per (8 output dims d, kv head).  The soft-max rows of the R2 heads of the group are rebuilt in shared
+// memory by all 256 threads at once (256 / R2 threads per head: max, ggml_v_expf on 8-groups / expf tail, double sum,
+// scale: ggml.c:14846-14940, 2814-2868); then each warp streams one V^T row once for all R2 heads (ggml_vec_dot_f32
+// lane order, leftovers in order) with 16 loads in flight per lane.
+template <int R2>
 __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
-                                                  const int32_t *__restrict__ pos_dev, int hs, int n_heads, int n_kv_heads, int n_ctx, long long *tl) {
-    extern __shared__ float s_p[]; // [r2][n_kv_pad]
-    __shared__ double sh[32];
-    __shared__ float shf[32];
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl) {
+    extern __shared__ float s_p[]; // [R2][stride]
+    __shared__ double shd[8];
+    __shared__ float shf[8];
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(tl, 2);
     const int64_t n_kv = (int64_t)pos_dev[0] + 1;
-    const int g = blockIdx.y, r2 = n_heads / n_kv_heads, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    constexpr int TPH = 256 / R2, WPH = TPH / 32;          // threads / warps per head
+    const int hh = tid / TPH, ht = tid % TPH;
     const int64_t stride = (n_kv + 31) & ~(int64_t)31;
     const int64_t n8 = n_kv & ~(int64_t)7;
-    for (int hh = 0; hh < r2; hh++) {
-        const float *wp = sc + (int64_t)(g * r2 + hh) * n_ctx;
+    {
+        const float *wp = sc + (int64_t)(g * R2 + hh) * n_ctx;
         float *pp = s_p + hh * stride;
         float mx = -INFINITY;
-        for (int64_t j = tid; j < n_kv; j += blockDim.x) {
+        for (int64_t j = ht; j < n_kv; j += TPH) {
             const float vv = wp[j];
             pp[j] = vv;
             mx = fmaxf(mx, vv);
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
-        __syncthreads();
         if (lane == 0) shf[warp] = mx;
         __syncthreads();
-        mx = shf[0];
-        for (int t = 1; t < 8; t++) mx = fmaxf(mx, shf[t]);
+        mx = shf[hh * WPH];
+#pragma unroll
+        for (int t = 1; t < WPH; t++) mx = fmaxf(mx, shf[hh * WPH + t]);
         double s = 0.0;
-        for (int64_t gi = tid; gi < n8 / 8; gi += blockDim.x) {
+        for (int64_t gi = ht; gi < n8 / 8; gi += TPH) {
             float vv[8];
 #pragma unroll
             for (int l = 0; l < 8; l++) {
@@ -245,49 +253,65 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
             const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
             s += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
         }
-        for (int64_t j = n8 + tid; j < n_kv; j += blockDim.x) {
+        for (int64_t j = n8 + ht; j < n_kv; j += TPH) { // scalar tail: libm expf
             const float vv = ps_expf_glibc(__fadd_rn(pp[j], -mx));
             pp[j] = vv;
             s += (double)vv;
         }
-        const double sum = ps_block_sum_double(s, sh);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(PS_FULL, s, o);
+        if (lane == 0) shd[warp] = s;
+        __syncthreads();
+        double sum = shd[hh * WPH];
+#pragma unroll
+        for (int t = 1; t < WPH; t++) sum += shd[hh * WPH + t];
         const float inv = (float)(1.0 / sum);
-        for (int64_t j = tid; j < n_kv; j += blockDim.x) pp[j] = __fmul_rn(pp[j], inv);
+        for (int64_t j = ht; j < n_kv; j += TPH) pp[j] = __fmul_rn(pp[j], inv);
     }
     __syncthreads();
     ps_tl_max(tl, 3);
     const int d = blockIdx.x * 8 + warp;
-    if (d >= hs) return;
-    const float *vrow = vct + ((int64_t)g * hs + d) * n_ctx;
-    const int64_t np = n_kv & ~(int64_t)31;
-    float sum[8];
+    if (d < hs) {
+        const float *vrow = vct + ((int64_t)g * hs + d) * n_ctx;
+        const int64_t np = n_kv & ~(int64_t)31;
+        float sum[R2];
 #pragma unroll
-    for (int hh = 0; hh < 8; hh++) sum[hh] = 0.f;
-    int64_t s0 = 0;
-    for (; s0 + 256 <= np; s0 += 256) { // 8 independent V loads in flight per lane; the FMA chains stay in position order
-        float vv[8];
+        for (int h2 = 0; h2 < R2; h2++) sum[h2] = 0.f;
+        const int ntail = (int)(n_kv - np);
+        const float vtail = (lane < ntail) ? vrow[np + lane] : 0.f;
+        int64_t s0 = 0;
+        for (; s0 + 512 <= np; s0 += 512) { // 16 independent V loads in flight per lane; the FMA chains stay in position order
+            float vv[16];
 #pragma unroll
-        for (int u = 0; u < 8; u++) vv[u] = vrow[s0 + 32 * u + lane];
+            for (int u = 0; u < 16; u++) vv[u] = vrow[s0 + 32 * u + lane];
 #pragma unroll
-        for (int u = 0; u < 8; u++)
+            for (int u = 0; u < 16; u++)
 #pragma unroll
-            for (int hh = 0; hh < 8; hh++)
-                if (hh < r2) sum[hh] = __fmaf_rn(vv[u], s_p[hh * stride + s0 + 32 * u + lane], sum[hh]);
-    }
-    for (; s0 < np; s0 += 32) {
-        const float vv = vrow[s0 + lane];
+                for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(vv[u], s_p[h2 * stride + s0 + 32 * u + lane], sum[h2]);
+        }
+        if (s0 < np) {
+            float vv[16];
 #pragma unroll
-        for (int hh = 0; hh < 8; hh++)
-            if (hh < r2) sum[hh] = __fmaf_rn(vv, s_p[hh * stride + s0 + lane], sum[hh]);
-    }
+            for (int u = 0; u < 16; u++) vv[u] = (s0 + 32 * u < np) ? vrow[s0 + 32 * u + lane] : 0.f;
 #pragma unroll
-    for (int hh = 0; hh < 8; hh++) {
-        if (hh < r2) {
-            float r = ps_f32x8_reduce(sum[hh]);
-            if (lane == 0) {
-                for (int64_t j = np; j < n_kv; j++) r = __fadd_rn(r, __fmul_rn(vrow[j], s_p[hh * stride + j]));
-                att[(int64_t)(g * r2 + hh) * hs + d] = r;
-            }
+            for (int u = 0; u < 16; u++)
+                if (s0 + 32 * u < np) {
+#pragma unroll
+                    for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(vv[u], s_p[h2 * stride + s0 + 32 * u + lane], sum[h2]);
+                }
+        }
+        ps_f32x8_reduce_n<R2>(sum);
+        for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order (every lane computes the same chain)
+            const float v = __shfl_sync(PS_FULL, vtail, t);
+#pragma unroll
+            for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fadd_rn(sum[h2], __fmul_rn(v, s_p[h2 * stride + np + t]));
+        }
+        if (lane < R2) {
+            float v = sum[0];
+#pragma unroll
+            for (int h2 = 1; h2 < R2; h2++)
+                if (lane == h2) v = sum[h2];
+            att[(int64_t)(g * R2 + lane) * hs + d] = v;
         }
     }
     ps_tl_max(tl, 1);
@@ -318,19 +342,23 @@ __global__ void __launch_bounds__(256) ps_k_embed_dev(float *__restrict__ dst, c
     ps_tl_max(tl, 1);
 }
 
-// greedy pick + device-side step bookkeeping: ids[*ctr] = argmax, token feedback, position and counter advance
-__global__ void __launch_bounds__(1024) ps_k_argmax_step(const float *__restrict__ logits, int64_t n, int32_t *__restrict__ ids,
-                                                         int32_t *__restrict__ ctr, int32_t *__restrict__ next_token, int32_t *__restrict__ pos, long long *tl) {
-    __shared__ float sv[32];
-    __shared__ int si[32];
+// greedy pick (Model::decode with top_k = 1: ProbArray + greedy_sample, src/model/llama/llama_model.cpp:124-128), stage 2:
+// reduce the lm_head kernel's per-CTA partial maxima (first maximum wins) and do the device-side step bookkeeping:
+// ids[*ctr] = argmax, token feedback, position and counter advance.
+__global__ void __launch_bounds__(256) ps_k_argmax_step(const float *__restrict__ part_val, const int *__restrict__ part_idx, int n_part,
+                                                        int32_t *__restrict__ ids, int32_t *__restrict__ ctr, int32_t *__restrict__ next_token,
+                                                        int32_t *__restrict__ pos, long long *tl) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     float best = -INFINITY;
     int bi = 0x7fffffff;
-    for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {
-        const float v = logits[t];
-        if (v > best || (v == best && (int)t < bi)) { best = v; bi = (int)t; }
+    for (int t = threadIdx.x; t < n_part; t += blockDim.x) {
+        const float v = part_val[t];
+        const int i = part_idx[t];
+        if (v > best || (v == best && i < bi)) { best = v; bi = i; }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) {

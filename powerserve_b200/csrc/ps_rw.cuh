@@ -26,10 +26,13 @@
 #define PS_RW_OCTET_BLOCK 1152                 // 8 rows x 144 bytes
 #define PS_RW_MAX_NS 8
 
+enum { PS_RW_OUT_PLAIN = 0, PS_RW_OUT_ROPE = 1, PS_RW_OUT_ROPE_KCACHE = 2, PS_RW_OUT_VCACHE_T = 3 };
+
 struct PsRwSeg {
     float *dst;         // output rows of this segment (indexed by row - row_begin)
     const float *bias;  // optional
     int row_begin, row_end;
+    int mode;           // PS_RW_OUT_*: the q / k / v epilogues fuse ROPE and the two KV-cache COPY ops (norm_attention.cpp:72-105)
 };
 
 struct PsRwArgs {
@@ -39,12 +42,21 @@ struct PsRwArgs {
     int kb;                // super-blocks per pipeline stage
     int ns;                // stages per warp ring
     int n_act;             // warps of a CTA that own octets (ring slots exist only for these)
+    int pre;               // ring slots requested before griddepcontrol.wait; the rest follow once x has been read, so the
+                           // activation loads do not queue behind ~200 KB per SM of weight prefetch
     PsRwSeg seg[3];
     int n_seg;
     const float *x;        // fp32 activation [K]
     const float *norm_w;   // non-null: quantise rmsnorm(x) * norm_w
     float eps;
     const float *residual; // PS_EPI_RESIDUAL
+    // fused ROPE / KV store (decode): position from device memory, cos/sin table row = pos (ggml.c:15342-15356)
+    const int32_t *pos_dev;
+    const float *rope_table;
+    int hs, kvd, n_ctx;
+    double inv_k;          // 1 / K when K is a power of two (the mean is then an exact scaling), else 0
+    float *part_val;       // optional (lm_head): per-CTA partial arg-max of the produced rows, [gridDim.x]
+    int *part_idx;
     long long *tl;         // optional timeline slot (option "trace")
 };
 
@@ -152,15 +164,24 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
         ps_bulk_g2s(my_ring + (size_t)slot * stage_bytes, src, stage_bytes, &my_bar[slot]);
     };
     ps_tl_min(a.tl, 0);
+    // the norm weights do not depend on the previous kernel either: request them before the weight prefetch floods HBM
+    float wv0[8];
+    const bool early_w = a.norm_w != nullptr && warp < nb;
+    if (early_w) {
+        const float4 w0 = *reinterpret_cast<const float4 *>(a.norm_w + warp * 256 + 4 * lane);
+        const float4 w1 = *reinterpret_cast<const float4 *>(a.norm_w + warp * 256 + 128 + 4 * lane);
+        wv0[0] = w0.x; wv0[1] = w0.y; wv0[2] = w0.z; wv0[3] = w0.w; wv0[4] = w1.x; wv0[5] = w1.y; wv0[6] = w1.z; wv0[7] = w1.w;
+    }
     if (n_stages > 0 && lane == 0) {
         for (int s = 0; s < ns; s++) ps_mbar_init(&my_bar[s], 1);
         ps_fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < ns && s < n_stages; s++) issue(s); // weights never depend on the previous kernel
+        for (int s = 0; s < a.pre && s < n_stages; s++) issue(s); // weights never depend on the previous kernel
     }
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(a.tl, 2);
+    const long long t_dep = (a.tl && tid == 0) ? ps_globaltimer() : 0;
 
     // ---- prologue: (RMSNorm) + Q8_K quantisation of x into shared memory, one warp per 256-block
     {
@@ -181,6 +202,9 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
                 }
             }
         }
+        // the rest of the ring, once this warp's x values have arrived (the compare consumes a loaded register)
+        if (n_stages > 0 && lane == 0 && (warp >= nb || __float_as_uint(e[0][0]) != 0xffc0dead))
+            for (int s = a.pre; s < ns && s < n_stages; s++) issue(s);
         float nscale = 1.f;
         if (a.norm_w) {
 #pragma unroll
@@ -190,7 +214,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             double t = (lane < PS_RW_WARPS) ? sh_red[lane] : 0.0;
 #pragma unroll
             for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(PS_FULL, t, o);
-            const float mean = (float)(t / (double)K);
+            const float mean = (float)(a.inv_k != 0.0 ? t * a.inv_k : t / (double)K);
             nscale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, a.eps)));
         }
 #pragma unroll
@@ -198,9 +222,15 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             const int i = warp + u * PS_RW_WARPS;
             if (u < per_warp && i < nb) {
                 if (a.norm_w) {
-                    const float4 w0 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 4 * lane);
-                    const float4 w1 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 128 + 4 * lane);
-                    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+                    float wv[8];
+                    if (u == 0) {
+#pragma unroll
+                        for (int t = 0; t < 8; t++) wv[t] = wv0[t];
+                    } else {
+                        const float4 w0 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 4 * lane);
+                        const float4 w1 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 128 + 4 * lane);
+                        wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
+                    }
 #pragma unroll
                     for (int t = 0; t < 8; t++) e[u][t] = __fmul_rn(e[u][t], __fmul_rn(wv[t], nscale)); // y = x * (w * scale)
                 }
@@ -218,9 +248,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
         }
     }
     __syncthreads();
-    ps_tl_max(a.tl, 3);
+    if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + 3), (unsigned long long)(ps_globaltimer() - t_dep)); // slowest CTA's prologue
 
     // ---- the stream
+    float best_v = -INFINITY;
+    int best_i = 0x7fffffff;
     int s = 0;
     for (int m = 0; m < n_mine; m++) {
         const int oct = o0 + warp + m * a.n_act;
@@ -249,17 +281,50 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             if (q == 0 && row < a.seg[0].row_end) a.seg[0].dst[row] = ps_silu_mul(g, u);
         } else {
             float res = ps_rw_row_result(acc[0]);
-            if (q == 0) {
-                int sg = 0;
-                if (a.n_seg > 1 && row >= a.seg[1].row_begin) sg = 1;
-                if (a.n_seg > 2 && row >= a.seg[2].row_begin) sg = 2;
-                if (row < a.seg[sg].row_end) {
-                    const int n = row - a.seg[sg].row_begin;
-                    if (a.seg[sg].bias) res = __fadd_rn(res, a.seg[sg].bias[n]);
-                    if (EPI == PS_EPI_RESIDUAL) res = __fadd_rn(a.residual[n], res);
-                    a.seg[sg].dst[n] = res;
+            int sg = 0;
+            if (a.n_seg > 1 && row >= a.seg[1].row_begin) sg = 1;
+            if (a.n_seg > 2 && row >= a.seg[2].row_begin) sg = 2;
+            const bool live = row < a.seg[sg].row_end;
+            const int n = row - a.seg[sg].row_begin;
+            const int mode = a.seg[sg].mode;      // warp-uniform: segments are octet-aligned
+            if (live && a.seg[sg].bias) res = __fadd_rn(res, a.seg[sg].bias[n]);
+            if (EPI == PS_EPI_STORE && mode != PS_RW_OUT_PLAIN) {
+                const int pos = a.pos_dev[0];
+                if (mode == PS_RW_OUT_VCACHE_T) {         // V cache is stored transposed: [kv_dim][n_ctx]
+                    if (q == 0 && live) a.seg[sg].dst[(size_t)n * a.n_ctx + pos] = res;
+                } else {
+                    // ggml_compute_forward_rope_f32, adjacent pairs (ggml.c:15455-15486): rows (2p, 2p+1) sit in
+                    // neighbouring quads of the octet; products rounded separately, as the reference does
+                    const float other = __shfl_xor_sync(PS_FULL, res, 4);
+                    const int i0 = (n % a.hs) & ~1;
+                    const float c = live ? a.rope_table[(size_t)pos * a.hs + i0] : 0.f, sn = live ? a.rope_table[(size_t)pos * a.hs + i0 + 1] : 0.f;
+                    const float x0 = (r & 1) ? other : res, x1 = (r & 1) ? res : other;
+                    const float out = (r & 1) ? __fadd_rn(__fmul_rn(x0, sn), __fmul_rn(x1, c)) : __fadd_rn(__fmul_rn(x0, c), -__fmul_rn(x1, sn));
+                    if (q == 0 && live) a.seg[sg].dst[(mode == PS_RW_OUT_ROPE_KCACHE ? (size_t)pos * a.kvd : 0) + n] = out;
                 }
+            } else if (q == 0 && live) {
+                if (EPI == PS_EPI_RESIDUAL) res = __fadd_rn(a.residual[n], res);
+                a.seg[sg].dst[n] = res;
+                if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
             }
+        }
+    }
+    if (EPI == PS_EPI_STORE && a.part_val) { // greedy pick, stage 1: the CTA's best (value, lowest index)
+        __shared__ float sv[PS_RW_WARPS];
+        __shared__ int si[PS_RW_WARPS];
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+            const float ov = __shfl_xor_sync(PS_FULL, best_v, o);
+            const int oi = __shfl_xor_sync(PS_FULL, best_i, o);
+            if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+        }
+        if (lane == 0) { sv[warp] = best_v; si[warp] = best_i; }
+        __syncthreads();
+        if (tid == 0) {
+            for (int t = 1; t < PS_RW_WARPS; t++)
+                if (sv[t] > best_v || (sv[t] == best_v && si[t] < best_i)) { best_v = sv[t]; best_i = si[t]; }
+            a.part_val[blockIdx.x] = best_v;
+            a.part_idx[blockIdx.x] = best_i;
         }
     }
     __syncthreads();

@@ -42,7 +42,7 @@ for k in range(n):
     s, e, d, p = buf[k]
     f = lambda v: (v - t0) / 1e3
     dep = f"{f(d):7.2f}" if d < 2**62 else "      -"
-    pro = f"{f(p):7.2f}" if p > 0 else "      -"
+    pro = (f"{f(p):7.2f}" if p > 10**9 else f"{p / 1e3:6.2f}d") if p > 0 else "      -"
     if k < 14 or k >= n - 3:
         print(f"{k:3d} {names[k]:7s} {f(s):8.2f} {dep} {pro} {f(e):8.2f} {(e - s) / 1e3:6.2f} {(s - prev_end) / 1e3:6.2f}")
     tot.setdefault(names[k], []).append(((e - max(s, prev_end)) / 1e3, (e - prev_end) / 1e3))
