@@ -64,11 +64,13 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_pre = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
+    uint8_t *hq = nullptr;     // Q8_K image of the FFN hidden vector, written by the gate/up epilogue for the down mat-vec
+    int *blk_cnt = nullptr;    // per-256-block arrival counters of that hand-off (rest state: zero)
     float *part_val = nullptr; // per-CTA partial arg-max of the lm_head kernel (greedy pick, stage 1)
     int *part_idx = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
@@ -226,7 +228,7 @@ int launch_k(ps_cuda_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, si
 // timeline slot of the next fused-path launch (nullptr when option "trace" is off)
 long long *tl_slot(ps_cuda_ctx *ctx) {
     if (!ctx->trace_dev) return nullptr;
-    return ctx->trace_dev + (size_t)(ctx->trace_launch++ % PS_TL_SLOTS) * 4;
+    return ctx->trace_dev + (size_t)(ctx->trace_launch++ % PS_TL_SLOTS) * 8;
 }
 
 // ---- row-walker mat-vec (ps_rw.cuh)
@@ -254,7 +256,6 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     ns = std::min(ns, PS_RW_MAX_NS);
     if (ns < 2) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
     a.ns = ns;
-    a.pre = std::min(ns, ctx->opt_pre);
     const size_t smem = fixed + (size_t)a.n_act * ns * (stage + 8);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
@@ -263,9 +264,9 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
         PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr[ctx->device] = true;
     }
-    if (epi == PS_EPI_SILU) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_SILU>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
-    if (epi == PS_EPI_RESIDUAL) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_RESIDUAL>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
-    return launch_k(ctx, ps_k_rw_matvec<PS_EPI_STORE>, dim3(grid), dim3(PS_RW_THREADS), smem, a);
+    if (epi == PS_EPI_SILU) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_SILU>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
+    if (epi == PS_EPI_RESIDUAL) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_RESIDUAL>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
+    return launch_k(ctx, ps_k_rw_matvec<PS_EPI_STORE>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
 }
 
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
@@ -300,8 +301,10 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
                     (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx));
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
-              bool partial_argmax = false) {
+              bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr) {
     PsRwArgs a{};
+    a.xq_in = xq_in;
+    a.next_norm_w = next_norm_w; a.next_norm_n = ctx->d.dim;
     if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; }
     a.w = w; a.n_oct = (n_rows + 7) / 8; a.K = K; a.n_seg = 1;
     a.seg[0] = {dst, nullptr, 0, n_rows};
@@ -314,6 +317,7 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     a.w = ld.rw_gu; a.n_oct = (d.ffn_dim + 7) / 8; a.K = d.dim; a.n_seg = 1;
     a.seg[0] = {ctx->g, nullptr, 0, d.ffn_dim};
     a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
+    a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt;
     return launch_rw(ctx, a, PS_EPI_SILU);
 }
 
@@ -334,9 +338,10 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
         default: rc = launch_attn<8>(ctx, L); break;
         }
         if (rc) return rc;
-        if ((rc = rw_single(ctx, ld.rw_o, dim, qdim, ctx->x, ctx->att, nullptr, ctx->x))) return rc;      // x += Wo . att
+        const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
+        if ((rc = rw_single(ctx, ld.rw_o, dim, qdim, ctx->x, ctx->att, nullptr, ctx->x, false, nullptr, ld.ffn_norm))) return rc; // x += Wo . att
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
-        if ((rc = rw_single(ctx, ld.rw_down, dim, ffn, ctx->x, ctx->g, nullptr, ctx->x))) return rc;      // x += Wdown . g
+        if ((rc = rw_single(ctx, ld.rw_down, dim, ffn, ctx->x, ctx->g, nullptr, ctx->x, false, ctx->hq, norm_after))) return rc; // x += Wdown . g
     }
     if (lm_head) {
         if ((rc = rw_single(ctx, ctx->rw_out, d.vocab_size, dim, ctx->logits, ctx->x, ctx->w_out_norm, nullptr, pick))) return rc;
@@ -446,6 +451,9 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
+    PS_AL(ctx->hq, (size_t)d.ffn_dim + (size_t)(d.ffn_dim / 256 + 1) * 32);
+    PS_AL(ctx->blk_cnt, 4 * (size_t)(d.ffn_dim / 256 + 1));
+    PS_CKC(cudaMemsetAsync(ctx->blk_cnt, 0, 4 * (size_t)(d.ffn_dim / 256 + 1), ctx->stream));
     PS_AL(ctx->part_val, 4 * 1024);
     PS_AL(ctx->part_idx, 4 * 1024);
     { int v = 148; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) ctx->n_sm = v; }
@@ -940,16 +948,15 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
-    else if (!strcmp(name, "pre")) ctx->opt_pre = value;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
-            int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 4);
+            int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 8);
             if (rc) return rc;
         }
         if (!value && ctx->trace_dev) { ps_cuda_free(ctx, ctx->trace_dev); ctx->trace_dev = nullptr; }
         if (ctx->trace_dev) {
-            std::vector<long long> init((size_t)PS_TL_SLOTS * 4);
-            for (size_t i = 0; i < init.size(); i++) init[i] = (i & 1) ? 0 : 0x7fffffffffffffffLL; // [0],[2] take minima
+            std::vector<long long> init((size_t)PS_TL_SLOTS * 8, 0);
+            for (size_t i = 0; i < init.size(); i += 8) init[i] = init[i + 2] = 0x7fffffffffffffffLL; // [0],[2] take minima
             PS_CK(cudaStreamSynchronize(ctx->stream));
             PS_CK(cudaMemcpy(ctx->trace_dev, init.data(), init.size() * sizeof(long long), cudaMemcpyHostToDevice));
         }
@@ -972,7 +979,7 @@ int ps_cuda_read_trace(ps_cuda_ctx *ctx, long long *host, int n_launches) {
     if (!ctx->trace_dev) return fail(ctx, PS_CUDA_ERR_INVALID, "trace is off");
     if (n_launches < 0 || n_launches > PS_TL_SLOTS) return fail(ctx, PS_CUDA_ERR_INVALID, "read_trace: at most %d slots", PS_TL_SLOTS);
     PS_CK(cudaStreamSynchronize(ctx->stream));
-    PS_CK(cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * (size_t)n_launches * 4, cudaMemcpyDeviceToHost));
+    PS_CK(cudaMemcpy(host, ctx->trace_dev, sizeof(long long) * (size_t)n_launches * 8, cudaMemcpyDeviceToHost));
     return 0;
 }
 

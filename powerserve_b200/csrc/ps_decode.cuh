@@ -69,20 +69,19 @@ PS_D void ps_quant_block_q8k_regs(const float e[8], int lane, uint32_t words[2],
     float amax = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; t++) amax = fmaxf(amax, fabsf(e[t]));
-#pragma unroll
-    for (int o = 16; o; o >>= 1) amax = fmaxf(amax, __shfl_xor_sync(PS_FULL, amax, o));
+    // warp-wide reductions with redux.sync (one instruction each): |x| orders like its bit pattern
+    amax = __uint_as_float(__reduce_max_sync(PS_FULL, __float_as_uint(amax)));
+    // `if (ax > amax) { amax = ax; max = x[j]; }` keeps the FIRST element that attains the maximum magnitude
     int first = 1 << 20;
 #pragma unroll
     for (int t = 7; t >= 0; t--)
         if (fabsf(e[t]) == amax) first = (t < 4 ? idx0 + t : idx1 + t - 4);
-#pragma unroll
-    for (int o = 16; o; o >>= 1) first = min(first, __shfl_xor_sync(PS_FULL, first, o));
+    const int wfirst = __reduce_min_sync(PS_FULL, first);
     float mx = 0.f;
 #pragma unroll
     for (int t = 0; t < 8; t++)
-        if ((t < 4 ? idx0 + t : idx1 + t - 4) == first) mx = e[t];
-    const unsigned owner = __ballot_sync(PS_FULL, (first >= idx0 && first < idx0 + 4) || (first >= idx1 && first < idx1 + 4));
-    mx = __shfl_sync(PS_FULL, mx, __ffs(owner) - 1);
+        if ((t < 4 ? idx0 + t : idx1 + t - 4) == wfirst) mx = e[t];
+    mx = __uint_as_float(__reduce_or_sync(PS_FULL, (first == wfirst) ? __float_as_uint(mx) : 0u)); // exactly one owner
     if (amax == 0.f) { // warp-uniform
         words[0] = words[1] = 0;
         d_out = 0.f;
@@ -98,22 +97,20 @@ PS_D void ps_quant_block_q8k_regs(const float e[8], int lane, uint32_t words[2],
     }
     words[0] = (uint32_t)(q[0] & 0xff) | ((uint32_t)(q[1] & 0xff) << 8) | ((uint32_t)(q[2] & 0xff) << 16) | ((uint32_t)(q[3] & 0xff) << 24);
     words[1] = (uint32_t)(q[4] & 0xff) | ((uint32_t)(q[5] & 0xff) << 8) | ((uint32_t)(q[6] & 0xff) << 16) | ((uint32_t)(q[7] & 0xff) << 24);
-    int s0 = q[0] + q[1] + q[2] + q[3], s1 = q[4] + q[5] + q[6] + q[7]; // sub-blocks lane/8 and 4 + lane/8
+    // sub-block sums: lanes 8j..8j+7 hold sub-blocks j (first word) and 4 + j (second word)
+    int s0 = q[0] + q[1] + q[2] + q[3], s1 = q[4] + q[5] + q[6] + q[7];
 #pragma unroll
     for (int o = 1; o < 8; o <<= 1) {
-        s0 += __shfl_xor_sync(PS_FULL, s0, o);
-        s1 += __shfl_xor_sync(PS_FULL, s1, o);
+        const int t0 = __shfl_xor_sync(PS_FULL, s0, o), t1 = __shfl_xor_sync(PS_FULL, s1, o);
+        s0 += t0;
+        s1 += t1;
     }
-    int sj[8];
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-        sj[j] = __shfl_sync(PS_FULL, s0, j * 8);
-        sj[j + 4] = __shfl_sync(PS_FULL, s1, j * 8);
-    }
-    bsp_out = 0;
-#pragma unroll
-    for (int k = 0; k < 4; k++)
-        if (lane == k) bsp_out = ((uint32_t)sj[2 * k] & 0xffffu) | ((uint32_t)sj[2 * k + 1] << 16);
+    // lane k < 4 packs (s_{2k}, s_{2k+1}): k = 0,1 read the first-word sums of groups 2k, 2k+1; k = 2,3 the second-word sums
+    const int src = 8 * ((2 * lane) & 3);
+    const int a0 = __shfl_sync(PS_FULL, s0, src), a1 = __shfl_sync(PS_FULL, s0, src + 8);
+    const int b0 = __shfl_sync(PS_FULL, s1, src), b1 = __shfl_sync(PS_FULL, s1, src + 8);
+    const int lo = (lane < 2) ? a0 : b0, hi = (lane < 2) ? a1 : b1;
+    bsp_out = ((uint32_t)lo & 0xffffu) | ((uint32_t)hi << 16);
     d_out = __fdiv_rn(1.f, iscale);
 }
 

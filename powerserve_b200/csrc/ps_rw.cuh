@@ -42,8 +42,6 @@ struct PsRwArgs {
     int kb;                // super-blocks per pipeline stage
     int ns;                // stages per warp ring
     int n_act;             // warps of a CTA that own octets (ring slots exist only for these)
-    int pre;               // ring slots requested before griddepcontrol.wait; the rest follow once x has been read, so the
-                           // activation loads do not queue behind ~200 KB per SM of weight prefetch
     PsRwSeg seg[3];
     int n_seg;
     const float *x;        // fp32 activation [K]
@@ -54,6 +52,14 @@ struct PsRwArgs {
     const int32_t *pos_dev;
     const float *rope_table;
     int hs, kvd, n_ctx;
+    // producer-side activation quantisation (gate/up -> down): the SiLU epilogue's last-arriving warp of every 256-row
+    // block quantises it to Q8_K straight into the consumer's shared-memory image (xq_out, [K bytes][nb x 32]); the
+    // consumer (xq_in) then needs one bulk copy instead of a quantisation prologue.
+    uint8_t *xq_out;
+    int *blk_cnt;          // one arrival counter per 256-row block, left at zero
+    const uint8_t *xq_in;
+    const float *next_norm_w; // norm weights of the NEXT kernel in the chain: pulled into L2 here so that its prologue
+    int next_norm_n;          // does not wait on DRAM behind its own weight prefetch
     double inv_k;          // 1 / K when K is a power of two (the mean is then an exact scaling), else 0
     float *part_val;       // optional (lm_head): per-CTA partial arg-max of the produced rows, [gridDim.x]
     int *part_idx;
@@ -133,12 +139,36 @@ PS_D float ps_rw_row_result(const PsRwAcc &acc) {
 }
 
 // ---------------------------------------------------------------------------------------------------- the kernel
+// quantise one 256-block held as e[8] per lane (see ps_quant_block_q8k_regs) into the shared-memory image the block
+// math reads: qa[i][j2][q] = {sub-block 2*j2 words 2q, 2q+1 ; sub-block 2*j2+1 words 2q, 2q+1}, meta[i][q] = {d, bsums pair q}
+__device__ __noinline__ void ps_rw_quant_store(const float *e, int lane, uint32_t *qw, uint2 *meta) {
+    uint32_t words[2], bsp4;
+    float yd;
+    float v[8];
+#pragma unroll
+    for (int t = 0; t < 8; t++) v[t] = e[t];
+    ps_quant_block_q8k_regs(v, lane, words, yd, bsp4);
+    const int l = lane & 7, jA = lane >> 3, jB = 4 + (lane >> 3); // natural words: (sub-block L/8, word L%8), (4 + L/8, L%8)
+    qw[((jA >> 1) * 4 + (l >> 1)) * 4 + (jA & 1) * 2 + (l & 1)] = words[0];
+    qw[((jB >> 1) * 4 + (l >> 1)) * 4 + (jB & 1) * 2 + (l & 1)] = words[1];
+    if (lane < 4) meta[lane] = make_uint2(__float_as_uint(yd), bsp4);
+}
+
+PS_D void ps_rw_load8(const float *p, int lane, float e[8]) {
+    const float4 v0 = *reinterpret_cast<const float4 *>(p + 4 * lane);
+    const float4 v1 = *reinterpret_cast<const float4 *>(p + 128 + 4 * lane);
+    e[0] = v0.x; e[1] = v0.y; e[2] = v0.z; e[3] = v0.w; e[4] = v1.x; e[5] = v1.y; e[6] = v1.z; e[7] = v1.w;
+}
+
+// Threads: PS_RW_WARPS compute warps + one helper warp that initialises the mbarriers and fills every warp's ring
+// (lane w serves warp w) and then exits, so no compute warp ever stalls on the TMA queue during the prologue.
 // Dynamic shared memory: [qa: K bytes][meta: nb x 4 x 8][rings: n_act x ns x stage_bytes][bars: n_act x ns x 8]
 template <int EPI>
-__global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArgs a) {
+__global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const PsRwArgs a) {
     constexpr int RPT = (EPI == PS_EPI_SILU) ? 2 : 1;
     extern __shared__ __align__(128) uint8_t ps_rw_smem[];
     __shared__ double sh_red[PS_RW_WARPS];
+    __shared__ __align__(8) uint64_t xbar;
     const int K = a.K, nb = K / 256, kb = a.kb, ns = a.ns;
     const uint32_t stage_bytes = (uint32_t)kb * RPT * PS_RW_OCTET_BLOCK;
     uint4 *s_qa = reinterpret_cast<uint4 *>(ps_rw_smem);
@@ -149,120 +179,136 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
     // this CTA's octets [o0, o1); warp w walks o0 + w, o0 + w + n_act, ...
     const int o0 = (int)(((long long)blockIdx.x * a.n_oct) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.n_oct) / gridDim.x);
-    const int n_mine = (warp < a.n_act && o0 + warp < o1) ? (o1 - o0 - warp - 1) / a.n_act + 1 : 0;
     const int spo = nb / kb;                 // stages per octet
-    const int n_stages = n_mine * spo;
-    uint8_t *my_ring = s_ring + (size_t)warp * ns * stage_bytes;
-    uint64_t *my_bar = s_bar + warp * ns;
     const size_t oct_bytes = (size_t)nb * RPT * PS_RW_OCTET_BLOCK;
-
-    auto issue = [&](int s) { // lane 0: request stage #s of this warp's stream into slot s % ns
-        const int oct = o0 + warp + (s / spo) * a.n_act;
+    auto stages_of = [&](int w) { return (w < a.n_act && o0 + w < o1) ? ((o1 - o0 - w - 1) / a.n_act + 1) * spo : 0; };
+    auto issue = [&](int w, int s) { // request stage #s of warp w's stream into slot s % ns of its ring
+        const int oct = o0 + w + (s / spo) * a.n_act;
         const uint8_t *src = a.w + (size_t)oct * oct_bytes + (size_t)(s % spo) * stage_bytes;
-        const int slot = s % ns;
-        ps_mbar_expect_tx(&my_bar[slot], stage_bytes);
-        ps_bulk_g2s(my_ring + (size_t)slot * stage_bytes, src, stage_bytes, &my_bar[slot]);
+        uint64_t *bar = s_bar + w * ns + (s % ns);
+        ps_mbar_expect_tx(bar, stage_bytes);
+        ps_bulk_g2s(s_ring + ((size_t)w * ns + (s % ns)) * stage_bytes, src, stage_bytes, bar);
     };
     ps_tl_min(a.tl, 0);
-    // the norm weights do not depend on the previous kernel either: request them before the weight prefetch floods HBM
-    float wv0[8];
-    const bool early_w = a.norm_w != nullptr && warp < nb;
-    if (early_w) {
-        const float4 w0 = *reinterpret_cast<const float4 *>(a.norm_w + warp * 256 + 4 * lane);
-        const float4 w1 = *reinterpret_cast<const float4 *>(a.norm_w + warp * 256 + 128 + 4 * lane);
-        wv0[0] = w0.x; wv0[1] = w0.y; wv0[2] = w0.z; wv0[3] = w0.w; wv0[4] = w1.x; wv0[5] = w1.y; wv0[6] = w1.z; wv0[7] = w1.w;
-    }
-    if (n_stages > 0 && lane == 0) {
-        for (int s = 0; s < ns; s++) ps_mbar_init(&my_bar[s], 1);
+
+    if (warp == PS_RW_WARPS) {
+        // ===== helper warp: weights never depend on the previous kernel, so the rings fill while it drains
+        const int n = stages_of(lane);
+        if (n > 0) {
+            for (int s = 0; s < ns; s++) ps_mbar_init(s_bar + lane * ns + s, 1);
+        }
+        if (lane == 0) ps_mbar_init(&xbar, 1);
         ps_fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < a.pre && s < n_stages; s++) issue(s); // weights never depend on the previous kernel
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"n"(PS_RW_THREADS + 32) : "memory"); // barriers are live
+        ps_bar_sync(3, PS_RW_THREADS + 32); // the compute warps' norm-weight loads are on their way (DRAM queues are FIFO)
+        for (int s = 0; s < ns && s < n; s++) issue(lane, s);
+        return;
     }
+
+    // ===== compute warps
+    // the norm weights do not depend on the previous kernel either
+    float wv0[8];
+    const bool early_w = a.norm_w != nullptr && warp < nb;
+    if (early_w) ps_rw_load8(a.norm_w + warp * 256, lane, wv0);
+    asm volatile("bar.arrive 3, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(a.tl, 2);
     const long long t_dep = (a.tl && tid == 0) ? ps_globaltimer() : 0;
+#define PS_RW_PROBE(k)                                                                                                   \
+    do {                                                                                                                 \
+        if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
+    } while (0)
+    ps_bar_sync(1, PS_RW_THREADS + 32); // mbarriers initialised by the helper
+    if (a.next_norm_w && blockIdx.x == 0)
+        for (int i = tid * 32; i < a.next_norm_n; i += PS_RW_THREADS * 32)
+            asm volatile("prefetch.global.L2::evict_last [%0];" ::"l"(a.next_norm_w + i));
 
-    // ---- prologue: (RMSNorm) + Q8_K quantisation of x into shared memory, one warp per 256-block
-    {
-        float e[4][8];
-        double ss = 0.0;
-        const int per_warp = (nb + PS_RW_WARPS - 1) / PS_RW_WARPS; // <= 4 (K <= 16384)
-#pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = warp + u * PS_RW_WARPS;
-            if (u < per_warp && i < nb) {
-                const float4 v0 = *reinterpret_cast<const float4 *>(a.x + i * 256 + 4 * lane);
-                const float4 v1 = *reinterpret_cast<const float4 *>(a.x + i * 256 + 128 + 4 * lane);
-                e[u][0] = v0.x; e[u][1] = v0.y; e[u][2] = v0.z; e[u][3] = v0.w;
-                e[u][4] = v1.x; e[u][5] = v1.y; e[u][6] = v1.z; e[u][7] = v1.w;
-                if (a.norm_w) {
-#pragma unroll
-                    for (int t = 0; t < 8; t++) ss += (double)__fmul_rn(e[u][t], e[u][t]);
-                }
-            }
+    // ---- prologue: the Q8_K image of the activation vector in shared memory
+    if (a.xq_in) { // quantised by the producer kernel: one bulk copy
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)K + (uint32_t)nb * 32;
+            ps_mbar_expect_tx(&xbar, bytes);
+            ps_bulk_g2s(ps_rw_smem, a.xq_in, bytes, &xbar);
         }
-        // the rest of the ring, once this warp's x values have arrived (the compare consumes a loaded register)
-        if (n_stages > 0 && lane == 0 && (warp >= nb || __float_as_uint(e[0][0]) != 0xffc0dead))
-            for (int s = a.pre; s < ns && s < n_stages; s++) issue(s);
+        ps_mbar_wait(&xbar, 0);
+        PS_RW_PROBE(4);
+    } else { // (RMSNorm) + quantize_row_q8_K, one warp per 256-block
+        float e0[8];
+        const bool have0 = warp < nb;
+        if (have0) ps_rw_load8(a.x + warp * 256, lane, e0);
         float nscale = 1.f;
         if (a.norm_w) {
+            double ss = 0.0;
+            if (have0) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) ss += (double)__fmul_rn(e0[t], e0[t]);
+            }
+#pragma unroll 1
+            for (int i = warp + PS_RW_WARPS; i < nb; i += PS_RW_WARPS) {
+                float e[8];
+                ps_rw_load8(a.x + i * 256, lane, e);
+#pragma unroll
+                for (int t = 0; t < 8; t++) ss += (double)__fmul_rn(e[t], e[t]);
+            }
 #pragma unroll
             for (int o = 16; o; o >>= 1) ss += __shfl_xor_sync(PS_FULL, ss, o);
             if (lane == 0) sh_red[warp] = ss;
-            __syncthreads();
+            PS_RW_PROBE(4);
+            ps_bar_sync(2, PS_RW_THREADS);
             double t = (lane < PS_RW_WARPS) ? sh_red[lane] : 0.0;
 #pragma unroll
             for (int o = 16; o; o >>= 1) t += __shfl_xor_sync(PS_FULL, t, o);
             const float mean = (float)(a.inv_k != 0.0 ? t * a.inv_k : t / (double)K);
             nscale = __fdiv_rn(1.0f, __fsqrt_rn(__fadd_rn(mean, a.eps)));
         }
+        if (have0) {
+            if (a.norm_w) {
 #pragma unroll
-        for (int u = 0; u < 4; u++) {
-            const int i = warp + u * PS_RW_WARPS;
-            if (u < per_warp && i < nb) {
-                if (a.norm_w) {
-                    float wv[8];
-                    if (u == 0) {
-#pragma unroll
-                        for (int t = 0; t < 8; t++) wv[t] = wv0[t];
-                    } else {
-                        const float4 w0 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 4 * lane);
-                        const float4 w1 = *reinterpret_cast<const float4 *>(a.norm_w + i * 256 + 128 + 4 * lane);
-                        wv[0] = w0.x; wv[1] = w0.y; wv[2] = w0.z; wv[3] = w0.w; wv[4] = w1.x; wv[5] = w1.y; wv[6] = w1.z; wv[7] = w1.w;
-                    }
-#pragma unroll
-                    for (int t = 0; t < 8; t++) e[u][t] = __fmul_rn(e[u][t], __fmul_rn(wv[t], nscale)); // y = x * (w * scale)
-                }
-                // natural-order words: lane L -> (sub-block L/8, word L%8) and (sub-block 4 + L/8, word L%8)
-                uint32_t words[2];
-                float yd;
-                uint32_t bsp4;
-                ps_quant_block_q8k_regs(e[u], lane, words, yd, bsp4);
-                uint32_t *qw = reinterpret_cast<uint32_t *>(s_qa) + (size_t)i * 64;
-                const int l = lane & 7, jA = lane >> 3, jB = 4 + (lane >> 3);
-                qw[((jA >> 1) * 4 + (l >> 1)) * 4 + (jA & 1) * 2 + (l & 1)] = words[0];
-                qw[((jB >> 1) * 4 + (l >> 1)) * 4 + (jB & 1) * 2 + (l & 1)] = words[1];
-                if (lane < 4) s_meta[i * 4 + lane] = make_uint2(__float_as_uint(yd), bsp4);
+                for (int t = 0; t < 8; t++) e0[t] = __fmul_rn(e0[t], __fmul_rn(wv0[t], nscale)); // y = x * (w * scale)
             }
+            if (__float_as_uint(e0[0]) != 0xffc0dead) PS_RW_PROBE(5);
+            ps_rw_quant_store(e0, lane, reinterpret_cast<uint32_t *>(s_qa) + (size_t)warp * 64, s_meta + warp * 4);
         }
+#pragma unroll 1
+        for (int i = warp + PS_RW_WARPS; i < nb; i += PS_RW_WARPS) {
+            float e[8];
+            ps_rw_load8(a.x + i * 256, lane, e);
+            if (a.norm_w) {
+                float wv[8];
+                ps_rw_load8(a.norm_w + i * 256, lane, wv);
+#pragma unroll
+                for (int t = 0; t < 8; t++) e[t] = __fmul_rn(e[t], __fmul_rn(wv[t], nscale));
+            }
+            ps_rw_quant_store(e, lane, reinterpret_cast<uint32_t *>(s_qa) + (size_t)i * 64, s_meta + i * 4);
+        }
+        PS_RW_PROBE(6);
+        ps_bar_sync(2, PS_RW_THREADS);
     }
-    __syncthreads();
-    if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + 3), (unsigned long long)(ps_globaltimer() - t_dep)); // slowest CTA's prologue
+    PS_RW_PROBE(3); // slowest CTA's prologue
 
     // ---- the stream
+    const int n_stages = stages_of(warp);
+    const int n_mine = n_stages / spo;
+    uint8_t *my_ring = s_ring + (size_t)warp * ns * stage_bytes;
+    uint64_t *my_bar = s_bar + warp * ns;
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
     int s = 0;
+#pragma unroll 1
     for (int m = 0; m < n_mine; m++) {
         const int oct = o0 + warp + m * a.n_act;
         PsRwAcc acc[RPT];
 #pragma unroll
         for (int t = 0; t < RPT; t++) acc[t].a0 = acc[t].a1 = acc[t].am = 0.f;
+#pragma unroll 1
         for (int sb = 0; sb < spo; sb++, s++) {
             const int slot = s % ns;
             ps_mbar_wait(&my_bar[slot], (s / ns) & 1);
             const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
+#pragma unroll 1
             for (int b = 0; b < kb; b++) {
                 const int i = sb * kb + b;
                 const uint4 *qa = s_qa + (size_t)i * 16;
@@ -271,7 +317,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
                 for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, qa, meta, acc[t]);
             }
             __syncwarp();
-            if (lane == 0 && s + ns < n_stages) issue(s + ns); // the slot is drained: re-arm it
+            if (lane == 0 && s + ns < n_stages) issue(warp, s + ns); // the slot is drained: re-arm it
         }
         // ---- epilogue
         const int row = oct * 8 + r;
@@ -279,6 +325,29 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             const float g = ps_rw_row_result(acc[0]);
             const float u = ps_rw_row_result(acc[RPT - 1]);
             if (q == 0 && row < a.seg[0].row_end) a.seg[0].dst[row] = ps_silu_mul(g, u);
+            if (a.xq_out) {
+                const int i = oct >> 5; // 32 octets per 256-row block
+                __syncwarp();
+                int old = 0;
+                if (lane == 0) // release: the warp's h stores above; acquire: the other warps' before we read the block
+                    asm volatile("atom.acq_rel.gpu.global.add.s32 %0, [%1], 1;" : "=r"(old) : "l"(a.blk_cnt + i) : "memory");
+                old = __shfl_sync(PS_FULL, old, 0);
+                const int expect = min(32, a.n_oct - i * 32);
+                if (old == expect - 1) { // this warp completed the block: quantise it (quantize_row_q8_K_ref, one warp)
+                    const float4 v0 = __ldcg(reinterpret_cast<const float4 *>(a.seg[0].dst + i * 256 + 4 * lane));
+                    const float4 v1 = __ldcg(reinterpret_cast<const float4 *>(a.seg[0].dst + i * 256 + 128 + 4 * lane));
+                    const float e[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+                    uint32_t words[2], bsp4;
+                    float yd;
+                    ps_quant_block_q8k_regs(e, lane, words, yd, bsp4);
+                    uint32_t *qw = reinterpret_cast<uint32_t *>(a.xq_out) + (size_t)i * 64;
+                    const int l = lane & 7, jA = lane >> 3, jB = 4 + (lane >> 3);
+                    qw[((jA >> 1) * 4 + (l >> 1)) * 4 + (jA & 1) * 2 + (l & 1)] = words[0];
+                    qw[((jB >> 1) * 4 + (l >> 1)) * 4 + (jB & 1) * 2 + (l & 1)] = words[1];
+                    if (lane < 4) reinterpret_cast<uint2 *>(a.xq_out + (size_t)a.n_oct * 8)[i * 4 + lane] = make_uint2(__float_as_uint(yd), bsp4);
+                    if (lane == 0) a.blk_cnt[i] = 0;
+                }
+            }
         } else {
             float res = ps_rw_row_result(acc[0]);
             int sg = 0;
@@ -319,7 +388,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
         }
         if (lane == 0) { sv[warp] = best_v; si[warp] = best_i; }
-        __syncthreads();
+        ps_bar_sync(2, PS_RW_THREADS);
         if (tid == 0) {
             for (int t = 1; t < PS_RW_WARPS; t++)
                 if (sv[t] > best_v || (sv[t] == best_v && si[t] < best_i)) { best_v = sv[t]; best_i = si[t]; }
@@ -327,6 +396,6 @@ __global__ void __launch_bounds__(PS_RW_THREADS, 1) ps_k_rw_matvec(const PsRwArg
             a.part_idx[blockIdx.x] = best_i;
         }
     }
-    __syncthreads();
+    ps_bar_sync(2, PS_RW_THREADS);
     ps_tl_max(a.tl, 1);
 }

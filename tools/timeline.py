@@ -24,12 +24,13 @@ m = capi.CudaModel(desc=desc, tensors=tmap)
 m.prefill(synth.random_prompt(shape.vocab_size, ctx_len + 1), 128)
 m.be.set_option("pdl", 0 if "--nopdl" in sys.argv else 1)
 m.be.set_option("graph", 0 if "--nograph" in sys.argv else 1)
-m.decode_greedy(1, 4)
-ms = m.be.counter("last_device_ns") / 1e6 / 4
+m.decode_greedy(1, 4)          # graph capture + warm-up
+m.decode_greedy(1, 16)
+ms = m.be.counter("last_device_ns") / 1e6 / 16
 m.be.set_option("trace", 1)
 m.decode_greedy(1, 1)
 n = 1 + 6 * shape.n_layers + 2
-buf = np.zeros((n, 4), np.int64)
+buf = np.zeros((n, 8), np.int64)
 m.be._ck(m.be.L.ps_cuda_read_trace(m.be.h, buf.ctypes.data, n))
 m.be.set_option("trace", 0)
 names = ["EMBED"] + ["QKV", "ATTN1", "ATTN2", "WO", "GATEUP", "DOWN"] * shape.n_layers + ["LMHEAD", "ARGMAX"]
@@ -39,12 +40,13 @@ print(f"{'#':>3s} {'kernel':7s} {'start':>8s} {'dep_ok':>7s} {'pro_ok':>7s} {'en
 prev_end = t0
 tot = {}
 for k in range(n):
-    s, e, d, p = buf[k]
+    s, e, d, p = buf[k][:4]
+    extra = " ".join(f"{v / 1e3:5.2f}" for v in buf[k][4:7]) if buf[k][4:7].any() else ""
     f = lambda v: (v - t0) / 1e3
     dep = f"{f(d):7.2f}" if d < 2**62 else "      -"
     pro = (f"{f(p):7.2f}" if p > 10**9 else f"{p / 1e3:6.2f}d") if p > 0 else "      -"
     if k < 14 or k >= n - 3:
-        print(f"{k:3d} {names[k]:7s} {f(s):8.2f} {dep} {pro} {f(e):8.2f} {(e - s) / 1e3:6.2f} {(s - prev_end) / 1e3:6.2f}")
+        print(f"{k:3d} {names[k]:7s} {f(s):8.2f} {dep} {pro} {f(e):8.2f} {(e - s) / 1e3:6.2f} {(s - prev_end) / 1e3:6.2f}  {extra}")
     tot.setdefault(names[k], []).append(((e - max(s, prev_end)) / 1e3, (e - prev_end) / 1e3))
     prev_end = e
 print("per-kernel-kind mean exclusive time (end - max(start, prev end)) and step share (end - prev end):")
