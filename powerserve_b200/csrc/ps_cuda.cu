@@ -69,6 +69,7 @@ struct ps_cuda_ctx {
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
+    uint8_t *ximg = nullptr;   // Q8_K images of up to max_batch activation columns (multi-column row-walker)
     uint8_t *hq = nullptr;     // Q8_K image of the FFN hidden vector, written by the gate/up epilogue for the down mat-vec
     int *blk_cnt = nullptr;    // per-256-block arrival counters of that hand-off (rest state: zero)
     float *part_val = nullptr; // per-CTA partial arg-max of the lm_head kernel (greedy pick, stage 1)
@@ -321,6 +322,51 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     return launch_rw(ctx, a, PS_EPI_SILU);
 }
 
+// ---- multi-column row-walker (prefill chunks / verify batches)
+template <int C> int launch_rwm_c(ps_cuda_ctx *ctx, PsRwmArgs a) {
+    const int nb = a.K / 256;
+    int kb = 2;
+    while (nb % kb) kb >>= 1;
+    a.kb = kb;
+    a.n_act = PS_RW_WARPS;
+    const size_t stage = (size_t)kb * PS_RW_OCTET_BLOCK, fixed = (size_t)C * ((size_t)a.K + (size_t)nb * 32);
+    const size_t budget = 212 * 1024;
+    if (fixed + (size_t)PS_RW_WARPS * 2 * (stage + 8) > budget) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matmul: K=%d does not fit", a.K);
+    a.ns = (int)std::min<size_t>(PS_RW_MAX_NS, (budget - fixed) / ((size_t)PS_RW_WARPS * (stage + 8)));
+    const size_t smem = fixed + (size_t)PS_RW_WARPS * a.ns * (stage + 8);
+    const int n_units = ((a.bs + C - 1) / C) * ((a.n_oct + PS_RW_WARPS - 1) / PS_RW_WARPS);
+    const int grid = std::min(ctx->n_sm, n_units);
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matmul<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        attr[ctx->device] = true;
+    }
+    ps_k_rw_matmul<C><<<grid, PS_RW_THREADS + 32, smem, ctx->stream>>>(a);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+// quantise bs columns of K floats into Q8_K images (ctx->ximg), then dst = W . x on the octet-interleaved weights
+int rwm_quantize(ps_cuda_ctx *ctx, const float *x, int K, int bs) {
+    ps_k_rw_quant_img<<<dim3((unsigned)((K / 256 + 3) / 4), (unsigned)bs), 128, 0, ctx->stream>>>(x, K, ctx->ximg);
+    PS_LAUNCH_CK();
+    return 0;
+}
+int launch_rwm(ps_cuda_ctx *ctx, PsRwmArgs a) {
+    a.x_img = ctx->ximg;
+    const size_t img = (size_t)a.K + (size_t)(a.K / 256) * 32;
+    if (16 * img <= 100 * 1024 && a.bs > 8) return launch_rwm_c<16>(ctx, a);
+    if (8 * img <= 140 * 1024 && a.bs > 4) return launch_rwm_c<8>(ctx, a);
+    return launch_rwm_c<4>(ctx, a);
+}
+int rwm_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, int slot, int n_slots, float *dst, int bs, const float *bias, const float *residual) {
+    PsRwmArgs a{};
+    a.w = w; a.n_oct = (n_rows + 7) / 8; a.K = K; a.slot = slot; a.n_slots = n_slots; a.n_seg = 1; a.bs = bs;
+    a.seg[0] = {dst, bias, 0, n_rows, 0};
+    a.residual = residual;
+    return launch_rwm(ctx, a);
+}
+
 // one decode step on the token in tokens_dev[0] at position pos_dev[0]; `pick`: run the greedy pick + bookkeeping
 int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     const ps_cuda_model_desc &d = ctx->d;
@@ -451,6 +497,7 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
+    PS_AL(ctx->ximg, (size_t)B * ((size_t)ctx->maxK + (size_t)(ctx->maxK / 256 + 1) * 32));
     PS_AL(ctx->hq, (size_t)d.ffn_dim + (size_t)(d.ffn_dim / 256 + 1) * 32);
     PS_AL(ctx->blk_cnt, 4 * (size_t)(d.ffn_dim / 256 + 1));
     PS_CKC(cudaMemsetAsync(ctx->blk_cnt, 0, 4 * (size_t)(d.ffn_dim / 256 + 1), ctx->stream));
@@ -786,6 +833,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
     const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
     const int64_t n_kv = (int64_t)pos0 + bs; // pos.back() + 1
     const float kq_scale = 1.0f / sqrtf((float)hs);
+    const bool rw = ctx->fused_ok && ctx->opt_fused && bs > 1; // octet-interleaved copies exist: multi-column row-walker
     int rc;
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
     PS_LAUNCH_CK();
@@ -795,10 +843,20 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         const LayerDev &ld = ctx->layers[L];
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if ((rc = quantize_act(ctx, ld.tq, ctx->xn, dim, bs))) return rc;
-        if ((rc = matmul_q(ctx, ctx->q, ld.wq, ld.tq, dim, qdim, bs, d.qkv_bias ? ld.q_bias : nullptr, nullptr))) return rc;
-        if ((rc = matmul_q(ctx, ctx->k, ld.wk, ld.tk, dim, kvd, bs, d.qkv_bias ? ld.k_bias : nullptr, nullptr))) return rc;
-        if ((rc = matmul_q(ctx, ctx->v, ld.wv, ld.tv, dim, kvd, bs, d.qkv_bias ? ld.v_bias : nullptr, nullptr))) return rc;
+        if (rw) { // q | k | v rows in one pass over the concatenated octets
+            if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+            PsRwmArgs a{};
+            a.w = ld.rw_qkv; a.n_oct = (int)((qdim + 2 * kvd) / 8); a.K = (int)dim; a.slot = 0; a.n_slots = 1; a.n_seg = 3; a.bs = bs;
+            a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, (int)qdim, 0};
+            a.seg[1] = {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, (int)qdim, (int)(qdim + kvd), 0};
+            a.seg[2] = {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, (int)(qdim + kvd), (int)(qdim + 2 * kvd), 0};
+            if ((rc = launch_rwm(ctx, a))) return rc;
+        } else {
+            if ((rc = quantize_act(ctx, ld.tq, ctx->xn, dim, bs))) return rc;
+            if ((rc = matmul_q(ctx, ctx->q, ld.wq, ld.tq, dim, qdim, bs, d.qkv_bias ? ld.q_bias : nullptr, nullptr))) return rc;
+            if ((rc = matmul_q(ctx, ctx->k, ld.wk, ld.tk, dim, kvd, bs, d.qkv_bias ? ld.k_bias : nullptr, nullptr))) return rc;
+            if ((rc = matmul_q(ctx, ctx->v, ld.wv, ld.tv, dim, kvd, bs, d.qkv_bias ? ld.v_bias : nullptr, nullptr))) return rc;
+        }
         ps_k_rope<<<dim3((unsigned)nh, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->qr, ctx->q, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
         PS_LAUNCH_CK();
         ps_k_rope<<<dim3((unsigned)nkv, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
@@ -809,25 +867,53 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         PS_LAUNCH_CK();
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
-        ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        if (bs > 1 && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
+            static bool pv_attr = false;
+            if (!pv_attr) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr = true; }
+            ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
+                ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        } else {
+            ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        }
         PS_LAUNCH_CK();
-        if ((rc = quantize_act(ctx, ld.to, ctx->att, qdim, bs))) return rc;
-        if ((rc = matmul_q(ctx, ctx->x, ld.wo, ld.to, qdim, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wo.att
+        if (rw) {
+            if ((rc = rwm_quantize(ctx, ctx->att, (int)qdim, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_o, (int)dim, (int)qdim, 0, 1, ctx->x, bs, nullptr, ctx->x))) return rc;
+        } else {
+            if ((rc = quantize_act(ctx, ld.to, ctx->att, qdim, bs))) return rc;
+            if ((rc = matmul_q(ctx, ctx->x, ld.wo, ld.to, qdim, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wo.att
+        }
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.ffn_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if ((rc = quantize_act(ctx, ld.tgate, ctx->xn, dim, bs))) return rc;
-        if ((rc = matmul_q(ctx, ctx->g, ld.wgate, ld.tgate, dim, ffn, bs, nullptr, nullptr))) return rc;
-        if ((rc = matmul_q(ctx, ctx->u, ld.wup, ld.tup, dim, ffn, bs, nullptr, nullptr))) return rc;
+        if (rw) {
+            if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn, (int)dim, 0, 2, ctx->g, bs, nullptr, nullptr))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn, (int)dim, 1, 2, ctx->u, bs, nullptr, nullptr))) return rc;
+        } else {
+            if ((rc = quantize_act(ctx, ld.tgate, ctx->xn, dim, bs))) return rc;
+            if ((rc = matmul_q(ctx, ctx->g, ld.wgate, ld.tgate, dim, ffn, bs, nullptr, nullptr))) return rc;
+            if ((rc = matmul_q(ctx, ctx->u, ld.wup, ld.tup, dim, ffn, bs, nullptr, nullptr))) return rc;
+        }
         ps_k_silu_hadamard<<<grid1d(ffn * bs), 256, 0, ctx->stream>>>(ctx->g, ctx->g, ctx->u, ffn * bs);
         PS_LAUNCH_CK();
-        if ((rc = quantize_act(ctx, ld.tdown, ctx->g, ffn, bs))) return rc;
-        if ((rc = matmul_q(ctx, ctx->x, ld.wdown, ld.tdown, ffn, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wdown.h
+        if (rw) {
+            if ((rc = rwm_quantize(ctx, ctx->g, (int)ffn, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_down, (int)dim, (int)ffn, 0, 1, ctx->x, bs, nullptr, ctx->x))) return rc;
+        } else {
+            if ((rc = quantize_act(ctx, ld.tdown, ctx->g, ffn, bs))) return rc;
+            if ((rc = matmul_q(ctx, ctx->x, ld.wdown, ld.tdown, ffn, dim, bs, nullptr, ctx->x))) return rc; // x = x + Wdown.h
+        }
     }
     if (lm_head) {
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ctx->w_out_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if ((rc = quantize_act(ctx, ctx->t_out, ctx->xn, dim, bs))) return rc;
-        if ((rc = matmul_q(ctx, ctx->logits, ctx->w_out, ctx->t_out, dim, d.vocab_size, bs, nullptr, nullptr))) return rc;
+        if (rw) {
+            if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = rwm_single(ctx, ctx->rw_out, d.vocab_size, (int)dim, 0, 1, ctx->logits, bs, nullptr, nullptr))) return rc;
+        } else {
+            if ((rc = quantize_act(ctx, ctx->t_out, ctx->xn, dim, bs))) return rc;
+            if ((rc = matmul_q(ctx, ctx->logits, ctx->w_out, ctx->t_out, dim, d.vocab_size, bs, nullptr, nullptr))) return rc;
+        }
     }
     return 0;
 }

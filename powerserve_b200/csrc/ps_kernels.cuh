@@ -600,6 +600,67 @@ __global__ void __launch_bounds__(128) ps_k_attn_pv(float *__restrict__ out, con
         }
 }
 
+// Same operator for batches (prefill chunks): one CTA per (block of 8 queries, head).  The 8 probability rows sit in
+// shared memory for the whole kernel; each warp then streams V^T rows (one output dim d at a time, 16 loads in flight)
+// against all 8 queries, so P is read once and V^T is re-read from L2 only once per 8 queries.  Per-lane FMA chains,
+// reduction and leftovers are those of ggml_vec_dot_f32 (ggml.c:2092-2131), exactly as in ps_k_attn_pv.
+#define PS_PV_QB 8
+__global__ void __launch_bounds__(256) ps_k_attn_pv_batch(float *__restrict__ out, const float *__restrict__ vct, const float *__restrict__ p,
+                                                          int hs, int n_heads, int n_kv_heads, int64_t n_kv, int64_t n_ctx, int bs) {
+    extern __shared__ float s_pq[]; // [PS_PV_QB][n_kv]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.x * PS_PV_QB, h = blockIdx.y, g = h / (n_heads / n_kv_heads);
+    const int nq = min(PS_PV_QB, bs - i0);
+    for (int qi = 0; qi < nq; qi++) {
+        const float *pr = p + ((int64_t)h * bs + i0 + qi) * n_kv;
+        for (int64_t j = tid; j < n_kv; j += 256) s_pq[qi * n_kv + j] = pr[j];
+    }
+    __syncthreads();
+    const int64_t np = n_kv & ~(int64_t)31;
+    const int ntail = (int)(n_kv - np);
+    for (int d = warp; d < hs; d += 8) {
+        const float *vrow = vct + ((int64_t)g * hs + d) * n_ctx;
+        float sum[PS_PV_QB];
+#pragma unroll
+        for (int qi = 0; qi < PS_PV_QB; qi++) sum[qi] = 0.f;
+        const float vtail = (lane < ntail) ? vrow[np + lane] : 0.f;
+        for (int64_t s0 = 0; s0 < np; s0 += 512) {
+            float vv[16];
+#pragma unroll
+            for (int u = 0; u < 16; u++) vv[u] = (s0 + 32 * u < np) ? vrow[s0 + 32 * u + lane] : 0.f;
+#pragma unroll
+            for (int u = 0; u < 16; u++)
+                if (s0 + 32 * u < np) {
+#pragma unroll
+                    for (int qi = 0; qi < PS_PV_QB; qi++)
+                        if (qi < nq) sum[qi] = __fmaf_rn(vv[u], s_pq[qi * n_kv + s0 + 32 * u + lane], sum[qi]);
+                }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; k++) { // GGML_F32x8_REDUCE butterfly (see ps_f32x8_reduce), interleaved over the queries
+            const int step = (k == 0) ? 16 : (k == 1) ? 8 : (k == 2) ? 4 : (k == 3) ? 1 : 2;
+            float o[PS_PV_QB];
+#pragma unroll
+            for (int qi = 0; qi < PS_PV_QB; qi++) o[qi] = __shfl_xor_sync(PS_FULL, sum[qi], step);
+#pragma unroll
+            for (int qi = 0; qi < PS_PV_QB; qi++) sum[qi] = __fadd_rn(sum[qi], o[qi]);
+        }
+        for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order
+            const float v = __shfl_sync(PS_FULL, vtail, t);
+#pragma unroll
+            for (int qi = 0; qi < PS_PV_QB; qi++)
+                if (qi < nq) sum[qi] = __fadd_rn(sum[qi], __fmul_rn(v, s_pq[qi * n_kv + np + t]));
+        }
+        if (lane < nq) {
+            float v = sum[0];
+#pragma unroll
+            for (int qi = 1; qi < PS_PV_QB; qi++)
+                if (lane == qi) v = sum[qi];
+            out[((int64_t)(i0 + lane) * n_heads + h) * hs + d] = v;
+        }
+    }
+}
+
 // GGMLBackend::silu_hadamard (src/backend/ggml/ggml.cpp:115-129)
 __global__ void ps_k_silu_hadamard(float *__restrict__ dst, const float *__restrict__ g, const float *__restrict__ u, int64_t n) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)

@@ -399,3 +399,175 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     ps_bar_sync(2, PS_RW_THREADS);
     ps_tl_max(a.tl, 1);
 }
+
+// ====================================================================================================================
+// Multi-column row-walker: dst{N, bs} = W{K, N} . x{K, bs} for prefill chunks and speculative-verify batches.
+// Same exact arithmetic per column as the mat-vec above (each column owns its FMA chains), same octet-interleaved weights
+// and per-warp TMA rings; a weight block is unpacked ONCE and then multiplied with the C columns of the current column
+// group, whose Q8_K images sit in shared memory.  The CTA's weight slice is re-streamed (from L2) once per column group.
+// ====================================================================================================================
+struct PsRwmArgs {
+    const uint8_t *w;      // repacked weights: [n_oct][nb][n_slots][1152]
+    int n_oct, K, kb, ns, n_act;
+    int slot, n_slots;     // which interleaved matrix of the buffer (gate | up)
+    PsRwSeg seg[3];        // dst of a segment is [bs][rows of the segment]; mode unused
+    int n_seg;
+    const uint8_t *x_img;  // Q8_K images of the activation columns: [bs][K + nb * 32]
+    int bs;
+    const float *residual; // optional, same layout as seg[0].dst (single-segment calls only)
+};
+
+// (RMSNorm output or any fp32 activation) -> Q8_K shared-memory image, one warp per (256-block, column)
+__global__ void __launch_bounds__(128) ps_k_rw_quant_img(const float *__restrict__ x, int64_t K, uint8_t *__restrict__ img) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int64_t nb = K / 256, i = (int64_t)blockIdx.x * 4 + warp, col = blockIdx.y;
+    if (i >= nb) return;
+    float e[8];
+    ps_rw_load8(x + col * K + i * 256, lane, e);
+    uint8_t *base = img + col * (K + nb * 32);
+    ps_rw_quant_store(e, lane, reinterpret_cast<uint32_t *>(base) + i * 64, reinterpret_cast<uint2 *>(base + K) + i * 4);
+}
+
+// Work decomposition: a UNIT is (tile of PS_RW_WARPS octets = 128 rows, column group of C columns); units are dealt
+// round-robin to the persistent CTAs, and inside a unit warp w owns octet w of the tile, so all warps are busy however
+// few rows the matrix has.  A warp's weight stream is simply the concatenation of its octets over the CTA's units.
+template <int C>
+__global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const PsRwmArgs a) {
+    extern __shared__ __align__(128) uint8_t ps_rw_smem[];
+    __shared__ __align__(8) uint64_t xbar;
+    const int K = a.K, nb = K / 256, kb = a.kb, ns = a.ns;
+    const uint32_t img_bytes = (uint32_t)K + (uint32_t)nb * 32;
+    const uint32_t stage_bytes = (uint32_t)kb * PS_RW_OCTET_BLOCK;
+    uint8_t *s_act = ps_rw_smem;                                   // [C][img_bytes]
+    uint8_t *s_ring = ps_rw_smem + (size_t)C * img_bytes;
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + (size_t)PS_RW_WARPS * ns * stage_bytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
+    const int spo = nb / kb;
+    const int n_cg = (a.bs + C - 1) / C, n_tiles = (a.n_oct + PS_RW_WARPS - 1) / PS_RW_WARPS;
+    const int n_units = n_cg * n_tiles;                            // unit u = (tile u / n_cg, column group u % n_cg)
+    const int my_units = (n_units > (int)blockIdx.x) ? (n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    // stage #s of warp w: unit s / spo of this CTA (octets beyond n_oct are skipped by both sides: they own no stages)
+    auto issue = [&](int w, int s) {
+        const int u = (int)blockIdx.x + (s / spo) * (int)gridDim.x;
+        const int oct = (u / n_cg) * PS_RW_WARPS + w;
+        uint64_t *bar = s_bar + w * ns + (s % ns);
+        uint8_t *dst = s_ring + ((size_t)w * ns + (s % ns)) * stage_bytes;
+        ps_mbar_expect_tx(bar, stage_bytes);
+        for (int b = 0; b < kb; b++) {
+            const int oo = min(oct, a.n_oct - 1); // a ragged last tile re-reads a valid octet; its results are discarded
+            const uint8_t *src = a.w + (((size_t)oo * nb + (size_t)(s % spo) * kb + b) * a.n_slots + a.slot) * PS_RW_OCTET_BLOCK;
+            ps_bulk_g2s(dst + (size_t)b * PS_RW_OCTET_BLOCK, src, PS_RW_OCTET_BLOCK, bar);
+        }
+    };
+    const int n_stages = my_units * spo;
+    if (warp == PS_RW_WARPS) { // helper warp: barrier init + first ring fill (lane w serves warp w)
+        if (lane < PS_RW_WARPS)
+            for (int s = 0; s < ns; s++) ps_mbar_init(s_bar + lane * ns + s, 1);
+        if (lane == 0) ps_mbar_init(&xbar, 1);
+        ps_fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        __syncwarp();
+        asm volatile("bar.arrive 1, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
+        if (lane < PS_RW_WARPS)
+            for (int s = 0; s < ns && s < n_stages; s++) issue(lane, s);
+        return;
+    }
+    ps_bar_sync(1, PS_RW_THREADS + 32);
+    uint8_t *my_ring = s_ring + (size_t)warp * ns * stage_bytes;
+    uint64_t *my_bar = s_bar + warp * ns;
+    int s = 0;
+#pragma unroll 1
+    for (int mu = 0; mu < my_units; mu++) {
+        const int u = (int)blockIdx.x + mu * (int)gridDim.x;
+        const int col0 = (u % n_cg) * C, ncol = min(C, a.bs - col0);
+        const int oct = (u / n_cg) * PS_RW_WARPS + warp;
+        ps_bar_sync(2, PS_RW_THREADS); // everyone is done with the previous unit's images
+        if (tid == 0) {
+            ps_mbar_expect_tx(&xbar, (uint32_t)ncol * img_bytes);
+            for (int c = 0; c < ncol; c++) ps_bulk_g2s(s_act + (size_t)c * img_bytes, a.x_img + (size_t)(col0 + c) * img_bytes, img_bytes, &xbar);
+        }
+        ps_mbar_wait(&xbar, mu & 1);
+        {
+            PsRwAcc acc[C];
+#pragma unroll
+            for (int c = 0; c < C; c++) acc[c].a0 = acc[c].a1 = acc[c].am = 0.f;
+#pragma unroll 1
+            for (int sb = 0; sb < spo; sb++, s++) {
+                const int slot = s % ns;
+                ps_mbar_wait(&my_bar[slot], (s / ns) & 1);
+                const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
+#pragma unroll 1
+                for (int b = 0; b < kb; b++) {
+                    const int i = sb * kb + b;
+                    const uint8_t *ob = st + (size_t)b * PS_RW_OCTET_BLOCK;
+                    // ---- unpack the weight block once (see ps_rw_block)
+                    const uint4 h = *reinterpret_cast<const uint4 *>(ob + 16 * r);
+                    const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
+                    const uint32_t scA = h.y & k1, scB = (h.w & k2) | (((h.y >> 6) & k3) << 4);
+                    const uint32_t mA = h.z & k1, mB = ((h.w >> 4) & k2) | (((h.z >> 6) & k3) << 4);
+                    uint32_t lo[8], hi[8];
+                    int s_lo[4], s_hi[4];
+#pragma unroll
+                    for (int j2 = 0; j2 < 4; j2++) {
+                        const uint2 w = *reinterpret_cast<const uint2 *>(ob + 128 + 256 * j2 + 32 * r + 8 * q);
+                        lo[2 * j2] = w.x & 0x0f0f0f0fu; lo[2 * j2 + 1] = w.y & 0x0f0f0f0fu;
+                        hi[2 * j2] = w.x & 0xf0f0f0f0u; hi[2 * j2 + 1] = w.y & 0xf0f0f0f0u;
+                        const uint32_t scw = (j2 < 2) ? scA : scB;
+                        s_lo[j2] = (scw >> (16 * (j2 & 1))) & 0xff;
+                        s_hi[j2] = (scw >> (16 * (j2 & 1) + 8)) & 0xff;
+                    }
+                    const uint32_t mw = (q < 2) ? mA : mB;
+                    const int m0 = (mw >> (16 * (q & 1))) & 0xff, m1 = (mw >> (16 * (q & 1) + 8)) & 0xff;
+                    const float xd = ps_half_bits_to_float(h.x & 0xffffu), xmin = ps_half_bits_to_float(h.x >> 16);
+                    // ---- every column of the group
+#pragma unroll
+                    for (int c = 0; c < C; c++) {
+                        if (c < ncol) {
+                            const uint4 *qa = reinterpret_cast<const uint4 *>(s_act + (size_t)c * img_bytes) + (size_t)i * 16;
+                            const uint2 meta = reinterpret_cast<const uint2 *>(s_act + (size_t)c * img_bytes + K)[i * 4 + q];
+                            int S0 = 0, S1 = 0, H0 = 0, H1 = 0;
+#pragma unroll
+                            for (int j2 = 0; j2 < 4; j2++) {
+                                const uint4 av = qa[j2 * 4 + q];
+                                S0 += s_lo[j2] * __dp4a((int)lo[2 * j2], (int)av.x, 0);
+                                S1 += s_lo[j2] * __dp4a((int)lo[2 * j2 + 1], (int)av.y, 0);
+                                H0 += s_hi[j2] * ps_dp4a_us(hi[2 * j2], (int)av.z, 0);
+                                H1 += s_hi[j2] * ps_dp4a_us(hi[2 * j2 + 1], (int)av.w, 0);
+                            }
+                            S0 += H0 >> 4;
+                            S1 += H1 >> 4;
+                            const int P = m0 * (int)(short)(meta.y & 0xffffu) + m1 * (int)(short)(meta.y >> 16);
+                            const float yd = __uint_as_float(meta.x);
+                            const float d = __fmul_rn(yd, xd), dm = __fmul_rn(-yd, xmin);
+                            acc[c].a0 = __fmaf_rn(d, __int2float_rn(S0), acc[c].a0);
+                            acc[c].a1 = __fmaf_rn(d, __int2float_rn(S1), acc[c].a1);
+                            acc[c].am = __fmaf_rn(dm, __int2float_rn(P), acc[c].am);
+                        }
+                    }
+                }
+                __syncwarp();
+                if (lane == 0 && s + ns < n_stages) issue(warp, s + ns);
+            }
+            // ---- epilogue: bias / residual, dst[col][row]
+            const int row = oct * 8 + r;
+            int sg = 0;
+            if (a.n_seg > 1 && row >= a.seg[1].row_begin) sg = 1;
+            if (a.n_seg > 2 && row >= a.seg[2].row_begin) sg = 2;
+            const bool live = row < a.seg[sg].row_end;
+            const int n = row - a.seg[sg].row_begin, ld = a.seg[sg].row_end - a.seg[sg].row_begin;
+            const float bias = (live && a.seg[sg].bias) ? a.seg[sg].bias[n] : 0.f;
+#pragma unroll
+            for (int c = 0; c < C; c++) {
+                if (c < ncol) {
+                    float res = ps_rw_row_result(acc[c]);
+                    if (q == 0 && live) {
+                        const size_t o = (size_t)(col0 + c) * ld + n;
+                        if (a.seg[sg].bias) res = __fadd_rn(res, bias);
+                        if (a.residual) res = __fadd_rn(a.residual[o], res);
+                        a.seg[sg].dst[o] = res;
+                    }
+                }
+            }
+        }
+    }
+}
