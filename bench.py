@@ -195,6 +195,17 @@ def main():
         dev_ms = model.be.counter("last_device_ns") / 1e6
     launches = model.be.counter("kernel_launches") - l0
     barrier()
+    # --- roofline leg: the dominant kernel (the row-walker Q4_K mat-vec, 5 launch sites per step: q|k|v, o, gate|up, down,
+    # lm_head) timed launch by launch with CUDA events on the backend stream (un-graphed, no PDL overlap, same step sequence)
+    model.be.kv_rollback(args.steps)
+    k_steps = min(args.steps, 16)
+    model.be.set_option("ktime", 1)
+    model.decode_greedy(tok, 2)
+    model.decode_greedy(tok, k_steps)
+    mv_ns, mv_n = model.be.counter("matvec_kernel_ns"), model.be.counter("matvec_kernel_launches")
+    model.be.set_option("ktime", 0)
+    model.be.kv_rollback(2 + k_steps)
+    barrier()
     # --- e2e: host token -> ps_cuda_forward -> host logits, every step
     model.be.kv_rollback(args.steps)
     h0, d0 = model.be.counter("h2d_bytes"), model.be.counter("d2h_bytes")
@@ -215,7 +226,14 @@ def main():
         ms_dev, e2e_ms = tt.tolist()
     value = world * args.steps / (ms_dev / 1e3)
     e2e_value = world * args.steps / (e2e_ms / 1e3)
-    achieved = wbytes * args.steps / (ms_dev / 1e3) / 1e9  # per GPU
+    step_gbs = wbytes * args.steps / (ms_dev / 1e3) / 1e9  # per GPU, whole step
+    mv_bytes_per_launch = wbytes * k_steps / max(mv_n, 1)          # algorithmic bytes of an average mat-vec launch
+    mv_avg_s = mv_ns / 1e9 / max(mv_n, 1)
+    achieved = mv_bytes_per_launch / max(mv_avg_s, 1e-12) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "ncu_matvec_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get(args.model, {}).get("dram_bytes_per_launch")
     out = {"metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
            "dtype": "int8xint4 dot, fp32 accumulate (bit-exact with the ggml CPU reference)", "data": "synthetic", "config": cfg,
@@ -223,8 +241,12 @@ def main():
            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
-                        "traffic": None, "peak_source": peak_src,
-                        "what": "decode step: algorithmic weight bytes per token / CUDA-event step time"},
+                        "traffic": traffic, "peak_source": peak_src + ", sustained copy",
+                        "kernel": "ps_k_rw_matvec (row-walker Q4_K mat-vec, all launch sites of the decode step)",
+                        "bytes_per_launch": mv_bytes_per_launch, "avg_launch_us": mv_avg_s * 1e6, "launches_timed": int(mv_n),
+                        "what": "algorithmic GGUF weight bytes per mat-vec launch / average launch duration (CUDA events on the backend stream)",
+                        "step": {"achieved": step_gbs, "frac": step_gbs / hbm_peak,
+                                 "what": "whole decode step incl. attention, prologues and launch gaps: weight bytes per token / step time"}},
            "clocks": clk.summary(), "greedy_ids_head": [int(x) for x in ids[:8]]}
     if rank == 0 and not args.no_cpu_baseline:
         try:

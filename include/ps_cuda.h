@@ -134,14 +134,19 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
 const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
 
 /* execution switches (0/1): "graph" = replay the decode step as a captured CUDA graph, "fused" = fused decode
- * kernels instead of one kernel per table op.  Both produce bit-identical results; they exist so tests can prove it. */
+ * kernels instead of one kernel per table op, "pdl" = programmatic dependent launch between the fused kernels.  All
+ * produce bit-identical results; they exist so tests can prove it.  "ktime" = 1 runs the fused step un-graphed with
+ * CUDA events around every mat-vec launch (bench.py's roofline leg); "trace" = 1 records a per-kernel device timeline. */
 int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
 /* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes",
- * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call) */
+ * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call),
+ * "matvec_kernel_ns" / "matvec_kernel_launches" (option "ktime": summed event time / count of the mat-vec launches of
+ * the last decode_greedy call) */
 int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name);
 
-/* debug: with option "trace" = 1 the fused mat-vec records per-CTA globaltimer stamps (16 per CTA, 148 CTAs, ring of
- * 256 launches); read them back here.  Not used in production. */
+/* debug: with option "trace" = 1 every kernel of the fused decode step records globaltimer stamps into its slot
+ * (8 x int64 per launch: first start, last end, first dependency-resolved, slowest prologue, 3 prologue probes, spare;
+ * at most 512 launches); read the first n_launches slots back here.  Not used in production. */
 int ps_cuda_read_trace(ps_cuda_ctx *ctx, long long *host, int n_launches);
 
 /* host-side restatement of glibc expf used by the device code; exported so CPU-only tests can pin it against libm */

@@ -64,7 +64,11 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0;
+    std::vector<cudaEvent_t> kt_events; // option "ktime": event pairs around every row-walker mat-vec launch
+    size_t kt_used = 0;
+    double kt_ms = 0.0;                 // summed mat-vec kernel time of the last decode call
+    int64_t kt_launches = 0;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
@@ -219,7 +223,7 @@ int launch_k(ps_cuda_ctx *ctx, void (*kern)(KArgs...), dim3 grid, dim3 block, si
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = ctx->opt_pdl ? 1 : 0;
+    cfg.numAttrs = (ctx->opt_pdl && !ctx->opt_ktime) ? 1 : 0;
     cudaError_t e = cudaLaunchKernelEx(&cfg, kern, KArgs(args)...);
     ctx->n_launch++;
     if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "kernel launch failed: %s", cudaGetErrorString(e));
@@ -240,7 +244,22 @@ int rw_repack(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int64_t n_rows
     return 0;
 }
 
+int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi);
 int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
+    if (!ctx->opt_ktime) return launch_rw_impl(ctx, a, epi);
+    // kernel timing pass: CUDA events on the launching stream around this launch (no graph, no PDL overlap)
+    while (ctx->kt_events.size() < ctx->kt_used + 2) {
+        cudaEvent_t e;
+        PS_CK(cudaEventCreate(&e));
+        ctx->kt_events.push_back(e);
+    }
+    PS_CK(cudaEventRecord(ctx->kt_events[ctx->kt_used], ctx->stream));
+    int rc = launch_rw_impl(ctx, a, epi);
+    PS_CK(cudaEventRecord(ctx->kt_events[ctx->kt_used + 1], ctx->stream));
+    ctx->kt_used += 2;
+    return rc;
+}
+int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     a.tl = tl_slot(ctx);
     a.inv_k = (a.K & (a.K - 1)) == 0 ? 1.0 / (double)a.K : 0.0;
     const int nb = a.K / 256, rpt = (epi == PS_EPI_SILU) ? 2 : 1;
@@ -402,7 +421,7 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
 
 // capture one step into a graph (lazily), then replay it
 int run_step(ps_cuda_ctx *ctx, bool pick) {
-    if (!ctx->opt_graph) return decode_step_fused(ctx, true, pick);
+    if (!ctx->opt_graph || ctx->opt_ktime) return decode_step_fused(ctx, true, pick);
     cudaGraphExec_t &ge = pick ? ctx->g_step : ctx->g_fwd;
     if (!ge) {
         cudaGraph_t graph = nullptr;
@@ -541,6 +560,7 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
     if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
+    for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
     if (ctx->stream) cudaStreamDestroy(ctx->stream);
@@ -990,6 +1010,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         PS_CK(cudaMemcpyAsync(ctx->pos_dev, &slot[0], 4, cudaMemcpyHostToDevice, ctx->stream));
         PS_CK(cudaMemcpyAsync(ctx->ctr_dev, &slot[1], 4, cudaMemcpyHostToDevice, ctx->stream));
         ctx->h2d += 8;
+        ctx->kt_used = 0;
         PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         for (int s = 0; s < n_steps; s++) {
             int rc = run_step(ctx, true);
@@ -998,6 +1019,15 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
         PS_CK(cudaStreamSynchronize(ctx->stream));
+        if (ctx->opt_ktime) {
+            ctx->kt_ms = 0.0;
+            for (size_t i = 0; i + 1 < ctx->kt_used; i += 2) {
+                float ms = 0.f;
+                PS_CK(cudaEventElapsedTime(&ms, ctx->kt_events[i], ctx->kt_events[i + 1]));
+                ctx->kt_ms += ms;
+            }
+            ctx->kt_launches = (int64_t)(ctx->kt_used / 2);
+        }
         { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
         memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
         ctx->d2h += (int64_t)n_steps * 4;
@@ -1034,6 +1064,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
             int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 8);
@@ -1057,7 +1088,9 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "graph_replays")) return ctx->n_graph;
     if (!strcmp(name, "h2d_bytes")) return ctx->h2d;
     if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
-    if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6); // CUDA-event time of the last forward / decode
+    if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6);
+    if (!strcmp(name, "matvec_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the mat-vec launches
+    if (!strcmp(name, "matvec_kernel_launches")) return ctx->kt_launches; // CUDA-event time of the last forward / decode
     return -1;
 }
 
