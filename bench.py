@@ -11,8 +11,10 @@ facing call (`ps_cuda_forward`: HOST token ids in, HOST logits out, every step);
 `prefill`.  Weights are synthetic random Q4_K blocks (no model files / network on the box); they are 4.2 GB per
 token, far larger than the 126 MB L2, so no explicit L2 flush is needed between steps.
 
-Multi-GPU (N > 1): until the tensor-parallel path lands the N ranks run independent replicas (weak scaling, no
-collective on the data path) and `value` is the sum over ranks.
+Multi-GPU (N > 1): ONE model row-sharded over the N GPUs (BASELINE.json configs[4], tensor parallel, strong scaling):
+every rank owns 1/N of the rows of every matrix and its own kv heads, outputs are exchanged with NCCL all-gathers inside
+the decode graph (bit-identical to one GPU).  `--replicas` runs N independent replicas instead (weak scaling, no
+collective on the data path; `value` is the sum over ranks).
 """
 from __future__ import annotations
 
@@ -124,6 +126,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of tensor parallelism")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -137,7 +140,8 @@ def main():
     cpu_threads = args.cpu_threads or max(1, min(n_cpu - 1, 32))
     cfg = {"workload": f"{args.model} Q4_K synthetic: decode 1 token/step at context {args.prompt}+ (BASELINE configs[2]: prefill {args.prompt} + decode)",
            "context": args.prompt, "prefill_batch": args.prefill_batch, "weight_bytes_per_token": wbytes,
-           "l2": "weights (>= 0.7 GB/token) exceed the 126 MB L2; no explicit flush", "parallelism": f"replicas x{world}" if world > 1 else "1 GPU"}
+           "l2": "weights (>= 0.7 GB/token) exceed the 126 MB L2; no explicit flush",
+           "parallelism": "1 GPU" if world == 1 else (f"replicas x{world}" if args.replicas else f"tp{world} (row-sharded, NCCL all-gather)")}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -165,13 +169,21 @@ def main():
 
     from powerserve_b200 import build, capi
 
+    torch.cuda.set_device(local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     build.build()
-    tensors = synth.generate_tensors(shape, args.seed + 1000 * rank)
+    tp = world if (world > 1 and not args.replicas) else 1
+    tensors = synth.generate_tensors(shape, args.seed + (1000 * rank if tp == 1 else 0))   # tensor parallel: the SAME model on every rank
     tmap = {n: gguf.GGUFTensor(n, t, tuple(s), np.ascontiguousarray(d).view(np.uint8).reshape(-1)) for n, t, s, d in tensors}
-    desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=args.prefill_batch, n_ctx=shape.n_ctx, qkv_bias=shape.qkv_bias)
-    model = capi.CudaModel(desc=desc, tensors=tmap, device=local_rank)
+    nccl_id = None
+    if tp > 1:  # rank 0's NCCL id reaches the other ranks through torch.distributed (plumbing only)
+        idt = torch.frombuffer(bytearray(capi.tp_unique_id() if rank == 0 else bytes(128)), dtype=torch.uint8).cuda()
+        dist.broadcast(idt, 0)
+        nccl_id = bytes(idt.cpu().numpy().tobytes())
+    desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=args.prefill_batch, n_ctx=shape.n_ctx, qkv_bias=shape.qkv_bias,
+                                     tp_rank=rank if tp > 1 else 0, tp_size=tp)
+    model = capi.CudaModel(desc=desc, tensors=tmap, device=local_rank, nccl_id=nccl_id)
     prompt = synth.random_prompt(shape.vocab_size, args.prompt + 1, seed=1234)
 
     # prefill (ModelTokenIterator loop: prompt[:-1] in chunks, lm_head=false), wall clock through the C ABI
@@ -224,20 +236,22 @@ def main():
         tt = torch.tensor([ms_dev, e2e_ms], device="cuda", dtype=torch.float64)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         ms_dev, e2e_ms = tt.tolist()
-    value = world * args.steps / (ms_dev / 1e3)
-    e2e_value = world * args.steps / (e2e_ms / 1e3)
-    step_gbs = wbytes * args.steps / (ms_dev / 1e3) / 1e9  # per GPU, whole step
-    mv_bytes_per_launch = wbytes * k_steps / max(mv_n, 1)          # algorithmic bytes of an average mat-vec launch
+    n_models = world if tp == 1 else 1                      # replicas decode `world` streams, a tensor-parallel group one
+    value = n_models * args.steps / (ms_dev / 1e3)
+    e2e_value = n_models * args.steps / (e2e_ms / 1e3)
+    wbytes_gpu = wbytes // tp
+    step_gbs = wbytes_gpu * args.steps / (ms_dev / 1e3) / 1e9  # per GPU, whole step
+    mv_bytes_per_launch = wbytes_gpu * k_steps / max(mv_n, 1)      # algorithmic bytes (of this GPU's shard) of an average mat-vec launch
     mv_avg_s = mv_ns / 1e9 / max(mv_n, 1)
     achieved = mv_bytes_per_launch / max(mv_avg_s, 1e-12) / 1e9
     traffic = None
-    tp = os.path.join(ROOT, "profiles", "ncu_matvec_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
-    if os.path.exists(tp):
-        traffic = json.load(open(tp)).get(args.model, {}).get("dram_bytes_per_launch")
+    tpath = os.path.join(ROOT, "profiles", "ncu_matvec_traffic.json")  # dram bytes per launch from the committed ncu --set full capture
+    if os.path.exists(tpath) and tp == 1:
+        traffic = json.load(open(tpath)).get(args.model, {}).get("dram_bytes_per_launch")
     out = {"metric": "decode_tok_s", "value": value, "unit": "tok/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak" if tp == 1 else "strong", "vs_baseline": None,
            "dtype": "int8xint4 dot, fp32 accumulate (bit-exact with the ggml CPU reference)", "data": "synthetic", "config": cfg,
-           "prefill": {"value": world * (len(prompt) - 1) / prefill_s, "unit": "tok/s", "tokens": len(prompt) - 1, "timing": "wall clock through ps_cuda_forward"},
+           "prefill": {"value": n_models * (len(prompt) - 1) / prefill_s, "unit": "tok/s", "tokens": len(prompt) - 1, "timing": "wall clock through ps_cuda_forward"},
            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
            "gpu_launches": int(launches),
            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
@@ -248,7 +262,10 @@ def main():
                         "step": {"achieved": step_gbs, "frac": step_gbs / hbm_peak,
                                  "what": "whole decode step incl. attention, prologues and launch gaps: weight bytes per token / step time"}},
            "clocks": clk.summary(), "greedy_ids_head": [int(x) for x in ids[:8]]}
-    if rank == 0 and not args.no_cpu_baseline:
+    if tp > 1:
+        out["tp"] = {"size": tp, "allgathers_per_step": (model.be.counter("tp_allgathers")) // max(1, model.be.counter("graph_replays") + 1),
+                     "note": "row sharding keeps every dot product whole: results are bit-identical to one GPU (tests/test_gpu_tp.py)"}
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
             cp = synth.random_prompt(shape.vocab_size, 17, seed=1234)
             res, kind = cpu_reference_run(shape, tensors, cp, 9, cpu_threads)

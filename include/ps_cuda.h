@@ -133,6 +133,15 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
 /* device-side logits of the last forward ([bs][vocab]) for callers that sample on the GPU */
 const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
 
+/* ---------------------------------------------------------------------------------------------- tensor parallelism
+ * One process per GPU.  A context created with desc.tp_size = N > 1 owns rows [rank * rows / N, (rank + 1) * rows / N) of
+ * EVERY matrix (bind_model slices the host tensors itself) and only its own kv heads of the cache; the sharded outputs
+ * of the fused decode step are exchanged with NCCL all-gathers on the context stream (4 per layer + 1 or 2 per token),
+ * so every dot product keeps its full K and the results stay bit-identical to one GPU.  The host side moves the
+ * 128-byte NCCL id from rank 0 to the other ranks (any transport: torch.distributed, MPI, a file). */
+int ps_cuda_tp_unique_id(void *out128);                        /* rank 0: ncclGetUniqueId */
+int ps_cuda_tp_init(ps_cuda_ctx *ctx, const void *id128);      /* every rank, after create, before the first forward */
+
 /* execution switches (0/1): "graph" = replay the decode step as a captured CUDA graph, "fused" = fused decode
  * kernels instead of one kernel per table op, "pdl" = programmatic dependent launch between the fused kernels.  All
  * produce bit-identical results; they exist so tests can prove it.  "ktime" = 1 runs the fused step un-graphed with
@@ -141,7 +150,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
 /* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes",
  * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call),
  * "matvec_kernel_ns" / "matvec_kernel_launches" (option "ktime": summed event time / count of the mat-vec launches of
- * the last decode_greedy call) */
+ * the last decode_greedy call), "tp_allgathers" (NCCL all-gathers enqueued since create) */
 int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name);
 
 /* debug: with option "trace" = 1 every kernel of the fused decode step records globaltimer stamps into its slot

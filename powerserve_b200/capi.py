@@ -92,6 +92,8 @@ def load_library() -> C.CDLL:
         "ps_cuda_forward": (ci, [vp, i32p, i32p, ci, ci, C.c_void_p]),
         "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
         "ps_cuda_logits_dev": (vp, [vp]),
+        "ps_cuda_tp_unique_id": (ci, [vp]),
+        "ps_cuda_tp_init": (ci, [vp, vp]),
         "ps_cuda_set_option": (ci, [vp, C.c_char_p, ci]),
         "ps_cuda_get_counter": (i64, [vp, C.c_char_p]),
         "ps_cuda_read_trace": (ci, [vp, C.c_void_p, ci]),
@@ -237,11 +239,21 @@ class CudaBackend:
         self._ck(self.L.ps_cuda_kv_truncate(self.h, n))
 
 
-def desc_from_model_json(cfg: dict, max_batch: int = 128, n_ctx: Optional[int] = None, qkv_bias: bool = False) -> ModelDesc:
+def desc_from_model_json(cfg: dict, max_batch: int = 128, n_ctx: Optional[int] = None, qkv_bias: bool = False,
+                         tp_rank: int = 0, tp_size: int = 1) -> ModelDesc:
     llm, rope = cfg["llm_config"], cfg["llm_config"]["rope_config"]
     return ModelDesc(llm["embed_dim"], llm["ffn_dim"], llm["n_layers"], llm["n_attn_heads"], llm["n_attn_kv_heads"], llm["head_size"],
                      llm["vocab_size"], n_ctx or llm["n_ctx"], llm["norm_eps"], rope["rope_dim"], rope["rope_type"],
-                     rope["rope_freq_base"], rope["rope_freq_scale"], rope["rope_attn_factor"], int(qkv_bias), max_batch, 0, 1)
+                     rope["rope_freq_base"], rope["rope_freq_scale"], rope["rope_attn_factor"], int(qkv_bias), max_batch, tp_rank, tp_size)
+
+
+def tp_unique_id() -> bytes:
+    """Rank 0 of a tensor-parallel group: the 128-byte NCCL id every rank passes to CudaModel(nccl_id=...)."""
+    buf = C.create_string_buffer(128)
+    rc = load_library().ps_cuda_tp_unique_id(buf)
+    if rc != 0:
+        raise PsCudaError(f"ps_cuda_tp_unique_id failed ({rc}): NCCL not available")
+    return buf.raw
 
 
 class CudaModel:
@@ -249,17 +261,21 @@ class CudaModel:
     forward / decode follow LlamaModel::forward / decode (src/model/llama/llama_model.cpp:52-132)."""
 
     def __init__(self, path: Optional[str] = None, *, desc: Optional[ModelDesc] = None,
-                 tensors: Optional[Dict[str, gguf.GGUFTensor]] = None, max_batch: int = 128, device: int = 0):
+                 tensors: Optional[Dict[str, gguf.GGUFTensor]] = None, max_batch: int = 128, device: int = 0,
+                 tp_rank: int = 0, tp_size: int = 1, nccl_id: Optional[bytes] = None):
         if path is not None:
             cfg = json.load(open(os.path.join(path, "model.json")))
             self._gguf = gguf.GGUFFile(os.path.join(path, "ggml", "weights.gguf"))
             tensors = self._gguf.tensors
-            desc = desc_from_model_json(cfg, max_batch=max_batch, qkv_bias="blk.0.attn_q.bias" in tensors)
+            desc = desc_from_model_json(cfg, max_batch=max_batch, qkv_bias="blk.0.attn_q.bias" in tensors, tp_rank=tp_rank, tp_size=tp_size)
         assert desc is not None and tensors is not None
         self.desc, self.tensors = desc, tensors
         self.vocab = desc.vocab_size
         self.be = CudaBackend(desc, device)
         L = self.be.L
+        if desc.tp_size > 1:
+            assert nccl_id is not None and len(nccl_id) == 128, "tensor parallel contexts need the group's NCCL id (capi.tp_unique_id on rank 0)"
+            self.be._ck(L.ps_cuda_tp_init(self.be.h, nccl_id))
 
         def T(name: Optional[str]) -> Tensor:
             if name is None:

@@ -4,6 +4,8 @@
 #include "ps_decode.cuh"
 #include "ps_rw.cuh"
 
+#include <dlfcn.h>
+
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -13,6 +15,35 @@
 #include <vector>
 
 #define PS_TL_SLOTS 512
+
+// NCCL is bound at run time (dlopen) and only when a tensor-parallel context is initialised: single-GPU users need no
+// NCCL, and inside a torch process the already-loaded libnccl.so.2 is reused.  Just the five entry points we call.
+struct PsNcclId { char internal[128]; }; // ncclUniqueId (passed by value to ncclCommInitRank)
+namespace {
+struct NcclApi {
+    void *lib = nullptr;
+    int (*GetUniqueId)(void *) = nullptr;
+    int (*CommInitRank)(void **, int, PsNcclId, int) = nullptr;
+    int (*CommDestroy)(void *) = nullptr;
+    int (*AllGather)(const void *, void *, size_t, int, void *, cudaStream_t) = nullptr;
+    const char *(*GetErrorString)(int) = nullptr;
+};
+NcclApi g_nccl;
+bool nccl_load() {
+    if (g_nccl.lib) return true;
+    void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+    if (!h) return false;
+    g_nccl.GetUniqueId = (int (*)(void *))dlsym(h, "ncclGetUniqueId");
+    g_nccl.CommInitRank = (int (*)(void **, int, PsNcclId, int))dlsym(h, "ncclCommInitRank");
+    g_nccl.CommDestroy = (int (*)(void *))dlsym(h, "ncclCommDestroy");
+    g_nccl.AllGather = (int (*)(const void *, void *, size_t, int, void *, cudaStream_t))dlsym(h, "ncclAllGather");
+    g_nccl.GetErrorString = (const char *(*)(int))dlsym(h, "ncclGetErrorString");
+    if (!g_nccl.GetUniqueId || !g_nccl.CommInitRank || !g_nccl.CommDestroy || !g_nccl.AllGather || !g_nccl.GetErrorString) return false;
+    g_nccl.lib = h;
+    return true;
+}
+} // namespace
 
 namespace {
 
@@ -73,6 +104,15 @@ struct ps_cuda_ctx {
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
+    // tensor parallelism (row sharding of every matrix + all-gather, bit-exact): local sizes of this rank
+    int tp = 1, rank = 0;
+    int nh_l = 0, nkv_l = 0, ffn_l = 0, vocab_l = 0, dim_l = 0;
+    void *nccl_comm = nullptr;
+    float *att_full = nullptr, *h_full = nullptr, *x_part = nullptr, *g_part = nullptr, *logits_part = nullptr;
+    float *all_val = nullptr;  // gathered arg-max partials [tp][n_sm]
+    int *all_idx = nullptr;
+    float *tp_rows = nullptr;  // logits of a token-by-token tensor-parallel batch, [max_batch][vocab] (allocated on first use)
+    int64_t n_gather = 0;      // all-gathers enqueued (counter "tp_allgathers")
     uint8_t *ximg = nullptr;   // Q8_K images of up to max_batch activation columns (multi-column row-walker)
     uint8_t *hq = nullptr;     // Q8_K image of the FFN hidden vector, written by the gate/up epilogue for the down mat-vec
     int *blk_cnt = nullptr;    // per-256-block arrival counters of that hand-off (rest state: zero)
@@ -290,10 +330,21 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
+// all-gather over the tensor-parallel group (NCCL on the context stream; capturable into the decode graph)
+int tp_all_gather(ps_cuda_ctx *ctx, const void *send, void *recv, size_t count, bool is_int = false) {
+    if (ctx->tp == 1) return 0;
+    if (!ctx->nccl_comm) return fail(ctx, PS_CUDA_ERR_INVALID, "tensor-parallel context without ps_cuda_tp_init");
+    const int rc = g_nccl.AllGather(send, recv, count, is_int ? 2 /* ncclInt32 */ : 7 /* ncclFloat32 */, ctx->nccl_comm, ctx->stream);
+    if (rc != 0) return fail(ctx, PS_CUDA_ERR_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
+    ctx->n_gather++;
+    return 0;
+}
+
 // q, k, v in one launch; the epilogue applies ROPE to q and k and writes k / v straight into the KV cache at pos_dev[0]
+// (tensor parallel: this rank's heads only)
 int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     const ps_cuda_model_desc &d = ctx->d;
-    const int qdim = d.n_heads * d.head_size, kvd = d.n_kv_heads * d.head_size;
+    const int qdim = ctx->nh_l * d.head_size, kvd = ctx->nkv_l * d.head_size;
     PsRwArgs a{};
     a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
     a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim, PS_RW_OUT_ROPE};
@@ -306,7 +357,7 @@ int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
 
 template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
     const ps_cuda_model_desc &d = ctx->d;
-    const int hs = d.head_size, nkv = d.n_kv_heads;
+    const int hs = d.head_size, nkv = ctx->nkv_l;
     const float kq_scale = 1.0f / sqrtf((float)hs);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
@@ -321,23 +372,23 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
                     (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx));
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
-              bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr) {
+              bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0) {
     PsRwArgs a{};
     a.xq_in = xq_in;
     a.next_norm_w = next_norm_w; a.next_norm_n = ctx->d.dim;
-    if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; }
+    if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; a.idx_offset = idx_offset; }
     a.w = w; a.n_oct = (n_rows + 7) / 8; a.K = K; a.n_seg = 1;
-    a.seg[0] = {dst, nullptr, 0, n_rows};
+    a.seg[0] = {dst, nullptr, 0, n_rows, 0};
     a.x = x; a.norm_w = norm_w; a.eps = ctx->d.norm_eps; a.residual = residual;
     return launch_rw(ctx, a, residual ? PS_EPI_RESIDUAL : PS_EPI_STORE);
 }
 int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     const ps_cuda_model_desc &d = ctx->d;
     PsRwArgs a{};
-    a.w = ld.rw_gu; a.n_oct = (d.ffn_dim + 7) / 8; a.K = d.dim; a.n_seg = 1;
-    a.seg[0] = {ctx->g, nullptr, 0, d.ffn_dim};
+    a.w = ld.rw_gu; a.n_oct = (ctx->ffn_l + 7) / 8; a.K = d.dim; a.n_seg = 1;
+    a.seg[0] = {ctx->g_part, nullptr, 0, ctx->ffn_l, 0};
     a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
-    a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt;
+    if (ctx->tp == 1) { a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt; } // the Q8_K hand-off needs the whole vector on one GPU
     return launch_rw(ctx, a, PS_EPI_SILU);
 }
 
@@ -386,10 +437,14 @@ int rwm_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, int slot, 
     return launch_rwm(ctx, a);
 }
 
-// one decode step on the token in tokens_dev[0] at position pos_dev[0]; `pick`: run the greedy pick + bookkeeping
+// one decode step on the token in tokens_dev[0] at position pos_dev[0]; `pick`: run
+// the greedy pick + bookkeeping.  Tensor parallel (ctx->tp > 1): every matrix is ROW-sharded, so each dot product keeps
+// its full K and the arithmetic stays bit-identical to one GPU; the sharded outputs are exchanged with all-gathers
+// (attention output, the two residual updates, the FFN hidden vector: 4 per layer) instead of K-split all-reduces.
 int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     const ps_cuda_model_desc &d = ctx->d;
     const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, qdim = nh * hs, ffn = d.ffn_dim;
+    const int tp = ctx->tp, rank = ctx->rank, dim_l = ctx->dim_l;
     int rc;
     ctx->trace_launch = 0;
     if ((rc = launch_k(ctx, ps_k_embed_dev, dim3(std::max(1, dim / 256)), dim3(256), 0, ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev, tl_slot(ctx)))) return rc;
@@ -403,17 +458,33 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
         default: rc = launch_attn<8>(ctx, L); break;
         }
         if (rc) return rc;
+        if ((rc = tp_all_gather(ctx, ctx->att, ctx->att_full, (size_t)qdim / tp))) return rc;
         const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
-        if ((rc = rw_single(ctx, ld.rw_o, dim, qdim, ctx->x, ctx->att, nullptr, ctx->x, false, nullptr, ld.ffn_norm))) return rc; // x += Wo . att
+        // x[rows of this rank] += Wo[rows] . att
+        if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, ctx->x + (size_t)rank * dim_l, false, nullptr, ld.ffn_norm))) return rc;
+        if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
-        if ((rc = rw_single(ctx, ld.rw_down, dim, ffn, ctx->x, ctx->g, nullptr, ctx->x, false, ctx->hq, norm_after))) return rc; // x += Wdown . g
+        if ((rc = tp_all_gather(ctx, ctx->g_part, ctx->h_full, (size_t)ctx->ffn_l))) return rc;
+        if ((rc = rw_single(ctx, ld.rw_down, dim_l, ffn, ctx->x_part, ctx->h_full, nullptr, ctx->x + (size_t)rank * dim_l, false,
+                            tp == 1 ? ctx->hq : nullptr, norm_after))) return rc;                          // x[rows] += Wdown[rows] . g
+        if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
     }
     if (lm_head) {
-        if ((rc = rw_single(ctx, ctx->rw_out, d.vocab_size, dim, ctx->logits, ctx->x, ctx->w_out_norm, nullptr, pick))) return rc;
+        if ((rc = rw_single(ctx, ctx->rw_out, ctx->vocab_l, dim, ctx->logits_part, ctx->x, ctx->w_out_norm, nullptr, pick, nullptr, nullptr,
+                            rank * ctx->vocab_l))) return rc;
         if (pick) {
-            const int n_part = std::min(ctx->n_sm, (d.vocab_size + 7) / 8);
-            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, (const float *)ctx->part_val, (const int *)ctx->part_idx, n_part,
-                               ctx->ids_dev, ctx->ctr_dev, ctx->tokens_dev, ctx->pos_dev, tl_slot(ctx)))) return rc;
+            const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
+            const float *pv = ctx->part_val;
+            const int *pi = ctx->part_idx;
+            if (tp > 1) {
+                if ((rc = tp_all_gather(ctx, ctx->part_val, ctx->all_val, (size_t)n_part))) return rc;
+                if ((rc = tp_all_gather(ctx, ctx->part_idx, ctx->all_idx, (size_t)n_part, true))) return rc;
+                pv = ctx->all_val; pi = ctx->all_idx;
+            }
+            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, pv, pi, n_part * tp, ctx->ids_dev, ctx->ctr_dev, ctx->tokens_dev,
+                               ctx->pos_dev, tl_slot(ctx)))) return rc;
+        } else if (tp > 1) {
+            if ((rc = tp_all_gather(ctx, ctx->logits_part, ctx->logits, (size_t)ctx->vocab_l))) return rc;
         }
     }
     return 0;
@@ -438,7 +509,7 @@ int run_step(ps_cuda_ctx *ctx, bool pick) {
     }
     PS_CK(cudaGraphLaunch(ge, ctx->stream));
     ctx->n_graph++;
-    ctx->n_launch += 1 + 6 * ctx->d.n_layers + 1 + (pick ? 1 : 0); // kernels inside the replayed graph
+    ctx->n_launch += 1 + 6 * ctx->d.n_layers + 1 + (pick ? 1 : 0); // OUR kernels inside the replayed graph (NCCL's are not counted)
     return 0;
 }
 
@@ -472,9 +543,17 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     if (d.n_heads % d.n_kv_heads || d.head_size % 32 || d.head_size > 256 || d.rope_n_dims != d.head_size)
         return fail(nullptr, PS_CUDA_ERR_UNSUPPORTED, "unsupported head geometry (heads %d/%d, head_size %d, rope dims %d)", d.n_heads,
                     d.n_kv_heads, d.head_size, d.rope_n_dims);
+    const int tp = d.tp_size > 0 ? d.tp_size : 1;
+    if (tp > 1 && (d.tp_rank < 0 || d.tp_rank >= tp || d.n_heads % tp || d.n_kv_heads % tp || d.ffn_dim % (8 * tp) || d.vocab_size % (8 * tp) ||
+                   d.dim % (8 * tp)))
+        return fail(nullptr, PS_CUDA_ERR_UNSUPPORTED, "tensor parallel size %d does not divide heads %d/%d, ffn %d, vocab %d or dim %d into octets", tp,
+                    d.n_heads, d.n_kv_heads, d.ffn_dim, d.vocab_size, d.dim);
     ctx = new ps_cuda_ctx();
     ctx->device = device;
     ctx->d = d;
+    ctx->tp = tp;
+    ctx->rank = tp > 1 ? d.tp_rank : 0;
+    ctx->nh_l = d.n_heads / tp; ctx->nkv_l = d.n_kv_heads / tp; ctx->ffn_l = d.ffn_dim / tp; ctx->vocab_l = d.vocab_size / tp; ctx->dim_l = d.dim / tp;
     auto bail = [&](int rc) {
         g_create_error = ctx->err;
         ps_cuda_destroy(ctx);
@@ -516,6 +595,17 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
+    if (tp > 1) {
+        PS_AL(ctx->att_full, 4 * qdim);
+        PS_AL(ctx->h_full, 4 * (int64_t)d.ffn_dim);
+        PS_AL(ctx->x_part, 4 * (int64_t)ctx->dim_l);
+        PS_AL(ctx->g_part, 4 * (int64_t)ctx->ffn_l);
+        PS_AL(ctx->logits_part, 4 * (int64_t)ctx->vocab_l);
+        PS_AL(ctx->all_val, 4 * 1024 * tp);
+        PS_AL(ctx->all_idx, 4 * 1024 * tp);
+    } else {
+        ctx->att_full = ctx->att; ctx->h_full = ctx->g; ctx->x_part = ctx->x; ctx->g_part = ctx->g; ctx->logits_part = ctx->logits;
+    }
     PS_AL(ctx->ximg, (size_t)B * ((size_t)ctx->maxK + (size_t)(ctx->maxK / 256 + 1) * 32));
     PS_AL(ctx->hq, (size_t)d.ffn_dim + (size_t)(d.ffn_dim / 256 + 1) * 32);
     PS_AL(ctx->blk_cnt, 4 * (size_t)(d.ffn_dim / 256 + 1));
@@ -526,10 +616,11 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     ctx->kc.resize(d.n_layers);
     ctx->vct.resize(d.n_layers);
     for (int L = 0; L < d.n_layers; L++) {
-        PS_AL(ctx->kc[L], 4 * kvd * d.n_ctx);
-        PS_AL(ctx->vct[L], 4 * kvd * d.n_ctx);
-        PS_CKC(cudaMemsetAsync(ctx->kc[L], 0, 4 * kvd * d.n_ctx, ctx->stream));
-        PS_CKC(cudaMemsetAsync(ctx->vct[L], 0, 4 * kvd * d.n_ctx, ctx->stream));
+        const int64_t kvd_l = kvd / tp; // a tensor-parallel rank caches only its own kv heads
+        PS_AL(ctx->kc[L], 4 * kvd_l * d.n_ctx);
+        PS_AL(ctx->vct[L], 4 * kvd_l * d.n_ctx);
+        PS_CKC(cudaMemsetAsync(ctx->kc[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
+        PS_CKC(cudaMemsetAsync(ctx->vct[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
     }
     {
         std::vector<float> t;
@@ -560,6 +651,7 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
     if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
+    if (ctx->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(ctx->nccl_comm);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
     if (ctx->ev1) cudaEventDestroy(ctx->ev1);
@@ -610,7 +702,8 @@ int ps_cuda_register_weight(ps_cuda_ctx *ctx, const void *host, int type, int64_
         return fail(ctx, PS_CUDA_ERR_INVALID, "register_weight: bad tensor (type %d, %lld x %lld)", type, (long long)ne0, (long long)ne1);
     auto it = ctx->weights.find(host);
     if (it != ctx->weights.end()) {
-        if (it->second.type != type || it->second.ne0 != ne0 || it->second.ne1 != ne1)
+        // a row prefix of a registered tensor aliases it (tied lm_head shard of tensor-parallel rank 0 == first rows of token_embd)
+        if (it->second.type != type || it->second.ne0 != ne0 || it->second.ne1 < ne1)
             return fail(ctx, PS_CUDA_ERR_INVALID, "register_weight: host pointer already registered with another shape");
         if (dev) *dev = it->second.dev;
         return 0;
@@ -780,8 +873,15 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
         int rc_ = reg(t, ne0, ne1, (const void **)&(dev), type);      \
         if (rc_) return rc_;                                          \
     } while (0)
+    // tensor parallel rank r owns rows [r * rows / tp, (r + 1) * rows / tp) of EVERY matrix (rows are contiguous in GGUF)
+    const int tp = ctx->tp, rank = ctx->rank;
+    const int64_t qdim_l = qdim / tp, kvd_l = kvd / tp, ffn_l = ctx->ffn_l, vocab_l = ctx->vocab_l, dim_l = ctx->dim_l;
+    auto rows_of = [&](ps_cuda_tensor t, int64_t ne0, int64_t rows_l) {
+        if (t.host && tp > 1) t.host = (const uint8_t *)t.host + (size_t)rank * (size_t)rows_l * (size_t)ps_row_bytes(t.type, ne0);
+        return t;
+    };
     REG(w->token_embd, d.dim, d.vocab_size, ctx->w_embd, &ctx->t_embd);
-    REG(w->output, d.dim, d.vocab_size, ctx->w_out, &ctx->t_out);
+    REG(rows_of(w->output, d.dim, vocab_l), d.dim, vocab_l, ctx->w_out, &ctx->t_out);
     REG(w->output_norm, d.dim, 1, ctx->w_out_norm, nullptr);
     if (w->output_norm.type != 0) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "norm weights must be F32");
     ctx->layers.assign(d.n_layers, LayerDev{});
@@ -791,19 +891,19 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
         if (lw.attn_norm.type != 0 || lw.ffn_norm.type != 0) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "norm weights must be F32");
         REG(lw.attn_norm, d.dim, 1, ld.attn_norm, nullptr);
         REG(lw.ffn_norm, d.dim, 1, ld.ffn_norm, nullptr);
-        REG(lw.attn_q, d.dim, qdim, ld.wq, &ld.tq);
-        REG(lw.attn_k, d.dim, kvd, ld.wk, &ld.tk);
-        REG(lw.attn_v, d.dim, kvd, ld.wv, &ld.tv);
-        REG(lw.attn_output, qdim, d.dim, ld.wo, &ld.to);
-        REG(lw.ffn_gate, d.dim, d.ffn_dim, ld.wgate, &ld.tgate);
-        REG(lw.ffn_up, d.dim, d.ffn_dim, ld.wup, &ld.tup);
-        REG(lw.ffn_down, d.ffn_dim, d.dim, ld.wdown, &ld.tdown);
+        REG(rows_of(lw.attn_q, d.dim, qdim_l), d.dim, qdim_l, ld.wq, &ld.tq);
+        REG(rows_of(lw.attn_k, d.dim, kvd_l), d.dim, kvd_l, ld.wk, &ld.tk);
+        REG(rows_of(lw.attn_v, d.dim, kvd_l), d.dim, kvd_l, ld.wv, &ld.tv);
+        REG(rows_of(lw.attn_output, qdim, dim_l), qdim, dim_l, ld.wo, &ld.to);
+        REG(rows_of(lw.ffn_gate, d.dim, ffn_l), d.dim, ffn_l, ld.wgate, &ld.tgate);
+        REG(rows_of(lw.ffn_up, d.dim, ffn_l), d.dim, ffn_l, ld.wup, &ld.tup);
+        REG(rows_of(lw.ffn_down, d.ffn_dim, dim_l), d.ffn_dim, dim_l, ld.wdown, &ld.tdown);
         if (d.qkv_bias) {
             if (lw.attn_q_bias.type != 0 || lw.attn_k_bias.type != 0 || lw.attn_v_bias.type != 0)
                 return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "bias tensors must be F32");
-            REG(lw.attn_q_bias, qdim, 1, ld.q_bias, nullptr);
-            REG(lw.attn_k_bias, kvd, 1, ld.k_bias, nullptr);
-            REG(lw.attn_v_bias, kvd, 1, ld.v_bias, nullptr);
+            REG(rows_of(lw.attn_q_bias, 1, qdim_l), qdim_l, 1, ld.q_bias, nullptr);
+            REG(rows_of(lw.attn_k_bias, 1, kvd_l), kvd_l, 1, ld.k_bias, nullptr);
+            REG(rows_of(lw.attn_v_bias, 1, kvd_l), kvd_l, 1, ld.v_bias, nullptr);
         }
         // q/k/v (and gate/up) share one quantised activation: their vec_dot_type must agree
         auto kq = [](int t) { return t == 12 || t == 14; };
@@ -815,29 +915,30 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
     for (const LayerDev &ld : ctx->layers)
         if (ld.tq != 12 || ld.tk != 12 || ld.tv != 12 || ld.to != 12 || ld.tgate != 12 || ld.tup != 12 || ld.tdown != 12) ctx->fused_ok = false;
     if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 64 || d.ffn_dim / 256 > 64 || d.n_heads / d.n_kv_heads > 8 ||
-        ((int64_t)d.n_heads * d.head_size) % 8 || ((int64_t)d.n_kv_heads * d.head_size) % 8 || (d.rope_type & 2) ||
+        (qdim_l % 8) || (kvd_l % 8) || (d.rope_type & 2) ||
         !(d.n_heads / d.n_kv_heads == 1 || d.n_heads / d.n_kv_heads == 2 || d.n_heads / d.n_kv_heads == 4 || d.n_heads / d.n_kv_heads == 8))
         ctx->fused_ok = false;
+    if (tp > 1 && !ctx->fused_ok) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "tensor parallelism needs the fused Q4_K decode path (all-Q4_K llama-style model)");
     if (ctx->fused_ok) {
         // octet-interleaved copies for the row-walker mat-vec (a permutation of the same bytes; see ps_rw.cuh)
         const int64_t dim = d.dim, ffn = d.ffn_dim;
         auto oct_bytes = [](int64_t rows, int64_t K, int slots) { return (size_t)((rows + 7) / 8) * (size_t)(K / 256) * slots * PS_RW_OCTET_BLOCK; };
         int rc;
         for (LayerDev &ld : ctx->layers) {
-            if ((rc = dev_alloc(ctx, (void **)&ld.rw_qkv, oct_bytes(qdim + 2 * kvd, dim, 1)))) return rc;
-            if ((rc = dev_alloc(ctx, (void **)&ld.rw_o, oct_bytes(dim, qdim, 1)))) return rc;
-            if ((rc = dev_alloc(ctx, (void **)&ld.rw_gu, oct_bytes(ffn, dim, 2)))) return rc;
-            if ((rc = dev_alloc(ctx, (void **)&ld.rw_down, oct_bytes(dim, ffn, 1)))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wq, qdim, dim, 0, 0, 1))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wk, kvd, dim, qdim / 8, 0, 1))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wv, kvd, dim, (qdim + kvd) / 8, 0, 1))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_o, ld.wo, dim, qdim, 0, 0, 1))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wgate, ffn, dim, 0, 0, 2))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wup, ffn, dim, 0, 1, 2))) return rc;
-            if ((rc = rw_repack(ctx, ld.rw_down, ld.wdown, dim, ffn, 0, 0, 1))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_qkv, oct_bytes(qdim_l + 2 * kvd_l, dim, 1)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_o, oct_bytes(dim_l, qdim, 1)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_gu, oct_bytes(ffn_l, dim, 2)))) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ld.rw_down, oct_bytes(dim_l, ffn, 1)))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wq, qdim_l, dim, 0, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wk, kvd_l, dim, qdim_l / 8, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_qkv, ld.wv, kvd_l, dim, (qdim_l + kvd_l) / 8, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_o, ld.wo, dim_l, qdim, 0, 0, 1))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wgate, ffn_l, dim, 0, 0, 2))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_gu, ld.wup, ffn_l, dim, 0, 1, 2))) return rc;
+            if ((rc = rw_repack(ctx, ld.rw_down, ld.wdown, dim_l, ffn, 0, 0, 1))) return rc;
         }
-        if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(d.vocab_size, dim, 1)))) return rc;
-        if ((rc = rw_repack(ctx, ctx->rw_out, ctx->w_out, d.vocab_size, dim, 0, 0, 1))) return rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(vocab_l, dim, 1)))) return rc;
+        if ((rc = rw_repack(ctx, ctx->rw_out, ctx->w_out, vocab_l, dim, 0, 0, 1))) return rc;
         PS_CK(cudaStreamSynchronize(ctx->stream));
     }
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
@@ -963,7 +1064,20 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += (int64_t)bs * 8;
     PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
-    if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
+    if (ctx->tp > 1 && bs > 1) {
+        // tensor parallel: the sharded path exists for the fused single-token step only; a batch is fed token by token
+        // (bit-identical to a batched pass — every column of the reference's batched ops is independent)
+        for (int i = 0; i < bs && !rc; i++) {
+            PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens + i, 4, cudaMemcpyHostToDevice, ctx->stream));
+            PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos + i, 4, cudaMemcpyHostToDevice, ctx->stream));
+            rc = decode_step_fused(ctx, lm_head != 0, false);
+            if (!rc && lm_head) {
+                if (!ctx->tp_rows) { int rc2 = dev_alloc(ctx, (void **)&ctx->tp_rows, (size_t)ctx->d.max_batch * ctx->d.vocab_size * 4); if (rc2) return rc2; }
+                PS_CK(cudaMemcpyAsync(ctx->tp_rows + (size_t)i * ctx->d.vocab_size, ctx->logits, (size_t)ctx->d.vocab_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+            }
+        }
+        if (!rc && lm_head) PS_CK(cudaMemcpyAsync(ctx->logits, ctx->tp_rows, (size_t)bs * ctx->d.vocab_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    } else if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
         if (lm_head) rc = run_step(ctx, false);
         else rc = decode_step_fused(ctx, false, false);
     } else {
@@ -1058,6 +1172,23 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
 
 const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx) { return ctx->logits; }
 
+int ps_cuda_tp_unique_id(void *out128) {
+    if (!out128 || !nccl_load()) return PS_CUDA_ERR_UNSUPPORTED;
+    return g_nccl.GetUniqueId(out128) == 0 ? 0 : PS_CUDA_ERR_CUDA;
+}
+
+int ps_cuda_tp_init(ps_cuda_ctx *ctx, const void *id128) {
+    if (ctx->tp <= 1) return 0;
+    if (!nccl_load()) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "tensor parallelism needs libnccl.so.2 (dlopen failed)");
+    if (ctx->nccl_comm) return fail(ctx, PS_CUDA_ERR_INVALID, "tp_init: already initialised");
+    PS_CK(cudaSetDevice(ctx->device));
+    PsNcclId id;
+    memcpy(&id, id128, sizeof id);
+    const int rc = g_nccl.CommInitRank(&ctx->nccl_comm, ctx->tp, id, ctx->rank);
+    if (rc != 0) { ctx->nccl_comm = nullptr; return fail(ctx, PS_CUDA_ERR_CUDA, "ncclCommInitRank failed: %s", g_nccl.GetErrorString(rc)); }
+    return 0;
+}
+
 int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
     if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
@@ -1090,7 +1221,8 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
     if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6);
     if (!strcmp(name, "matvec_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the mat-vec launches
-    if (!strcmp(name, "matvec_kernel_launches")) return ctx->kt_launches; // CUDA-event time of the last forward / decode
+    if (!strcmp(name, "matvec_kernel_launches")) return ctx->kt_launches;
+    if (!strcmp(name, "tp_allgathers")) return ctx->n_gather; // CUDA-event time of the last forward / decode
     return -1;
 }
 

@@ -63,6 +63,7 @@ struct PsRwArgs {
     double inv_k;          // 1 / K when K is a power of two (the mean is then an exact scaling), else 0
     float *part_val;       // optional (lm_head): per-CTA partial arg-max of the produced rows, [gridDim.x]
     int *part_idx;
+    int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
 };
 
@@ -393,7 +394,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             for (int t = 1; t < PS_RW_WARPS; t++)
                 if (sv[t] > best_v || (sv[t] == best_v && si[t] < best_i)) { best_v = sv[t]; best_i = si[t]; }
             a.part_val[blockIdx.x] = best_v;
-            a.part_idx[blockIdx.x] = best_i;
+            a.part_idx[blockIdx.x] = (best_i == 0x7fffffff) ? best_i : best_i + a.idx_offset;
         }
     }
     ps_bar_sync(2, PS_RW_THREADS);

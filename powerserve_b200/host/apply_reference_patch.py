@@ -2,10 +2,9 @@
 print it as a unified diff.  This is exactly the patch INTEGRATION.md asks a maintainer to make; it follows the QNN
 precedent (one OpType + one executor case + one Platform member, all behind `#if defined(POWERSERVE_WITH_CUDA)`).
 
-    python apply_reference_patch.py <reference_root> <out_dir> [--diff] [--overlay <dir>]
+    python apply_reference_patch.py <reference_root> <out_dir> [--diff]
 
-`--overlay` names a directory whose files replace the reference's before patching (the build uses it to start from the
-oracle's Q4_K-enabled copy of ggml_wrapper.cpp).  Only eleven files are touched; they are written under <out_dir>/src/... and take precedence on the include path.  Nothing
+Thirteen files are touched (two of them only for the Q4_K / Q6_K enum enablement, which is independent of CUDA); they are written under <out_dir>/src/... and take precedence on the include path.  Nothing
 from the reference is stored in this repository.
 """
 import difflib
@@ -130,7 +129,28 @@ def patch_model_forward(s):
     {""")
 
 
+# ---- Q4_K / Q6_K enablement (SURVEY F1): the reference's DataType layer rejects the K-quants its vendored ggml supports;
+# three enum / switch sites, no arithmetic (the same edit the oracle build applies with sed).
+def patch_data_type(s):
+    s = sub(s, "    GGML_Q8_0,\n", "    GGML_Q8_0,\n    GGML_Q4_K,\n    GGML_Q6_K,\n")
+    s = sub(s, "        return ggml_type_size(GGML_TYPE_Q8_0);\n", "        return ggml_type_size(GGML_TYPE_Q8_0);\n    case DataType::GGML_Q4_K:\n"
+            "        return ggml_type_size(GGML_TYPE_Q4_K);\n    case DataType::GGML_Q6_K:\n        return ggml_type_size(GGML_TYPE_Q6_K);\n")
+    return sub(s, "        return ggml_blck_size(GGML_TYPE_Q8_0);\n", "        return ggml_blck_size(GGML_TYPE_Q8_0);\n    case DataType::GGML_Q4_K:\n"
+               "        return ggml_blck_size(GGML_TYPE_Q4_K);\n    case DataType::GGML_Q6_K:\n        return ggml_blck_size(GGML_TYPE_Q6_K);\n")
+
+
+def patch_ggml_hpp(s):
+    s = sub(s, "        return GGML_TYPE_Q8_0;\n", "        return GGML_TYPE_Q8_0;\n    case DataType::GGML_Q4_K:\n        return GGML_TYPE_Q4_K;\n"
+            "    case DataType::GGML_Q6_K:\n        return GGML_TYPE_Q6_K;\n")
+    return sub(s, "        return DataType::GGML_Q8_0;\n", "        return DataType::GGML_Q8_0;\n    case GGML_TYPE_Q4_K:\n        return DataType::GGML_Q4_K;\n"
+               "    case GGML_TYPE_Q6_K:\n        return DataType::GGML_Q6_K;\n")
+
+
 def patch_ggml_wrapper(s):
+    s = sub(s, "            dequantize_row_q8_0((block_q8_0 *)src, dst_tb + i * dim, dim);\n",
+            "            dequantize_row_q8_0((block_q8_0 *)src, dst_tb + i * dim, dim);\n        } break;\n        case DataType::GGML_Q4_K: {\n"
+            "            dequantize_row_q4_K((block_q4_K *)src, dst_tb + i * dim, dim);\n        } break;\n        case DataType::GGML_Q6_K: {\n"
+            "            dequantize_row_q6_K((block_q6_K *)src, dst_tb + i * dim, dim);\n")
     # GGMLBackend::get_n_tasks sizes the CPU plan per op; the whole-model op needs no CPU tasks (same as QNN_FORWARD)
     return sub(s, "#if defined(POWERSERVE_WITH_QNN)\n    case OpType::QNN_FORWARD: {\n        n_tasks = 1;", """#if defined(POWERSERVE_WITH_CUDA)
     case OpType::CUDA_FORWARD: {
@@ -156,6 +176,8 @@ def patch_ggml_cpp(s):
 
 
 FILES = {
+    "src/core/data_type.hpp": patch_data_type,
+    "src/backend/ggml/ggml.hpp": patch_ggml_hpp,
     "src/backend/ggml/ggml.cpp": patch_ggml_cpp,
     "src/backend/ggml/ggml_wrapper.cpp": patch_ggml_wrapper,
     "src/graph/op_type.hpp": patch_op_type,
@@ -172,12 +194,8 @@ FILES = {
 
 def main():
     ref, out = sys.argv[1], sys.argv[2]
-    overlay = sys.argv[sys.argv.index("--overlay") + 1] if "--overlay" in sys.argv else None
     for rel, fn in FILES.items():
-        src = os.path.join(ref, rel)
-        if overlay and os.path.exists(os.path.join(overlay, rel)):
-            src = os.path.join(overlay, rel)
-        old = open(src).read()
+        old = open(os.path.join(ref, rel)).read()
         new = fn(old)
         dst = os.path.join(out, rel)
         os.makedirs(os.path.dirname(dst), exist_ok=True)

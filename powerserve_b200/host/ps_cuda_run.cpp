@@ -1,6 +1,6 @@
 // ps_cuda_run.cpp — PowerServe's own model stack (Model -> Graph -> Executor -> Platform) running on the CUDA backend.
-// Same command line and outputs as oracle/ref_driver.cpp (which drives the unmodified CPU path), so the two can be
-// diffed: it mirrors app/run/run.cpp:38-154 without CLI11 / tokenizer (the reference's submodules are empty here).
+// Same command line and outputs as the test suite's driver of the unmodified CPU path, so the two can be diffed: it
+// mirrors app/run/run.cpp:38-154 without CLI11 / tokenizer (the reference's submodules are empty here).
 //
 // usage: ps_cuda_run <model_dir> <n_threads> <batch_size> <prompt_ids.txt> <n_decode> <out_prefix> [--dump-logits N]
 #include "backend/platform.hpp"
