@@ -126,6 +126,7 @@ def main():
     ap.add_argument("--cpu-threads", type=int, default=0)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--tp-nccl", action="store_true", help="tensor parallel with NCCL all-gathers instead of the fused peer-store kernels")
     ap.add_argument("--replicas", action="store_true", help="N > 1: independent replicas instead of tensor parallelism")
     args = ap.parse_args()
 
@@ -141,7 +142,7 @@ def main():
     cfg = {"workload": f"{args.model} Q4_K synthetic: decode 1 token/step at context {args.prompt}+ (BASELINE configs[2]: prefill {args.prompt} + decode)",
            "context": args.prompt, "prefill_batch": args.prefill_batch, "weight_bytes_per_token": wbytes,
            "l2": "weights (>= 0.7 GB/token) exceed the 126 MB L2; no explicit flush",
-           "parallelism": "1 GPU" if world == 1 else (f"replicas x{world}" if args.replicas else f"tp{world} (row-sharded, NCCL all-gather)")}
+           "parallelism": "1 GPU" if world == 1 else (f"replicas x{world}" if args.replicas else f"tp{world} (row-sharded, " + ("NCCL all-gather)" if args.tp_nccl else "all-gather fused into the kernels as NVLink peer stores)"))}
 
     # ------------------------------------------------------------------ reference arm (CPU)
     if args.impl == "reference":
@@ -184,6 +185,11 @@ def main():
     desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=args.prefill_batch, n_ctx=shape.n_ctx, qkv_bias=shape.qkv_bias,
                                      tp_rank=rank if tp > 1 else 0, tp_size=tp)
     model = capi.CudaModel(desc=desc, tensors=tmap, device=local_rank, nccl_id=nccl_id)
+    if tp > 1 and not args.tp_nccl:  # fused compute + all-gather over NVLink peer memory: exchange the CUDA-IPC handles
+        mine = torch.frombuffer(bytearray(model.tp_export()), dtype=torch.uint8).cuda()
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        model.tp_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
     prompt = synth.random_prompt(shape.vocab_size, args.prompt + 1, seed=1234)
 
     # prefill (ModelTokenIterator loop: prompt[:-1] in chunks, lm_head=false), wall clock through the C ABI
@@ -263,7 +269,7 @@ def main():
                                  "what": "whole decode step incl. attention, prologues and launch gaps: weight bytes per token / step time"}},
            "clocks": clk.summary(), "greedy_ids_head": [int(x) for x in ids[:8]]}
     if tp > 1:
-        out["tp"] = {"size": tp, "allgathers_per_step": (model.be.counter("tp_allgathers")) // max(1, model.be.counter("graph_replays") + 1),
+        out["tp"] = {"size": tp, "p2p": bool(model.be.counter("tp_p2p")), "peer_wait_error": model.be.counter("tp_error"), "nccl_allgathers_per_step": (model.be.counter("tp_allgathers")) // max(1, model.be.counter("graph_replays") + 1),
                      "note": "row sharding keeps every dot product whole: results are bit-identical to one GPU (tests/test_gpu_tp.py)"}
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:

@@ -141,6 +141,13 @@ const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
  * 128-byte NCCL id from rank 0 to the other ranks (any transport: torch.distributed, MPI, a file). */
 int ps_cuda_tp_unique_id(void *out128);                        /* rank 0: ncclGetUniqueId */
 int ps_cuda_tp_init(ps_cuda_ctx *ctx, const void *id128);      /* every rank, after create, before the first forward */
+/* Fused compute + all-gather over NVLink peer memory (optional, on top of tp_init): every rank exports the CUDA-IPC
+ * handle of its exchange heap (64 bytes), the host gathers the N handles in rank order and every rank imports them.
+ * From then on the producing kernels store their output rows straight into every rank's copy of the gathered vector
+ * and publish an epoch flag; the consuming kernels wait on the flags (bounded spin; counter "tp_error").  Option
+ * "tp_p2p" = 0 switches back to NCCL all-gathers (same results; tests compare the two). */
+int ps_cuda_tp_export(ps_cuda_ctx *ctx, void *handle64);
+int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n);
 
 /* execution switches (0/1): "graph" = replay the decode step as a captured CUDA graph, "fused" = fused decode
  * kernels instead of one kernel per table op, "pdl" = programmatic dependent launch between the fused kernels.  All

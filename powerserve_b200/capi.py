@@ -94,6 +94,8 @@ def load_library() -> C.CDLL:
         "ps_cuda_logits_dev": (vp, [vp]),
         "ps_cuda_tp_unique_id": (ci, [vp]),
         "ps_cuda_tp_init": (ci, [vp, vp]),
+        "ps_cuda_tp_export": (ci, [vp, vp]),
+        "ps_cuda_tp_import": (ci, [vp, vp, ci]),
         "ps_cuda_set_option": (ci, [vp, C.c_char_p, ci]),
         "ps_cuda_get_counter": (i64, [vp, C.c_char_p]),
         "ps_cuda_read_trace": (ci, [vp, C.c_void_p, ci]),
@@ -295,6 +297,17 @@ class CudaModel:
         out = "output.weight" if "output.weight" in tensors else "token_embd.weight"  # weights.hpp:67
         self._w = ModelWeights(T("token_embd.weight"), T("output_norm.weight"), T(out), self._layers)
         self.be._ck(L.ps_cuda_bind_model(self.be.h, C.byref(self._w)))
+
+    def tp_export(self) -> bytes:
+        """CUDA-IPC handle (64 bytes) of this rank's exchange heap; gather them in rank order and call tp_import."""
+        buf = C.create_string_buffer(64)
+        self.be._ck(self.be.L.ps_cuda_tp_export(self.be.h, buf))
+        return buf.raw
+
+    def tp_import(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * self.desc.tp_size
+        self.be._ck(self.be.L.ps_cuda_tp_import(self.be.h, blob, self.desc.tp_size))
 
     @property
     def position(self) -> int:

@@ -15,6 +15,7 @@
 #include <vector>
 
 #define PS_TL_SLOTS 512
+enum { PS_TP_SLOT_ATT = 0, PS_TP_SLOT_X1 = 1, PS_TP_SLOT_H = 2, PS_TP_SLOT_X2 = 3, PS_TP_SLOT_PART = 4, PS_TP_SLOT_LOGITS = 5, PS_TP_SLOTS = 6 };
 
 // NCCL is bound at run time (dlopen) and only when a tensor-parallel context is initialised: single-GPU users need no
 // NCCL, and inside a torch process the already-loaded libnccl.so.2 is reused.  Just the five entry points we call.
@@ -111,6 +112,15 @@ struct ps_cuda_ctx {
     float *att_full = nullptr, *h_full = nullptr, *x_part = nullptr, *g_part = nullptr, *logits_part = nullptr;
     float *all_val = nullptr;  // gathered arg-max partials [tp][n_sm]
     int *all_idx = nullptr;
+    // peer-memory exchange (fused compute + all-gather): one IPC-exported heap per rank
+    //   [att_full qdim][x dim][h_full ffn][all_val tp*1024][all_idx tp*1024][flags PS_TP_SLOTS x PS_TP_MAX u32]
+    uint8_t *heap = nullptr;
+    size_t heap_bytes = 0, off_att = 0, off_x = 0, off_h = 0, off_val = 0, off_idx = 0, off_logits = 0, off_flags = 0;
+    uint8_t *peer_heap[PS_TP_MAX] = {};
+    bool p2p = false;          // peers imported: all-gathers run as peer stores inside the producing kernels
+    uint32_t *epoch_dev = nullptr; // [PS_TP_SLOTS] local epoch counters
+    int *done_dev = nullptr;       // [PS_TP_SLOTS] local CTA arrival counters
+    int *tp_err_dev = nullptr;
     float *tp_rows = nullptr;  // logits of a token-by-token tensor-parallel batch, [max_batch][vocab] (allocated on first use)
     int64_t n_gather = 0;      // all-gathers enqueued (counter "tp_allgathers")
     uint8_t *ximg = nullptr;   // Q8_K images of up to max_batch activation columns (multi-column row-walker)
@@ -330,9 +340,33 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
+// peer-store all-gather links of one phase (`slot`): where the producer's rows land on every rank, and what the consumer waits for
+PsTpOut tp_out(ps_cuda_ctx *ctx, int slot, size_t heap_off_bytes, size_t my_elem_off) {
+    PsTpOut o{};
+    if (!ctx->p2p) return o;
+    o.n = ctx->tp;
+    for (int p = 0; p < ctx->tp; p++) {
+        o.peer_dst[p] = reinterpret_cast<float *>(ctx->peer_heap[p] + heap_off_bytes) + my_elem_off;
+        o.peer_idx[p] = reinterpret_cast<int *>(ctx->peer_heap[p] + ctx->off_idx) + my_elem_off;
+        o.peer_flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_heap[p] + ctx->off_flags) + slot * PS_TP_MAX + ctx->rank;
+    }
+    o.epoch = ctx->epoch_dev + slot;
+    o.done = ctx->done_dev + slot;
+    return o;
+}
+PsTpIn tp_in(ps_cuda_ctx *ctx, int slot) {
+    PsTpIn i{};
+    if (!ctx->p2p) return i;
+    i.n = ctx->tp;
+    i.flags = reinterpret_cast<const uint32_t *>(ctx->heap + ctx->off_flags) + slot * PS_TP_MAX;
+    i.epoch = ctx->epoch_dev + slot;
+    i.err = ctx->tp_err_dev;
+    return i;
+}
+
 // all-gather over the tensor-parallel group (NCCL on the context stream; capturable into the decode graph)
-int tp_all_gather(ps_cuda_ctx *ctx, const void *send, void *recv, size_t count, bool is_int = false) {
-    if (ctx->tp == 1) return 0;
+int tp_all_gather(ps_cuda_ctx *ctx, const void *send, void *recv, size_t count, bool is_int = false, bool always = false) {
+    if (ctx->tp == 1 || (ctx->p2p && !always)) return 0; // p2p: the producing kernel already stored into every rank
     if (!ctx->nccl_comm) return fail(ctx, PS_CUDA_ERR_INVALID, "tensor-parallel context without ps_cuda_tp_init");
     const int rc = g_nccl.AllGather(send, recv, count, is_int ? 2 /* ncclInt32 */ : 7 /* ncclFloat32 */, ctx->nccl_comm, ctx->stream);
     if (rc != 0) return fail(ctx, PS_CUDA_ERR_CUDA, "ncclAllGather failed: %s", g_nccl.GetErrorString(rc));
@@ -346,6 +380,7 @@ int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     const ps_cuda_model_desc &d = ctx->d;
     const int qdim = ctx->nh_l * d.head_size, kvd = ctx->nkv_l * d.head_size;
     PsRwArgs a{};
+    if (L > 0) a.tpi = tp_in(ctx, PS_TP_SLOT_X2);
     a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
     a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim, PS_RW_OUT_ROPE};
     a.seg[1] = {ctx->kc[L], d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd, PS_RW_OUT_ROPE_KCACHE};
@@ -369,11 +404,14 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
                        (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx)))) return rc;
     const size_t a2smem = (size_t)R2 * (size_t)((d.n_ctx + 31) & ~31) * 4;
     return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
-                    (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx));
+                    (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx),
+                    tp_out(ctx, PS_TP_SLOT_ATT, ctx->off_att, (size_t)ctx->rank * ctx->nh_l * hs));
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
-              bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0) {
+              bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0,
+              PsTpIn tpi = PsTpIn{}, PsTpOut tpo = PsTpOut{}) {
     PsRwArgs a{};
+    a.tpi = tpi; a.tpo = tpo;
     a.xq_in = xq_in;
     a.next_norm_w = next_norm_w; a.next_norm_n = ctx->d.dim;
     if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; a.idx_offset = idx_offset; }
@@ -388,6 +426,8 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     a.w = ld.rw_gu; a.n_oct = (ctx->ffn_l + 7) / 8; a.K = d.dim; a.n_seg = 1;
     a.seg[0] = {ctx->g_part, nullptr, 0, ctx->ffn_l, 0};
     a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
+    a.tpi = tp_in(ctx, PS_TP_SLOT_X1);
+    a.tpo = tp_out(ctx, PS_TP_SLOT_H, ctx->off_h, (size_t)ctx->rank * ctx->ffn_l);
     if (ctx->tp == 1) { a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt; } // the Q8_K hand-off needs the whole vector on one GPU
     return launch_rw(ctx, a, PS_EPI_SILU);
 }
@@ -461,19 +501,23 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
         if ((rc = tp_all_gather(ctx, ctx->att, ctx->att_full, (size_t)qdim / tp))) return rc;
         const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
         // x[rows of this rank] += Wo[rows] . att
-        if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, ctx->x + (size_t)rank * dim_l, false, nullptr, ld.ffn_norm))) return rc;
+        if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, ctx->x + (size_t)rank * dim_l, false, nullptr, ld.ffn_norm, 0,
+                            tp_in(ctx, PS_TP_SLOT_ATT), tp_out(ctx, PS_TP_SLOT_X1, ctx->off_x, (size_t)rank * dim_l)))) return rc;
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
         if ((rc = tp_all_gather(ctx, ctx->g_part, ctx->h_full, (size_t)ctx->ffn_l))) return rc;
         if ((rc = rw_single(ctx, ld.rw_down, dim_l, ffn, ctx->x_part, ctx->h_full, nullptr, ctx->x + (size_t)rank * dim_l, false,
-                            tp == 1 ? ctx->hq : nullptr, norm_after))) return rc;                          // x[rows] += Wdown[rows] . g
+                            tp == 1 ? ctx->hq : nullptr, norm_after, 0, tp_in(ctx, PS_TP_SLOT_H),
+                            tp_out(ctx, PS_TP_SLOT_X2, ctx->off_x, (size_t)rank * dim_l)))) return rc;     // x[rows] += Wdown[rows] . g
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
     }
     if (lm_head) {
+        const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
         if ((rc = rw_single(ctx, ctx->rw_out, ctx->vocab_l, dim, ctx->logits_part, ctx->x, ctx->w_out_norm, nullptr, pick, nullptr, nullptr,
-                            rank * ctx->vocab_l))) return rc;
+                            rank * ctx->vocab_l, d.n_layers > 0 ? tp_in(ctx, PS_TP_SLOT_X2) : PsTpIn{},
+                            pick ? tp_out(ctx, PS_TP_SLOT_PART, ctx->off_val, (size_t)rank * n_part)
+                                 : tp_out(ctx, PS_TP_SLOT_LOGITS, ctx->off_logits, (size_t)rank * ctx->vocab_l)))) return rc;
         if (pick) {
-            const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
             const float *pv = ctx->part_val;
             const int *pi = ctx->part_idx;
             if (tp > 1) {
@@ -482,9 +526,11 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
                 pv = ctx->all_val; pi = ctx->all_idx;
             }
             if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, pv, pi, n_part * tp, ctx->ids_dev, ctx->ctr_dev, ctx->tokens_dev,
-                               ctx->pos_dev, tl_slot(ctx)))) return rc;
-        } else if (tp > 1) {
-            if ((rc = tp_all_gather(ctx, ctx->logits_part, ctx->logits, (size_t)ctx->vocab_l))) return rc;
+                               ctx->pos_dev, tl_slot(ctx), tp_in(ctx, PS_TP_SLOT_PART)))) return rc;
+        } else if (tp > 1) { // host-visible logits
+            if (ctx->p2p) rc = launch_k(ctx, ps_k_tp_wait, dim3(1), dim3(32), 0, tp_in(ctx, PS_TP_SLOT_LOGITS));
+            else rc = tp_all_gather(ctx, ctx->logits_part, ctx->logits, (size_t)ctx->vocab_l);
+            if (rc) return rc;
         }
     }
     return 0;
@@ -596,13 +642,33 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
     if (tp > 1) {
-        PS_AL(ctx->att_full, 4 * qdim);
-        PS_AL(ctx->h_full, 4 * (int64_t)d.ffn_dim);
+        auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
+        ctx->off_att = 0;
+        ctx->off_x = up(ctx->off_att + 4 * (size_t)qdim);
+        ctx->off_h = up(ctx->off_x + 4 * (size_t)dim);
+        ctx->off_val = up(ctx->off_h + 4 * (size_t)d.ffn_dim);
+        ctx->off_idx = up(ctx->off_val + 4 * 1024 * (size_t)tp);
+        ctx->off_logits = up(ctx->off_idx + 4 * 1024 * (size_t)tp);
+        ctx->off_flags = up(ctx->off_logits + 4 * (size_t)d.vocab_size);
+        ctx->heap_bytes = up(ctx->off_flags + 4 * PS_TP_SLOTS * PS_TP_MAX);
+        PS_AL(ctx->heap, ctx->heap_bytes);
+        PS_CKC(cudaMemsetAsync(ctx->heap, 0, ctx->heap_bytes, ctx->stream));
+        PS_AL(ctx->epoch_dev, 4 * PS_TP_SLOTS);
+        PS_AL(ctx->done_dev, 4 * PS_TP_SLOTS);
+        PS_AL(ctx->tp_err_dev, 4);
+        PS_CKC(cudaMemsetAsync(ctx->epoch_dev, 0, 4 * PS_TP_SLOTS, ctx->stream));
+        PS_CKC(cudaMemsetAsync(ctx->done_dev, 0, 4 * PS_TP_SLOTS, ctx->stream));
+        PS_CKC(cudaMemsetAsync(ctx->tp_err_dev, 0, 4, ctx->stream));
+        // the gathered vectors live in the heap (x replaces the workspace x allocated above for the decode path)
+        ctx->att_full = reinterpret_cast<float *>(ctx->heap + ctx->off_att);
+        ctx->x = reinterpret_cast<float *>(ctx->heap + ctx->off_x);
+        ctx->h_full = reinterpret_cast<float *>(ctx->heap + ctx->off_h);
+        ctx->all_val = reinterpret_cast<float *>(ctx->heap + ctx->off_val);
+        ctx->all_idx = reinterpret_cast<int *>(ctx->heap + ctx->off_idx);
+        ctx->logits = reinterpret_cast<float *>(ctx->heap + ctx->off_logits); // single-token logits (batches are staged through tp_rows)
         PS_AL(ctx->x_part, 4 * (int64_t)ctx->dim_l);
         PS_AL(ctx->g_part, 4 * (int64_t)ctx->ffn_l);
         PS_AL(ctx->logits_part, 4 * (int64_t)ctx->vocab_l);
-        PS_AL(ctx->all_val, 4 * 1024 * tp);
-        PS_AL(ctx->all_idx, 4 * 1024 * tp);
     } else {
         ctx->att_full = ctx->att; ctx->h_full = ctx->g; ctx->x_part = ctx->x; ctx->g_part = ctx->g; ctx->logits_part = ctx->logits;
     }
@@ -651,6 +717,8 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
     if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
+    for (int p = 0; p < PS_TP_MAX; p++)
+        if (ctx->peer_heap[p] && p != ctx->rank) cudaIpcCloseMemHandle(ctx->peer_heap[p]);
     if (ctx->nccl_comm && g_nccl.lib) g_nccl.CommDestroy(ctx->nccl_comm);
     for (cudaEvent_t e : ctx->kt_events) cudaEventDestroy(e);
     if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -1177,6 +1245,34 @@ int ps_cuda_tp_unique_id(void *out128) {
     return g_nccl.GetUniqueId(out128) == 0 ? 0 : PS_CUDA_ERR_CUDA;
 }
 
+int ps_cuda_tp_export(ps_cuda_ctx *ctx, void *handle64) {
+    if (ctx->tp <= 1 || !ctx->heap) return fail(ctx, PS_CUDA_ERR_INVALID, "tp_export: not a tensor-parallel context");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    PS_CK(cudaSetDevice(ctx->device));
+    cudaIpcMemHandle_t h;
+    PS_CK(cudaIpcGetMemHandle(&h, ctx->heap));
+    memcpy(handle64, &h, 64);
+    return 0;
+}
+
+int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n) {
+    if (ctx->tp <= 1 || n != ctx->tp) return fail(ctx, PS_CUDA_ERR_INVALID, "tp_import: expected %d handles", ctx->tp);
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    for (int p = 0; p < n; p++) {
+        if (p == ctx->rank) { ctx->peer_heap[p] = ctx->heap; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, (const uint8_t *)handles + (size_t)p * 64, 64);
+        void *ptr = nullptr;
+        PS_CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
+        ctx->peer_heap[p] = (uint8_t *)ptr;
+    }
+    ctx->p2p = true;
+    if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
+    if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
+    return 0;
+}
+
 int ps_cuda_tp_init(ps_cuda_ctx *ctx, const void *id128) {
     if (ctx->tp <= 1) return 0;
     if (!nccl_load()) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "tensor parallelism needs libnccl.so.2 (dlopen failed)");
@@ -1196,6 +1292,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
+    else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
             int rc = dev_alloc(ctx, (void **)&ctx->trace_dev, sizeof(long long) * PS_TL_SLOTS * 8);
@@ -1222,7 +1319,13 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6);
     if (!strcmp(name, "matvec_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the mat-vec launches
     if (!strcmp(name, "matvec_kernel_launches")) return ctx->kt_launches;
-    if (!strcmp(name, "tp_allgathers")) return ctx->n_gather; // CUDA-event time of the last forward / decode
+    if (!strcmp(name, "tp_allgathers")) return ctx->n_gather;
+    if (!strcmp(name, "tp_p2p")) return ctx->p2p ? 1 : 0;
+    if (!strcmp(name, "tp_error")) { // 1 if a peer wait gave up (bounded spin)
+        int v = 0;
+        if (ctx->tp_err_dev) { cudaStreamSynchronize(ctx->stream); cudaMemcpy(&v, ctx->tp_err_dev, 4, cudaMemcpyDeviceToHost); }
+        return v;
+    } // CUDA-event time of the last forward / decode
     return -1;
 }
 

@@ -58,6 +58,65 @@ PS_D int ps_dp4a_us(uint32_t a, int b, int c) { // unsigned bytes of a  x  signe
     return d;
 }
 
+// ---------------------------------------------------------------------------------------------------- tensor parallel
+// Fused compute + all-gather over NVLink peer memory (one process per GPU, buffers mapped with CUDA IPC).  A producer
+// kernel stores its output rows straight into EVERY rank's copy of the gathered vector; when its last CTA is done it
+// publishes a monotonically increasing epoch into flags[slot][my_rank] on every rank (release, system scope).  The
+// consumer kernel of the same phase waits (acquire, system scope) until all ranks' flags have reached the epoch its own
+// rank published in that phase.  Gathers are in place: the barrier chain of the decode step makes every buffer's next
+// write happen after all of its readers are done ("tensor parallelism").
+#define PS_TP_MAX 8
+struct PsTpOut {
+    float *peer_dst[PS_TP_MAX];      // where this kernel's output goes on every rank (own rank included), already offset
+    int *peer_idx[PS_TP_MAX];        // lm_head partial arg-max only: the index array next to the value array
+    uint32_t *peer_flag[PS_TP_MAX];  // &flags[slot][my_rank] on every rank
+    uint32_t *epoch;                 // local: epoch counter of the slot (single writer: the last CTA)
+    int *done;                       // local: CTA arrival counter (rest state 0)
+    int n;                           // ranks; 0 = not tensor parallel
+};
+struct PsTpIn {
+    const uint32_t *flags;           // local flags[slot][0..n)
+    const uint32_t *epoch;           // local epoch counter of the slot
+    int *err;                        // set to 1 if the wait gave up (a peer died): bounded spin, never a hang
+    int n;
+};
+PS_D uint32_t ps_ld_acquire_sys(const uint32_t *p) {
+    uint32_t v;
+    asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+PS_D void ps_st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
+
+// consumer: ONE thread of the CTA calls this after griddepcontrol.wait and before the CTA touches the gathered vector
+PS_D void ps_tp_wait(const PsTpIn &in) {
+    if (in.n == 0) return;
+    const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(in.epoch);
+    for (int s = 0; s < in.n; s++) {
+        long long spins = 0;
+        while ((int32_t)(ps_ld_acquire_sys(in.flags + s) - e) < 0) {
+            if (++spins > (1ll << 26)) { *in.err = 1; break; }   // ~seconds; results are garbage but the GPU is not hung
+        }
+    }
+}
+// producer: every thread's stores are done (CTA-wide barrier before the call); ONE thread of the CTA calls this
+PS_D void ps_tp_signal(const PsTpOut &out, int n_ctas) {
+    if (out.n == 0) return;
+    __threadfence_system();
+    if (atomicAdd(out.done, 1) == n_ctas - 1) {
+        *out.done = 0;
+        const uint32_t e = *out.epoch + 1;
+        *out.epoch = e;
+        __threadfence_system();
+        for (int p = 0; p < out.n; p++) ps_st_release_sys(out.peer_flag[p], e);
+    }
+}
+
+// stand-alone consumer wait (before a device-to-host copy of a gathered vector)
+__global__ void ps_k_tp_wait(const PsTpIn tpi) {
+    ps_grid_dep_wait();
+    if (threadIdx.x == 0) ps_tp_wait(tpi);
+}
+
 // ---------------------------------------------------------------------------------------------------- prologue
 // quantize_row_q8_K_ref (ggml-quants.c:3799-3837) of one 256-block by one warp; e[0..3] = elements 4*lane..+3,
 // e[4..7] = elements 128+4*lane..+3.  Writes the natural-order words (word w = elements 4w..4w+3), d and the four
@@ -209,7 +268,7 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 // lane order, leftovers in order) with 16 loads in flight per lane.
 template <int R2>
 __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
-                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl) {
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut tpo) {
     extern __shared__ float s_p[]; // [R2][stride]
     __shared__ double shd[8];
     __shared__ float shf[8];
@@ -309,7 +368,12 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
             for (int h2 = 1; h2 < R2; h2++)
                 if (lane == h2) v = sum[h2];
             att[(int64_t)(g * R2 + lane) * hs + d] = v;
+            for (int p = 0; p < tpo.n; p++) tpo.peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v; // all-gather by peer stores
         }
+    }
+    if (tpo.n) {
+        __syncthreads();
+        if (tid == 0) ps_tp_signal(tpo, (int)(gridDim.x * gridDim.y));
     }
     ps_tl_max(tl, 1);
 }
@@ -344,12 +408,16 @@ __global__ void __launch_bounds__(256) ps_k_embed_dev(float *__restrict__ dst, c
 // ids[*ctr] = argmax, token feedback, position and counter advance.
 __global__ void __launch_bounds__(256) ps_k_argmax_step(const float *__restrict__ part_val, const int *__restrict__ part_idx, int n_part,
                                                         int32_t *__restrict__ ids, int32_t *__restrict__ ctr, int32_t *__restrict__ next_token,
-                                                        int32_t *__restrict__ pos, long long *tl) {
+                                                        int32_t *__restrict__ pos, long long *tl, const PsTpIn tpi) {
     __shared__ float sv[8];
     __shared__ int si[8];
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
+    if (tpi.n) {
+        if (threadIdx.x == 0) ps_tp_wait(tpi);
+        __syncthreads();
+    }
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int t = threadIdx.x; t < n_part; t += blockDim.x) {

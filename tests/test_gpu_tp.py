@@ -1,5 +1,6 @@
 """Tensor parallelism on real GPUs: N processes, one per GPU, row-sharded weights, NCCL all-gathers
-inside the decode graph.  Row sharding keeps every dot product whole, so the result must be BIT-IDENTICAL to one GPU —
+inside the decode graph (mode nccl) or fused into the producing kernels as NVLink peer stores + epoch flags (mode p2p).
+Row sharding keeps every dot product whole, so the result must be BIT-IDENTICAL to one GPU —
 checked against the oracle.  Needs >= 2 GPUs (skipped otherwise; run with `gpurun --gpus 2`)."""
 import os
 import subprocess
@@ -24,13 +25,14 @@ def n_gpus():
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
+@pytest.mark.parametrize("mode", ["p2p", "nccl"])
 @pytest.mark.parametrize("preset,size", [("tiny-llama", 2), ("slice-1b", 2)])
-def test_tp_decode_bit_exact(preset, size):
+def test_tp_decode_bit_exact(preset, size, mode):
     d = M.model_dir(preset)
     n_prompt, n_dec = 19, 12
     with tempfile.TemporaryDirectory() as td:
         procs = [subprocess.Popen([sys.executable, os.path.join(L.ROOT, "tools", "tp_worker.py"), str(r), str(size), os.path.join(td, "id"), d,
-                                   str(n_prompt), str(n_dec), os.path.join(td, "out")], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+                                   str(n_prompt), str(n_dec), os.path.join(td, "out"), mode], stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
                  for r in range(size)]
         outs = [p.communicate(timeout=300)[0] for p in procs]
         assert all(p.returncode == 0 for p in procs), "\n".join(outs)
@@ -47,4 +49,7 @@ def test_tp_decode_bit_exact(preset, size):
         assert list(r["ids"]) == ids_o
         L.assert_bit_equal(r["logits"], lg_o, "tensor-parallel logits vs oracle")
         assert list(r["dev_ids"]) == ids_long
-        assert int(r["gathers"]) > 0
+        assert int(r["tp_error"]) == 0
+        assert int(r["p2p"]) == (1 if mode == "p2p" else 0)
+        if mode == "nccl":
+            assert int(r["gathers"]) > 0

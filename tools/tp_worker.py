@@ -1,9 +1,11 @@
 """One rank of a tensor-parallel group (one process per GPU): loads a synthetic model directory with row-sharded
 weights, prefills a prompt, decodes greedily on the device, and dumps ids (+ the logits of a few host-driven steps).
 
-    python tools/tp_worker.py <rank> <size> <id_file> <model_dir> <n_prompt> <n_decode> <out_prefix>
+    python tools/tp_worker.py <rank> <size> <id_file> <model_dir> <n_prompt> <n_decode> <out_prefix> [nccl|p2p]
 
-The 128-byte NCCL id travels through <id_file> (rank 0 writes it); any other transport works as well.
+The 128-byte NCCL id travels through <id_file> (rank 0 writes it), the 64-byte CUDA-IPC handles of the exchange heaps
+through <id_file>.ipc<rank>; any other transport works as well.  Mode `p2p` (default) = all-gathers fused into the
+producing kernels as peer stores; `nccl` = NCCL all-gathers between the kernels.
 """
 import os
 import sys
@@ -27,12 +29,27 @@ else:
             raise SystemExit("no NCCL id after 120 s")
         time.sleep(0.05)
     nid = open(id_file, "rb").read()
+mode = sys.argv[8] if len(sys.argv) > 8 else "p2p"
 m = capi.CudaModel(model_dir, max_batch=32, device=rank, tp_rank=rank, tp_size=size, nccl_id=nid)
+if mode == "p2p":
+    with open(f"{id_file}.ipc{rank}.tmp", "wb") as f:
+        f.write(m.tp_export())
+    os.replace(f"{id_file}.ipc{rank}.tmp", f"{id_file}.ipc{rank}")
+    handles = []
+    for r in range(size):
+        t0 = time.time()
+        while not os.path.exists(f"{id_file}.ipc{r}"):
+            if time.time() - t0 > 120:
+                raise SystemExit("no IPC handle after 120 s")
+            time.sleep(0.05)
+        handles.append(open(f"{id_file}.ipc{r}", "rb").read())
+    m.tp_import(handles)
 prompt = synth.random_prompt(m.vocab, n_prompt, seed=11)
 ids, logits = m.generate(prompt, 4, batch_size=16)            # host-driven steps: logits gathered on every rank
 m.reset()
 m.prefill(prompt, 16)
 dev_ids = m.decode_greedy(int(prompt[-1]), n_decode)           # graph-replayed device loop
 np.savez(f"{out}.rank{rank}.npz", ids=np.asarray(ids, np.int32), logits=logits, dev_ids=dev_ids,
-         gathers=m.be.counter("tp_allgathers"), ms=m.be.counter("last_device_ns") / 1e6 / n_decode)
+         gathers=m.be.counter("tp_allgathers"), p2p=m.be.counter("tp_p2p"), tp_error=m.be.counter("tp_error"),
+         ms=m.be.counter("last_device_ns") / 1e6 / n_decode)
 m.close()
