@@ -1,0 +1,68 @@
+"""Tensor-parallel sharding logic on CPU: world_size 2 over torch.distributed `gloo`.  Each rank runs the oracle's
+operators on its row shards (tests/_tp_sim.py, a phase-by-phase mirror of the CUDA decode step) and the shards are
+exchanged with dist.all_gather; the result must be BIT-IDENTICAL to the unsharded oracle (row sharding keeps every dot
+product whole).  Also checks the sharding plan's validation and byte ranges."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from powerserve_b200 import gguf, synth, tp
+from tests import _libs as L
+from tests import _model as M
+
+
+def _worker(rank, size, port, model_dir, prompt, out_dir):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=size)
+    from tests._tp_sim import ShardedOracle
+
+    def all_gather(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        outs = [torch.empty_like(t) for _ in range(size)]
+        dist.all_gather(outs, t)
+        return torch.cat(outs).numpy()
+
+    m = ShardedOracle(model_dir, rank, size, all_gather)
+    logits = []
+    for tok in prompt[:-1]:
+        m.step(int(tok), lm_head=False)
+    tok = int(prompt[-1])
+    for _ in range(3):
+        lg = m.step(tok)
+        logits.append(lg)
+        tok = int(np.argmax(lg))
+    np.save(os.path.join(out_dir, f"logits{rank}.npy"), np.stack(logits))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("preset", ["tiny-llama", "tiny-qwen2"])
+def test_row_sharded_forward_is_bit_identical(preset):
+    d = M.model_dir(preset)
+    prompt = synth.random_prompt(synth.PRESETS[preset].vocab_size, 7, seed=21)
+    om = M.OracleModel(d)
+    _, ref = om.generate(prompt, 3, batch_size=1)
+    om.close()
+    with tempfile.TemporaryDirectory() as td:
+        port = 29600 + os.getpid() % 300
+        mp.spawn(_worker, args=(2, port, d, prompt, td), nprocs=2, join=True)
+        for r in range(2):
+            L.assert_bit_equal(np.load(os.path.join(td, f"logits{r}.npy")), ref, f"{preset}: rank {r} sharded logits vs unsharded oracle")
+
+
+def test_sharding_plan():
+    with pytest.raises(ValueError):
+        tp.validate(32, 8, 14336, 128256, 4096, 3)
+    tp.validate(32, 8, 14336, 128256, 4096, 8)
+    g = gguf.GGUFFile(os.path.join(M.model_dir("tiny-llama"), "ggml", "weights.gguf"))
+    t = g["blk.0.ffn_down.weight"]                      # {K = ffn, rows = dim}
+    row_bytes = gguf.tensor_bytes(t.ggml_type, (t.shape[0], 1))
+    off, rows = tp.shard_tensor("blk.0.ffn_down.weight", t, 1, 2)
+    assert rows == t.shape[1] // 2 and off == rows * row_bytes
+    off, rows = tp.shard_tensor("blk.0.attn_norm.weight", g["blk.0.attn_norm.weight"], 1, 2)
+    assert off == 0                                      # norm weights are replicated
+    assert tp.gathers_per_token(32) == 129
