@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libps_cuda.so")
 SOURCES = ["ps_cuda.cu"]
-HEADERS = ["ps_rw.cuh", "ps_decode.cuh", "ps_kernels.cuh", "ps_math.cuh", os.path.join("..", "..", "include", "ps_cuda.h")]
+HEADERS = ["ps_tc.cuh", "ps_rw.cuh", "ps_decode.cuh", "ps_kernels.cuh", "ps_math.cuh", os.path.join("..", "..", "include", "ps_cuda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

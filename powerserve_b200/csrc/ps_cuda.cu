@@ -3,6 +3,7 @@
 #include "../../include/ps_cuda.h"
 #include "ps_decode.cuh"
 #include "ps_rw.cuh"
+#include "ps_tc.cuh"
 
 #include <dlfcn.h>
 
@@ -62,6 +63,8 @@ struct LayerDev {
     int tq, tk, tv, to, tgate, tup, tdown;
     // octet-interleaved copies for the row-walker mat-vec (ps_rw.cuh): q|k|v rows, o, gate|up slots, down
     uint8_t *rw_qkv = nullptr, *rw_o = nullptr, *rw_gu = nullptr, *rw_down = nullptr;
+    // fp16-expanded tensor-core operands for the prefill GEMM (ps_tc.cuh): q|k|v rows, o, gate, up, down
+    uint8_t *tc_qkv = nullptr, *tc_o = nullptr, *tc_gate = nullptr, *tc_up = nullptr, *tc_down = nullptr;
 };
 
 } // namespace
@@ -96,7 +99,12 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1;
+    bool tc_ok = false;        // tensor-core prefill operands are resident
+    uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
+    size_t tc_b_bytes = 0;
+    int *tc_err_dev = nullptr; // pipeline time-out flag of the tcgen05 GEMM (counter "tc_error")
+    int64_t n_tc = 0;          // tcgen05 GEMM launches (counter "tc_gemm_launches")
     std::vector<cudaEvent_t> kt_events; // option "ktime": event pairs around every row-walker mat-vec launch
     size_t kt_used = 0;
     double kt_ms = 0.0;                 // summed mat-vec kernel time of the last decode call
@@ -924,6 +932,39 @@ float *ps_cuda_kv_k(ps_cuda_ctx *ctx, int layer) { return (layer >= 0 && layer <
 float *ps_cuda_kv_v(ps_cuda_ctx *ctx, int layer) { return (layer >= 0 && layer < ctx->d.n_layers) ? ctx->vct[layer] : nullptr; }
 
 // ---------------------------------------------------------------------------------------------- whole model
+// ---- tcgen05 prefill GEMM (ps_tc.cuh)
+static int tc_expand(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *w, int64_t n_rows, int64_t K, int64_t tile0) {
+    ps_k_tc_expand_a<<<dim3((unsigned)(K / 256), (unsigned)((n_rows + PS_TC_M - 1) / PS_TC_M)), 256, 0, ctx->stream>>>(dst, w, n_rows, K / 256, tile0);
+    PS_LAUNCH_CK();
+    return 0;
+}
+static int tc_prep_b(ps_cuda_ctx *ctx, const float *x, int K, int bs) {
+    const int n_cg = (bs + PS_TC_N - 1) / PS_TC_N;
+    ps_k_tc_prep_b<<<dim3((unsigned)((K / 256 + 3) / 4), (unsigned)(n_cg * PS_TC_N)), 128, 0, ctx->stream>>>(ctx->tc_b, x, K, bs);
+    PS_LAUNCH_CK();
+    return 0;
+}
+static int tc_gemm(ps_cuda_ctx *ctx, const uint8_t *a_blocks, int n_rows, int K, int bs, const PsRwSeg *segs, int n_seg, const float *residual) {
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_tc_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, PS_TC_STAGES * PS_TC_STAGE));
+        attr[ctx->device] = true;
+    }
+    PsTcArgs a{};
+    a.err = ctx->tc_err_dev;
+    a.a = a_blocks; a.b = ctx->tc_b; a.nb = K / 256; a.n_cg = (bs + PS_TC_N - 1) / PS_TC_N; a.n_seg = n_seg; a.bs = bs; a.residual = residual;
+    for (int t = 0; t < n_seg; t++) a.seg[t] = segs[t];
+    const int n_tiles = (n_rows + PS_TC_M - 1) / PS_TC_M;
+    ps_k_tc_gemm<<<(unsigned)(n_tiles * a.n_cg), PS_TC_THREADS, PS_TC_STAGES * PS_TC_STAGE, ctx->stream>>>(a);
+    PS_LAUNCH_CK();
+    ctx->n_tc++;
+    return 0;
+}
+static int tc_single(ps_cuda_ctx *ctx, const uint8_t *a_blocks, int n_rows, int K, float *dst, int bs, const float *residual) {
+    PsRwSeg sg = {dst, nullptr, 0, n_rows, 0};
+    return tc_gemm(ctx, a_blocks, n_rows, K, bs, &sg, 1, residual);
+}
+
 int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
     const ps_cuda_model_desc &d = ctx->d;
     const int64_t qdim = (int64_t)d.n_heads * d.head_size, kvd = (int64_t)d.n_kv_heads * d.head_size;
@@ -1005,6 +1046,37 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
             if ((rc = rw_repack(ctx, ld.rw_gu, ld.wup, ffn_l, dim, 0, 1, 2))) return rc;
             if ((rc = rw_repack(ctx, ld.rw_down, ld.wdown, dim_l, ffn, 0, 0, 1))) return rc;
         }
+        // fp16-expanded tensor-core operands for the prefill GEMM (2 B / weight; single GPU only, and only if HBM has room)
+        ctx->tc_ok = false;
+        if (tp == 1 && ctx->opt_tc && qdim % PS_TC_M == 0 && kvd % PS_TC_M == 0) {
+            auto a_bytes = [](int64_t rows, int64_t K) { return (size_t)((rows + PS_TC_M - 1) / PS_TC_M) * (size_t)(K / 256) * PS_TC_A_BLOCK; };
+            const size_t per_layer = a_bytes(qdim + 2 * kvd, dim) + a_bytes(dim, qdim) + 2 * a_bytes(ffn, dim) + a_bytes(dim, ffn);
+            size_t free_b = 0, total_b = 0;
+            PS_CK(cudaMemGetInfo(&free_b, &total_b));
+            if (per_layer * (size_t)d.n_layers + ((size_t)8 << 30) < free_b) {
+                for (LayerDev &ld : ctx->layers) {
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_qkv, a_bytes(qdim + 2 * kvd, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_o, a_bytes(dim, qdim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_gate, a_bytes(ffn, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_up, a_bytes(ffn, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_down, a_bytes(dim, ffn)))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wq, qdim, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wk, kvd, dim, qdim / PS_TC_M))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wv, kvd, dim, (qdim + kvd) / PS_TC_M))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_o, ld.wo, dim, qdim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_gate, ld.wgate, ffn, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_up, ld.wup, ffn, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_down, ld.wdown, dim, ffn, 0))) return rc;
+                }
+                const size_t bb = (size_t)((d.max_batch + PS_TC_N - 1) / PS_TC_N) * (size_t)(ctx->maxK / 256) * PS_TC_B_BLOCK;
+                if ((rc = dev_alloc(ctx, (void **)&ctx->tc_b, bb))) return rc;
+                PS_CK(cudaMemsetAsync(ctx->tc_b, 0, bb, ctx->stream)); // the mins tiles are zero outside each lane's four K positions
+                ctx->tc_b_bytes = bb;
+                if ((rc = dev_alloc(ctx, (void **)&ctx->tc_err_dev, 4))) return rc;
+                PS_CK(cudaMemsetAsync(ctx->tc_err_dev, 0, 4, ctx->stream));
+                ctx->tc_ok = true;
+            }
+        }
         if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(vocab_l, dim, 1)))) return rc;
         if ((rc = rw_repack(ctx, ctx->rw_out, ctx->w_out, vocab_l, dim, 0, 0, 1))) return rc;
         PS_CK(cudaStreamSynchronize(ctx->stream));
@@ -1022,6 +1094,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
     const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
     const int64_t n_kv = (int64_t)pos0 + bs; // pos.back() + 1
     const float kq_scale = 1.0f / sqrtf((float)hs);
+    const bool tc = ctx->tc_ok && ctx->opt_tc && ctx->opt_fused && bs >= 16; // tensor-core GEMM on the fp16-expanded operands
     const bool rw = ctx->fused_ok && ctx->opt_fused && bs > 1; // octet-interleaved copies exist: multi-column row-walker
     int rc;
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
@@ -1032,7 +1105,13 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         const LayerDev &ld = ctx->layers[L];
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if (rw) { // q | k | v rows in one pass over the concatenated octets
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->xn, (int)dim, bs))) return rc;
+            PsRwSeg sg[3] = {{ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, (int)qdim, 0},
+                             {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, (int)qdim, (int)(qdim + kvd), 0},
+                             {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, (int)(qdim + kvd), (int)(qdim + 2 * kvd), 0}};
+            if ((rc = tc_gemm(ctx, ld.tc_qkv, (int)(qdim + 2 * kvd), (int)dim, bs, sg, 3, nullptr))) return rc;
+        } else if (rw) { // q | k | v rows in one pass over the concatenated octets
             if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
             PsRwmArgs a{};
             a.w = ld.rw_qkv; a.n_oct = (int)((qdim + 2 * kvd) / 8); a.K = (int)dim; a.slot = 0; a.n_slots = 1; a.n_seg = 3; a.bs = bs;
@@ -1065,7 +1144,10 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
             ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
         }
         PS_LAUNCH_CK();
-        if (rw) {
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->att, (int)qdim, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_o, (int)dim, (int)qdim, ctx->x, bs, ctx->x))) return rc;
+        } else if (rw) {
             if ((rc = rwm_quantize(ctx, ctx->att, (int)qdim, bs))) return rc;
             if ((rc = rwm_single(ctx, ld.rw_o, (int)dim, (int)qdim, 0, 1, ctx->x, bs, nullptr, ctx->x))) return rc;
         } else {
@@ -1074,7 +1156,11 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         }
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.ffn_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if (rw) {
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_gate, (int)ffn, (int)dim, ctx->g, bs, nullptr))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_up, (int)ffn, (int)dim, ctx->u, bs, nullptr))) return rc;
+        } else if (rw) {
             if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
             if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn, (int)dim, 0, 2, ctx->g, bs, nullptr, nullptr))) return rc;
             if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn, (int)dim, 1, 2, ctx->u, bs, nullptr, nullptr))) return rc;
@@ -1085,7 +1171,10 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         }
         ps_k_silu_hadamard<<<grid1d(ffn * bs), 256, 0, ctx->stream>>>(ctx->g, ctx->g, ctx->u, ffn * bs);
         PS_LAUNCH_CK();
-        if (rw) {
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->g, (int)ffn, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_down, (int)dim, (int)ffn, ctx->x, bs, ctx->x))) return rc;
+        } else if (rw) {
             if ((rc = rwm_quantize(ctx, ctx->g, (int)ffn, bs))) return rc;
             if ((rc = rwm_single(ctx, ld.rw_down, (int)dim, (int)ffn, 0, 1, ctx->x, bs, nullptr, ctx->x))) return rc;
         } else {
@@ -1292,6 +1381,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "fused")) ctx->opt_fused = value;
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
+    else if (!strcmp(name, "tc")) ctx->opt_tc = value;
     else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {
@@ -1320,6 +1410,13 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "matvec_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the mat-vec launches
     if (!strcmp(name, "matvec_kernel_launches")) return ctx->kt_launches;
     if (!strcmp(name, "tp_allgathers")) return ctx->n_gather;
+    if (!strcmp(name, "tc_gemm_launches")) return ctx->n_tc;
+    if (!strcmp(name, "tc_ok")) return ctx->tc_ok ? 1 : 0;
+    if (!strcmp(name, "tc_error")) {
+        int v = 0;
+        if (ctx->tc_err_dev) { cudaStreamSynchronize(ctx->stream); cudaMemcpy(&v, ctx->tc_err_dev, 4, cudaMemcpyDeviceToHost); }
+        return v;
+    }
     if (!strcmp(name, "tp_p2p")) return ctx->p2p ? 1 : 0;
     if (!strcmp(name, "tp_error")) { // 1 if a peer wait gave up (bounded spin)
         int v = 0;
