@@ -955,7 +955,8 @@ static int tc_gemm(ps_cuda_ctx *ctx, const uint8_t *a_blocks, int n_rows, int K,
     a.a = a_blocks; a.b = ctx->tc_b; a.nb = K / 256; a.n_cg = (bs + PS_TC_N - 1) / PS_TC_N; a.n_seg = n_seg; a.bs = bs; a.residual = residual;
     for (int t = 0; t < n_seg; t++) a.seg[t] = segs[t];
     const int n_tiles = (n_rows + PS_TC_M - 1) / PS_TC_M;
-    ps_k_tc_gemm<<<(unsigned)(n_tiles * a.n_cg), PS_TC_THREADS, PS_TC_STAGES * PS_TC_STAGE, ctx->stream>>>(a);
+    a.n_units = n_tiles * a.n_cg;
+    ps_k_tc_gemm<<<(unsigned)std::min(a.n_units, ctx->n_sm), PS_TC_THREADS, PS_TC_STAGES * PS_TC_STAGE, ctx->stream>>>(a);
     PS_LAUNCH_CK();
     ctx->n_tc++;
     return 0;
@@ -1131,7 +1132,14 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         PS_LAUNCH_CK();
         ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
         PS_LAUNCH_CK();
-        ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
+        if (bs >= 8) {
+            const int r2 = (int)(nh / nkv);
+            const int qb = std::max(1, std::min(bs, (int)(8192 / (r2 * hs))));
+            ps_k_attn_scores_batch<<<dim3((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb)), 128, (size_t)qb * r2 * hs * 4, ctx->stream>>>(
+                ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs, qb);
+        } else {
+            ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
+        }
         PS_LAUNCH_CK();
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();

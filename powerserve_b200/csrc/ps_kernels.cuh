@@ -519,16 +519,43 @@ __global__ void __launch_bounds__(128) ps_k_attn_scores(float *__restrict__ kq, 
     const float *krow = kc + j * (int64_t)(hs * n_kv_heads) + g * hs;
     float kv[8];
     const int steps = hs / 32;
-    for (int s = 0; s < steps; s++) kv[s] = krow[32 * s + lane];
-    for (int i = 0; i < bs; i++)
-        for (int hh = 0; hh < r2; hh++) {
-            const int h = g * r2 + hh;
+#pragma unroll
+    for (int s = 0; s < 8; s++) kv[s] = (s < steps) ? krow[32 * s + lane] : 0.f;
+    // (query, head) pairs in batches of 8: eight independent FMA chains and eight interleaved butterfly reductions keep
+    // the shuffle latency covered (the arithmetic of every dot product is unchanged)
+    const int n_pairs = bs * r2;
+    for (int p0 = 0; p0 < n_pairs; p0 += 8) {
+        float sum[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+            const int p = min(p0 + u, n_pairs - 1), i = p / r2, h = g * r2 + p % r2;
             const float *qv = q + ((int64_t)i * n_heads + h) * hs;
-            float sum = 0.f;
-            for (int s = 0; s < steps; s++) sum = __fmaf_rn(kv[s], qv[32 * s + lane], sum);
-            sum = ps_f32x8_reduce(sum);
-            if (lane == 0) kq[((int64_t)h * bs + i) * n_kv + j] = sum;
+            float qe[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) qe[s] = (s < steps) ? qv[32 * s + lane] : 0.f; // all loads of the batch in flight
+            sum[u] = 0.f;
+#pragma unroll
+            for (int s = 0; s < 8; s++)
+                if (s < steps) sum[u] = __fmaf_rn(kv[s], qe[s], sum[u]);
         }
+#pragma unroll
+        for (int k = 0; k < 5; k++) { // GGML_F32x8_REDUCE order (see ps_f32x8_reduce)
+            const int step = (k == 0) ? 16 : (k == 1) ? 8 : (k == 2) ? 4 : (k == 3) ? 1 : 2;
+            float o[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) o[u] = __shfl_xor_sync(PS_FULL, sum[u], step);
+#pragma unroll
+            for (int u = 0; u < 8; u++) sum[u] = __fadd_rn(sum[u], o[u]);
+        }
+        if (lane < 8 && p0 + lane < n_pairs) {
+            float v = sum[0];
+#pragma unroll
+            for (int u = 1; u < 8; u++)
+                if (lane == u) v = sum[u];
+            const int p = p0 + lane, i = p / r2, h = g * r2 + p % r2;
+            kq[((int64_t)h * bs + i) * n_kv + j] = v;
+        }
+    }
 }
 
 // ggml_compute_forward_soft_max_f32 (ggml.c:14846-14940) + ggml_vec_soft_max_f32 AVX2 branch (:2814-2868).
@@ -598,6 +625,64 @@ __global__ void __launch_bounds__(128) ps_k_attn_pv(float *__restrict__ out, con
                 out[((int64_t)i * n_heads + h) * hs + d] = sum;
             }
         }
+}
+
+// Scores for batches (prefill chunks): one CTA per (32 cache positions, kv head); each warp keeps 8 K rows in registers,
+// the queries of the group come through shared memory in batches, and every query row read from shared memory is
+// dotted with the warp's 8 K rows at once — eight independent FMA chains and eight interleaved butterfly reductions
+// (ggml_vec_dot_f32 lane order and GGML_F32x8_REDUCE order, exactly as in ps_k_attn_scores).
+__global__ void __launch_bounds__(128) ps_k_attn_scores_batch(float *__restrict__ kq, const float *__restrict__ kc, const float *__restrict__ q,
+                                                              int hs, int n_heads, int n_kv_heads, int64_t n_kv, int bs, int qb) {
+    extern __shared__ float s_qb[]; // [qb * r2][hs]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int g = blockIdx.y, r2 = n_heads / n_kv_heads, steps = hs / 32;
+    const int64_t j0 = (int64_t)blockIdx.x * 32 + warp * 8;
+    float kv[8][8];
+#pragma unroll
+    for (int t = 0; t < 8; t++)
+#pragma unroll
+        for (int s = 0; s < 8; s++) kv[t][s] = (s < steps && j0 + t < n_kv) ? kc[(j0 + t) * (int64_t)(hs * n_kv_heads) + g * hs + 32 * s + lane] : 0.f;
+    {   // one query batch per CTA (blockIdx.z): the r2 heads of a group are adjacent in q, so a query is one contiguous chunk
+        const int i0 = blockIdx.z * qb;
+        const int nq = min(qb, bs - i0);
+        const int chunk4 = r2 * hs / 4; // float4s per query
+        for (int idx = tid; idx < nq * chunk4; idx += 128) {
+            const int qi = idx / chunk4, e = idx % chunk4;
+            reinterpret_cast<float4 *>(s_qb)[idx] = reinterpret_cast<const float4 *>(q + ((int64_t)(i0 + qi) * n_heads + g * r2) * hs)[e];
+        }
+        __syncthreads();
+#pragma unroll 2
+        for (int p = 0; p < nq * r2; p++) {
+            float qe[8];
+#pragma unroll
+            for (int s = 0; s < 8; s++) qe[s] = (s < steps) ? s_qb[p * hs + 32 * s + lane] : 0.f;
+            float sum[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                sum[t] = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < steps) sum[t] = __fmaf_rn(kv[t][s], qe[s], sum[t]);
+            }
+#pragma unroll
+            for (int k = 0; k < 5; k++) {
+                const int step = (k == 0) ? 16 : (k == 1) ? 8 : (k == 2) ? 4 : (k == 3) ? 1 : 2;
+                float o[8];
+#pragma unroll
+                for (int t = 0; t < 8; t++) o[t] = __shfl_xor_sync(PS_FULL, sum[t], step);
+#pragma unroll
+                for (int t = 0; t < 8; t++) sum[t] = __fadd_rn(sum[t], o[t]);
+            }
+            if (lane < 8 && j0 + lane < n_kv) { // lane t stores position j0 + t: 8 consecutive floats of the score row
+                float v = sum[0];
+#pragma unroll
+                for (int t = 1; t < 8; t++)
+                    if (lane == t) v = sum[t];
+                const int i = i0 + p / r2, h = g * r2 + p % r2;
+                kq[((int64_t)h * bs + i) * n_kv + j0 + lane] = v;
+            }
+        }
+    }
 }
 
 // Same operator for batches (prefill chunks): one CTA per (block of 8 queries, head).  The 8 probability rows sit in

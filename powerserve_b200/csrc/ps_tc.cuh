@@ -11,16 +11,18 @@
 //     dequantisation work on the prefill path); the mins use one shared K = 16 tile of the m_j.
 //   * B operand (activations): per (32-column group, super-block, lane) the q8 bytes as fp16, plus half-block sums for the
 //     mins, written per forward call by ps_k_tc_prep_b (same quantiser as everywhere else).
-//   * per super-block: 16 + 4 tcgen05.mma (M = 128, N = 32, K = 16) into 12 x 32 TMEM columns; 16 epilogue warps read the
-//     exact integers back (tcgen05.ld) and advance the FMA chains in registers, one (row, column) pair's 12 chains in ONE
-//     thread — the final hsum_float_8 order needs no shuffles.
-// Pipeline: TMA producer warp (2 stages, one bulk copy per operand block) -> single-thread MMA issuer -> epilogue warps,
-// linked by mbarriers (smem full/empty, tmem full/empty).
+//   * per super-block: 16 + 4 tcgen05.mma (M = 128, N = 16, K = 16) into 12 x 16 TMEM columns (double-buffered); 16
+//     epilogue warps read the exact integers back (12 tcgen05.ld in flight, one wait) and advance the FMA chains in
+//     registers, one (row, column) pair's 12 chains in ONE thread — the final hsum_float_8 order needs no shuffles.
+//     The tile is 128 x 16 because the chains, not the MMAs, set the budget: 12 fp32 accumulators per output element
+//     (24.5 K registers per tile) plus the 24.5 K registers the TMEM read-back lands in fill the register file.
+// Pipeline: persistent CTAs over (row tile, column group) units; TMA producer warp (2 stages, one bulk copy per operand
+// block) -> single-thread MMA issuer -> epilogue warps, linked by mbarriers (smem full/empty, tmem full/empty x 2).
 #pragma once
 #include "ps_rw.cuh"
 
 #define PS_TC_M 128
-#define PS_TC_N 32
+#define PS_TC_N 16
 #define PS_TC_EPI_WARPS 16
 #define PS_TC_THREADS ((PS_TC_EPI_WARPS + 2) * 32)
 // operand blocks in global / shared memory (bytes)
@@ -161,35 +163,37 @@ PS_D bool ps_tc_wait(uint64_t *bar, uint32_t parity) {
 struct PsTcArgs {
     const uint8_t *a;   // [row tiles][nb][PS_TC_A_BLOCK]
     const uint8_t *b;   // [column groups][nb][PS_TC_B_BLOCK]
-    int nb, n_cg;
+    int nb, n_cg, n_units; // units = row tiles x column groups
     PsRwSeg seg[3];     // dst of a segment is [bs][rows of the segment]
     int n_seg, bs;
     const float *residual;
     int *err;           // set to 1 if a pipeline wait timed out (results invalid)
 };
 
-// One CTA per (128-row tile, 32-column group); blockIdx.x = row_tile * n_cg + cg so that the column groups sharing an A
-// tile run next to each other (A comes out of L2 for all but the first).
+// Persistent CTAs; unit u = (row tile u / n_cg, column group u % n_cg), so that the column groups sharing an A tile run at
+// the same time on neighbouring CTAs (A comes out of L2 for all but the first).
 __global__ void __launch_bounds__(PS_TC_THREADS, 1) ps_k_tc_gemm(const PsTcArgs a) {
     extern __shared__ __align__(1024) uint8_t ps_tc_smem[];
-    __shared__ __align__(8) uint64_t bar_full[PS_TC_STAGES], bar_empty[PS_TC_STAGES], bar_tmem_full, bar_tmem_empty;
+    __shared__ __align__(8) uint64_t bar_full[PS_TC_STAGES], bar_empty[PS_TC_STAGES], bar_tmem_full[2], bar_tmem_empty[2];
     __shared__ uint32_t tmem_base_smem;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int rt = blockIdx.x / a.n_cg, cg = blockIdx.x % a.n_cg, nb = a.nb;
-    const uint8_t *ga = a.a + (size_t)rt * nb * PS_TC_A_BLOCK;
-    const uint8_t *gb = a.b + (size_t)cg * nb * PS_TC_B_BLOCK;
+    const int nb = a.nb;
+    const int my_units = (a.n_units > (int)blockIdx.x) ? (a.n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int n_steps = my_units * nb; // (unit, super-block) steps of this CTA, in order
 
     if (tid == 0) {
         for (int s = 0; s < PS_TC_STAGES; s++) {
             ps_mbar_init(&bar_full[s], 1);
             ps_mbar_init(&bar_empty[s], 1 + PS_TC_EPI_WARPS); // the MMA commit + every epilogue warp (they read xd / yd from the stage)
         }
-        ps_mbar_init(&bar_tmem_full, 1);
-        ps_mbar_init(&bar_tmem_empty, PS_TC_EPI_WARPS);
+        for (int b = 0; b < 2; b++) {
+            ps_mbar_init(&bar_tmem_full[b], 1);
+            ps_mbar_init(&bar_tmem_empty[b], PS_TC_EPI_WARPS);
+        }
         ps_fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
-    if (warp == PS_TC_EPI_WARPS + 1) { // the MMA warp owns the tensor memory: 512 columns (12 x 32 used)
+    if (warp == PS_TC_EPI_WARPS + 1) { // the MMA warp owns the tensor memory: 512 columns (2 x 12 x 16 used)
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 512;" ::"r"(ps_smem_u32(&tmem_base_smem)) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
@@ -201,13 +205,13 @@ __global__ void __launch_bounds__(PS_TC_THREADS, 1) ps_k_tc_gemm(const PsTcArgs 
     if (warp == PS_TC_EPI_WARPS) {
         // ===== TMA producer
         if (lane == 0) {
-            for (int i = 0; i < nb; i++) {
-                const int s = i % PS_TC_STAGES;
-                if (i >= PS_TC_STAGES && !ps_tc_wait(&bar_empty[s], ((i / PS_TC_STAGES) - 1) & 1)) { *a.err = 1; break; }
+            for (int g = 0; g < n_steps; g++) {
+                const int u = (int)blockIdx.x + (g / nb) * (int)gridDim.x, i = g % nb, s = g % PS_TC_STAGES;
+                if (g >= PS_TC_STAGES && !ps_tc_wait(&bar_empty[s], ((g / PS_TC_STAGES) - 1) & 1)) { *a.err = 1; break; }
                 uint8_t *st = ps_tc_smem + (size_t)s * PS_TC_STAGE;
                 ps_mbar_expect_tx(&bar_full[s], PS_TC_STAGE);
-                ps_bulk_g2s(st, ga + (size_t)i * PS_TC_A_BLOCK, PS_TC_A_BLOCK, &bar_full[s]);
-                ps_bulk_g2s(st + PS_TC_A_BLOCK, gb + (size_t)i * PS_TC_B_BLOCK, PS_TC_B_BLOCK, &bar_full[s]);
+                ps_bulk_g2s(st, a.a + ((size_t)(u / a.n_cg) * nb + i) * PS_TC_A_BLOCK, PS_TC_A_BLOCK, &bar_full[s]);
+                ps_bulk_g2s(st + PS_TC_A_BLOCK, a.b + ((size_t)(u % a.n_cg) * nb + i) * PS_TC_B_BLOCK, PS_TC_B_BLOCK, &bar_full[s]);
             }
         }
     } else if (warp == PS_TC_EPI_WARPS + 1) {
@@ -215,94 +219,91 @@ __global__ void __launch_bounds__(PS_TC_THREADS, 1) ps_k_tc_gemm(const PsTcArgs 
         if (lane == 0) {
             // kind::f16, D = F32 (c_format 1 @ bit 4), A = B = F16 (0), K-major both, N >> 3 @ bit 17, M >> 4 @ bit 24
             const uint32_t idesc = (1u << 4) | ((uint32_t)(PS_TC_N >> 3) << 17) | ((uint32_t)(PS_TC_M >> 4) << 24);
-            for (int i = 0; i < nb; i++) {
-                const int s = i % PS_TC_STAGES;
-                if (!ps_tc_wait(&bar_full[s], (i / PS_TC_STAGES) & 1)) { *a.err = 2; break; }
-                if (i > 0 && !ps_tc_wait(&bar_tmem_empty, (i - 1) & 1)) { *a.err = 3; break; } // the epilogue has drained the previous super-block
+            for (int g = 0; g < n_steps; g++) {
+                const int s = g % PS_TC_STAGES, tb = g & 1;
+                if (!ps_tc_wait(&bar_full[s], (g / PS_TC_STAGES) & 1)) { *a.err = 2; break; }
+                if (g >= 2 && !ps_tc_wait(&bar_tmem_empty[tb], ((g >> 1) - 1) & 1)) { *a.err = 3; break; } // that accumulator buffer has been drained
                 ps_tc_fence_after();
                 const uint32_t sa = ps_smem_u32(ps_tc_smem + (size_t)s * PS_TC_STAGE), sb = sa + PS_TC_A_BLOCK;
+                const uint32_t td = tmem_base + tb * (12 * PS_TC_N);
 #pragma unroll 1
                 for (int l = 0; l < 8; l++)
 #pragma unroll
                     for (int h = 0; h < 2; h++)
-                        ps_tc_mma_f16(tmem_base + l * PS_TC_N, ps_tc_smem_desc(sa + (2 * l + h) * PS_TC_A_TILE, (PS_TC_M / 8) * 128, 128),
+                        ps_tc_mma_f16(td + l * PS_TC_N, ps_tc_smem_desc(sa + (2 * l + h) * PS_TC_A_TILE, (PS_TC_M / 8) * 128, 128),
                                       ps_tc_smem_desc(sb + (2 * l + h) * PS_TC_B_TILE, (PS_TC_N / 8) * 128, 128), idesc, h);
 #pragma unroll 1
                 for (int k = 0; k < 4; k++)
-                    ps_tc_mma_f16(tmem_base + (8 + k) * PS_TC_N, ps_tc_smem_desc(sa + 16 * PS_TC_A_TILE, (PS_TC_M / 8) * 128, 128),
+                    ps_tc_mma_f16(td + (8 + k) * PS_TC_N, ps_tc_smem_desc(sa + 16 * PS_TC_A_TILE, (PS_TC_M / 8) * 128, 128),
                                   ps_tc_smem_desc(sb + (16 + k) * PS_TC_B_TILE, (PS_TC_N / 8) * 128, 128), idesc, 0);
-                ps_tc_commit(&bar_empty[s]);   // operands consumed
-                ps_tc_commit(&bar_tmem_full);  // accumulators of this super-block complete
+                ps_tc_commit(&bar_empty[s]);        // operands consumed
+                ps_tc_commit(&bar_tmem_full[tb]);   // accumulators of this super-block complete
             }
         }
     } else {
-        // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. +31 (rows) and columns 8 * (w / 4) .. +7 of every accumulator
-        const int row = 32 * (warp & 3) + lane, c0 = 8 * (warp >> 2);
-        float acc[8][12];
-#pragma unroll
-        for (int c = 0; c < 8; c++)
-#pragma unroll
-            for (int l = 0; l < 12; l++) acc[c][l] = 0.f;
+        // ===== epilogue: warp w owns TMEM lanes 32 * (w % 4) .. +31 (rows) and columns 4 * (w / 4) .. +3 of every accumulator
+        const int row = 32 * (warp & 3) + lane, c0 = 4 * (warp >> 2);
         const uint32_t t_lane = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + c0;
-        for (int i = 0; i < nb; i++) {
-            const int s = i % PS_TC_STAGES;
-            if (!ps_tc_wait(&bar_tmem_full, i & 1)) { *a.err = 4; break; }
-            ps_tc_fence_after();
-            const uint8_t *st = ps_tc_smem + (size_t)s * PS_TC_STAGE;
-            const float2 xs = reinterpret_cast<const float2 *>(st + (size_t)17 * PS_TC_A_TILE)[row];
-            const float *ydp = reinterpret_cast<const float *>(st + PS_TC_A_BLOCK + (size_t)20 * PS_TC_B_TILE) + c0;
-            float yd[8];
+        int g = 0;
+        bool ok = true;
+        for (int mu = 0; mu < my_units && ok; mu++) {
+            const int u = (int)blockIdx.x + mu * (int)gridDim.x, rt = u / a.n_cg, cg = u % a.n_cg;
+            float acc[4][12];
 #pragma unroll
-            for (int c = 0; c < 8; c++) yd[c] = ydp[c];
-            __syncwarp();
-            if (lane == 0) ps_mbar_arrive(&bar_empty[s]); // this warp no longer needs the stage
-            {
-                float d[8];
+            for (int c = 0; c < 4; c++)
 #pragma unroll
-                for (int c = 0; c < 8; c++) d[c] = __fmul_rn(yd[c], xs.x);
+                for (int l = 0; l < 12; l++) acc[c][l] = 0.f;
+            for (int i = 0; i < nb; i++, g++) {
+                const int s = g % PS_TC_STAGES, tb = g & 1;
+                if (!ps_tc_wait(&bar_tmem_full[tb], (g >> 1) & 1)) { *a.err = 4; ok = false; break; }
+                ps_tc_fence_after();
+                const uint8_t *st = ps_tc_smem + (size_t)s * PS_TC_STAGE;
+                const float2 xs = reinterpret_cast<const float2 *>(st + (size_t)17 * PS_TC_A_TILE)[row];
+                const float4 yd = *reinterpret_cast<const float4 *>(st + PS_TC_A_BLOCK + (size_t)20 * PS_TC_B_TILE + 4 * c0);
+                __syncwarp();
+                if (lane == 0) ps_mbar_arrive(&bar_empty[s]); // this warp no longer needs the stage
+                uint32_t v[12][4];
 #pragma unroll
-                for (int l = 0; l < 8; l++) {
-                    float v[8];
-                    ps_tc_ld8(t_lane + l * PS_TC_N, v);
-                    ps_tc_ld_wait();
+                for (int l = 0; l < 12; l++)
+                    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0,%1,%2,%3}, [%4];"
+                                 : "=r"(v[l][0]), "=r"(v[l][1]), "=r"(v[l][2]), "=r"(v[l][3])
+                                 : "r"(t_lane + tb * (12 * PS_TC_N) + l * PS_TC_N)
+                                 : "memory");
+                ps_tc_ld_wait();
+                ps_tc_fence_before();
+                __syncwarp();
+                if (lane == 0) ps_mbar_arrive(&bar_tmem_empty[tb]); // the integers are in registers: the buffer can be refilled
+                const float ydc[4] = {yd.x, yd.y, yd.z, yd.w};
 #pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c][l] = __fmaf_rn(d[c], v[c], acc[c][l]); // v is the exact integer S_l
-                }
+                for (int c = 0; c < 4; c++) {
+                    const float d = __fmul_rn(ydc[c], xs.x), dm = __fmul_rn(-ydc[c], xs.y);
 #pragma unroll
-                for (int c = 0; c < 8; c++) d[c] = __fmul_rn(-yd[c], xs.y);
-#pragma unroll
-                for (int l = 8; l < 12; l++) {
-                    float v[8];
-                    ps_tc_ld8(t_lane + l * PS_TC_N, v);
-                    ps_tc_ld_wait();
-#pragma unroll
-                    for (int c = 0; c < 8; c++) acc[c][l] = __fmaf_rn(d[c], v[c], acc[c][l]); // v is the exact integer P_k
+                    for (int l = 0; l < 12; l++) // v is the exact integer S_l (l < 8) / P_k (l >= 8)
+                        acc[c][l] = __fmaf_rn(l < 8 ? d : dm, __uint_as_float(v[l][c]), acc[c][l]);
                 }
             }
-            ps_tc_fence_before();
-            __syncwarp();
-            if (lane == 0) ps_mbar_arrive(&bar_tmem_empty);
-        }
-        // ---- hsum_float_8 + mins sum (ggml-quants.c:62-68, 7862-7871), bias / residual, dst[col][row]
-        const int grow = rt * PS_TC_M + row;
-        int sg = 0;
-        if (a.n_seg > 1 && grow >= a.seg[1].row_begin) sg = 1;
-        if (a.n_seg > 2 && grow >= a.seg[2].row_begin) sg = 2;
-        if (grow < a.seg[sg].row_end) {
-            const int n = grow - a.seg[sg].row_begin, ld = a.seg[sg].row_end - a.seg[sg].row_begin;
-            const float bias = a.seg[sg].bias ? a.seg[sg].bias[n] : 0.f;
+            if (!ok) break;
+            // ---- hsum_float_8 + mins sum (ggml-quants.c:62-68, 7862-7871), bias / residual, dst[col][row]
+            const int grow = rt * PS_TC_M + row;
+            int sg = 0;
+            if (a.n_seg > 1 && grow >= a.seg[1].row_begin) sg = 1;
+            if (a.n_seg > 2 && grow >= a.seg[2].row_begin) sg = 2;
+            if (grow < a.seg[sg].row_end) {
+                const int n = grow - a.seg[sg].row_begin, ld = a.seg[sg].row_end - a.seg[sg].row_begin;
+                const float bias = a.seg[sg].bias ? a.seg[sg].bias[n] : 0.f;
 #pragma unroll
-            for (int c = 0; c < 8; c++) {
-                const int col = cg * PS_TC_N + c0 + c;
-                if (col < a.bs) {
-                    const float r0 = __fadd_rn(acc[c][4], acc[c][0]), r1 = __fadd_rn(acc[c][5], acc[c][1]);
-                    const float r2 = __fadd_rn(acc[c][6], acc[c][2]), r3 = __fadd_rn(acc[c][7], acc[c][3]);
-                    float res = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
-                    res = __fadd_rn(res, __fadd_rn(__fadd_rn(acc[c][8], acc[c][10]), __fadd_rn(acc[c][9], acc[c][11])));
-                    const size_t o = (size_t)col * ld + n;
-                    if (a.seg[sg].bias) res = __fadd_rn(res, bias);
-                    if (a.residual) res = __fadd_rn(a.residual[o], res);
-                    a.seg[sg].dst[o] = res;
+                for (int c = 0; c < 4; c++) {
+                    const int col = cg * PS_TC_N + c0 + c;
+                    if (col < a.bs) {
+                        const float r0 = __fadd_rn(acc[c][4], acc[c][0]), r1 = __fadd_rn(acc[c][5], acc[c][1]);
+                        const float r2 = __fadd_rn(acc[c][6], acc[c][2]), r3 = __fadd_rn(acc[c][7], acc[c][3]);
+                        float res = __fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+                        res = __fadd_rn(res, __fadd_rn(__fadd_rn(acc[c][8], acc[c][10]), __fadd_rn(acc[c][9], acc[c][11])));
+                        const size_t o = (size_t)col * ld + n;
+                        if (a.seg[sg].bias) res = __fadd_rn(res, bias);
+                        if (a.residual) res = __fadd_rn(a.residual[o], res);
+                        a.seg[sg].dst[o] = res;
+                    }
                 }
             }
         }
