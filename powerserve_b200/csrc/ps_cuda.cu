@@ -129,6 +129,8 @@ struct ps_cuda_ctx {
     uint32_t *epoch_dev = nullptr; // [PS_TP_SLOTS] local epoch counters
     int *done_dev = nullptr;       // [PS_TP_SLOTS] local CTA arrival counters
     int *tp_err_dev = nullptr;
+    PsTpOut *tpo_dev = nullptr; // [PS_TP_SLOTS] link tables of the peer-store exchange
+    PsTpIn *tpi_dev = nullptr;
     float *tp_rows = nullptr;  // logits of a token-by-token tensor-parallel batch, [max_batch][vocab] (allocated on first use)
     int64_t n_gather = 0;      // all-gathers enqueued (counter "tp_allgathers")
     uint8_t *ximg = nullptr;   // Q8_K images of up to max_batch activation columns (multi-column row-walker)
@@ -348,29 +350,10 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
-// peer-store all-gather links of one phase (`slot`): where the producer's rows land on every rank, and what the consumer waits for
-PsTpOut tp_out(ps_cuda_ctx *ctx, int slot, size_t heap_off_bytes, size_t my_elem_off) {
-    PsTpOut o{};
-    if (!ctx->p2p) return o;
-    o.n = ctx->tp;
-    for (int p = 0; p < ctx->tp; p++) {
-        o.peer_dst[p] = reinterpret_cast<float *>(ctx->peer_heap[p] + heap_off_bytes) + my_elem_off;
-        o.peer_idx[p] = reinterpret_cast<int *>(ctx->peer_heap[p] + ctx->off_idx) + my_elem_off;
-        o.peer_flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_heap[p] + ctx->off_flags) + slot * PS_TP_MAX + ctx->rank;
-    }
-    o.epoch = ctx->epoch_dev + slot;
-    o.done = ctx->done_dev + slot;
-    return o;
-}
-PsTpIn tp_in(ps_cuda_ctx *ctx, int slot) {
-    PsTpIn i{};
-    if (!ctx->p2p) return i;
-    i.n = ctx->tp;
-    i.flags = reinterpret_cast<const uint32_t *>(ctx->heap + ctx->off_flags) + slot * PS_TP_MAX;
-    i.epoch = ctx->epoch_dev + slot;
-    i.err = ctx->tp_err_dev;
-    return i;
-}
+// peer-store all-gather links of one phase (`slot`), resident in device memory (built once by ps_cuda_tp_import): where
+// the producer's rows land on every rank, and what the consumer waits for.  Null when the exchange is not peer-to-peer.
+const PsTpOut *tp_out(ps_cuda_ctx *ctx, int slot) { return ctx->p2p ? ctx->tpo_dev + slot : nullptr; }
+const PsTpIn *tp_in(ps_cuda_ctx *ctx, int slot) { return ctx->p2p ? ctx->tpi_dev + slot : nullptr; }
 
 // all-gather over the tensor-parallel group (NCCL on the context stream; capturable into the decode graph)
 int tp_all_gather(ps_cuda_ctx *ctx, const void *send, void *recv, size_t count, bool is_int = false, bool always = false) {
@@ -388,7 +371,7 @@ int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     const ps_cuda_model_desc &d = ctx->d;
     const int qdim = ctx->nh_l * d.head_size, kvd = ctx->nkv_l * d.head_size;
     PsRwArgs a{};
-    if (L > 0) a.tpi = tp_in(ctx, PS_TP_SLOT_X2);
+    a.tpi = L > 0 ? tp_in(ctx, PS_TP_SLOT_X2) : nullptr;
     a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
     a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim, PS_RW_OUT_ROPE};
     a.seg[1] = {ctx->kc[L], d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd, PS_RW_OUT_ROPE_KCACHE};
@@ -413,11 +396,11 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
     const size_t a2smem = (size_t)R2 * (size_t)((d.n_ctx + 31) & ~31) * 4;
     return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
                     (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx),
-                    tp_out(ctx, PS_TP_SLOT_ATT, ctx->off_att, (size_t)ctx->rank * ctx->nh_l * hs));
+                    tp_out(ctx, PS_TP_SLOT_ATT));
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
               bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0,
-              PsTpIn tpi = PsTpIn{}, PsTpOut tpo = PsTpOut{}) {
+              const PsTpIn *tpi = nullptr, const PsTpOut *tpo = nullptr) {
     PsRwArgs a{};
     a.tpi = tpi; a.tpo = tpo;
     a.xq_in = xq_in;
@@ -435,7 +418,7 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     a.seg[0] = {ctx->g_part, nullptr, 0, ctx->ffn_l, 0};
     a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
     a.tpi = tp_in(ctx, PS_TP_SLOT_X1);
-    a.tpo = tp_out(ctx, PS_TP_SLOT_H, ctx->off_h, (size_t)ctx->rank * ctx->ffn_l);
+    a.tpo = tp_out(ctx, PS_TP_SLOT_H);
     if (ctx->tp == 1) { a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt; } // the Q8_K hand-off needs the whole vector on one GPU
     return launch_rw(ctx, a, PS_EPI_SILU);
 }
@@ -510,21 +493,20 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
         const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
         // x[rows of this rank] += Wo[rows] . att
         if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, ctx->x + (size_t)rank * dim_l, false, nullptr, ld.ffn_norm, 0,
-                            tp_in(ctx, PS_TP_SLOT_ATT), tp_out(ctx, PS_TP_SLOT_X1, ctx->off_x, (size_t)rank * dim_l)))) return rc;
+                            tp_in(ctx, PS_TP_SLOT_ATT), tp_out(ctx, PS_TP_SLOT_X1)))) return rc;
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
         if ((rc = tp_all_gather(ctx, ctx->g_part, ctx->h_full, (size_t)ctx->ffn_l))) return rc;
         if ((rc = rw_single(ctx, ld.rw_down, dim_l, ffn, ctx->x_part, ctx->h_full, nullptr, ctx->x + (size_t)rank * dim_l, false,
                             tp == 1 ? ctx->hq : nullptr, norm_after, 0, tp_in(ctx, PS_TP_SLOT_H),
-                            tp_out(ctx, PS_TP_SLOT_X2, ctx->off_x, (size_t)rank * dim_l)))) return rc;     // x[rows] += Wdown[rows] . g
+                            tp_out(ctx, PS_TP_SLOT_X2)))) return rc;     // x[rows] += Wdown[rows] . g
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
     }
     if (lm_head) {
         const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
         if ((rc = rw_single(ctx, ctx->rw_out, ctx->vocab_l, dim, ctx->logits_part, ctx->x, ctx->w_out_norm, nullptr, pick, nullptr, nullptr,
-                            rank * ctx->vocab_l, d.n_layers > 0 ? tp_in(ctx, PS_TP_SLOT_X2) : PsTpIn{},
-                            pick ? tp_out(ctx, PS_TP_SLOT_PART, ctx->off_val, (size_t)rank * n_part)
-                                 : tp_out(ctx, PS_TP_SLOT_LOGITS, ctx->off_logits, (size_t)rank * ctx->vocab_l)))) return rc;
+                            rank * ctx->vocab_l, tp_in(ctx, PS_TP_SLOT_X2),
+                            pick ? tp_out(ctx, PS_TP_SLOT_PART) : tp_out(ctx, PS_TP_SLOT_LOGITS)))) return rc;
         if (pick) {
             const float *pv = ctx->part_val;
             const int *pi = ctx->part_idx;
@@ -1363,6 +1345,37 @@ int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n) {
         void *ptr = nullptr;
         PS_CK(cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess));
         ctx->peer_heap[p] = (uint8_t *)ptr;
+    }
+    {   // link tables: per slot, where this rank's shard lands on every rank, the flag it publishes, and what it waits for
+        const ps_cuda_model_desc &d = ctx->d;
+        const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
+        const size_t off[PS_TP_SLOTS] = {ctx->off_att, ctx->off_x, ctx->off_h, ctx->off_x, ctx->off_val, ctx->off_logits};
+        const size_t mine[PS_TP_SLOTS] = {(size_t)ctx->rank * ctx->nh_l * d.head_size, (size_t)ctx->rank * ctx->dim_l, (size_t)ctx->rank * ctx->ffn_l,
+                                          (size_t)ctx->rank * ctx->dim_l, (size_t)ctx->rank * n_part, (size_t)ctx->rank * ctx->vocab_l};
+        PsTpOut to[PS_TP_SLOTS];
+        PsTpIn ti[PS_TP_SLOTS];
+        memset(to, 0, sizeof to);
+        memset(ti, 0, sizeof ti);
+        for (int s = 0; s < PS_TP_SLOTS; s++) {
+            to[s].n = ti[s].n = ctx->tp;
+            for (int p = 0; p < ctx->tp; p++) {
+                to[s].peer_dst[p] = reinterpret_cast<float *>(ctx->peer_heap[p] + off[s]) + mine[s];
+                to[s].peer_idx[p] = reinterpret_cast<int *>(ctx->peer_heap[p] + ctx->off_idx) + mine[s];
+                to[s].peer_flag[p] = reinterpret_cast<uint32_t *>(ctx->peer_heap[p] + ctx->off_flags) + s * PS_TP_MAX + ctx->rank;
+            }
+            to[s].epoch = ctx->epoch_dev + s;
+            to[s].done = ctx->done_dev + s;
+            ti[s].flags = reinterpret_cast<const uint32_t *>(ctx->heap + ctx->off_flags) + s * PS_TP_MAX;
+            ti[s].epoch = ctx->epoch_dev + s;
+            ti[s].err = ctx->tp_err_dev;
+        }
+        if (!ctx->tpo_dev) {
+            int rc = dev_alloc(ctx, (void **)&ctx->tpo_dev, sizeof to);
+            if (rc) return rc;
+            if ((rc = dev_alloc(ctx, (void **)&ctx->tpi_dev, sizeof ti))) return rc;
+        }
+        PS_CK(cudaMemcpy(ctx->tpo_dev, to, sizeof to, cudaMemcpyHostToDevice));
+        PS_CK(cudaMemcpy(ctx->tpi_dev, ti, sizeof ti, cudaMemcpyHostToDevice));
     }
     ctx->p2p = true;
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }

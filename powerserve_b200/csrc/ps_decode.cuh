@@ -88,7 +88,9 @@ PS_D uint32_t ps_ld_acquire_sys(const uint32_t *p) {
 PS_D void ps_st_release_sys(uint32_t *p, uint32_t v) { asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
 // consumer: ONE thread of the CTA calls this after griddepcontrol.wait and before the CTA touches the gathered vector
-PS_D void ps_tp_wait(const PsTpIn &in) {
+PS_D void ps_tp_wait(const PsTpIn *inp) {
+    if (!inp) return;
+    const PsTpIn in = *inp;
     if (in.n == 0) return;
     const uint32_t e = *reinterpret_cast<const volatile uint32_t *>(in.epoch);
     for (int s = 0; s < in.n; s++) {
@@ -99,7 +101,9 @@ PS_D void ps_tp_wait(const PsTpIn &in) {
     }
 }
 // producer: every thread's stores are done (CTA-wide barrier before the call); ONE thread of the CTA calls this
-PS_D void ps_tp_signal(const PsTpOut &out, int n_ctas) {
+PS_D void ps_tp_signal(const PsTpOut *outp, int n_ctas) {
+    if (!outp) return;
+    const PsTpOut &out = *outp;
     if (out.n == 0) return;
     __threadfence_system();
     if (atomicAdd(out.done, 1) == n_ctas - 1) {
@@ -112,7 +116,7 @@ PS_D void ps_tp_signal(const PsTpOut &out, int n_ctas) {
 }
 
 // stand-alone consumer wait (before a device-to-host copy of a gathered vector)
-__global__ void ps_k_tp_wait(const PsTpIn tpi) {
+__global__ void ps_k_tp_wait(const PsTpIn *tpi) {
     ps_grid_dep_wait();
     if (threadIdx.x == 0) ps_tp_wait(tpi);
 }
@@ -268,7 +272,7 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 // lane order, leftovers in order) with 16 loads in flight per lane.
 template <int R2>
 __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
-                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut tpo) {
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut *tpo) {
     extern __shared__ float s_p[]; // [R2][stride]
     __shared__ double shd[8];
     __shared__ float shf[8];
@@ -368,10 +372,11 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
             for (int h2 = 1; h2 < R2; h2++)
                 if (lane == h2) v = sum[h2];
             att[(int64_t)(g * R2 + lane) * hs + d] = v;
-            for (int p = 0; p < tpo.n; p++) tpo.peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v; // all-gather by peer stores
+            if (tpo)
+                for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v; // all-gather by peer stores
         }
     }
-    if (tpo.n) {
+    if (tpo) {
         __syncthreads();
         if (tid == 0) ps_tp_signal(tpo, (int)(gridDim.x * gridDim.y));
     }
@@ -408,13 +413,13 @@ __global__ void __launch_bounds__(256) ps_k_embed_dev(float *__restrict__ dst, c
 // ids[*ctr] = argmax, token feedback, position and counter advance.
 __global__ void __launch_bounds__(256) ps_k_argmax_step(const float *__restrict__ part_val, const int *__restrict__ part_idx, int n_part,
                                                         int32_t *__restrict__ ids, int32_t *__restrict__ ctr, int32_t *__restrict__ next_token,
-                                                        int32_t *__restrict__ pos, long long *tl, const PsTpIn tpi) {
+                                                        int32_t *__restrict__ pos, long long *tl, const PsTpIn *tpi) {
     __shared__ float sv[8];
     __shared__ int si[8];
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
-    if (tpi.n) {
+    if (tpi) {
         if (threadIdx.x == 0) ps_tp_wait(tpi);
         __syncthreads();
     }

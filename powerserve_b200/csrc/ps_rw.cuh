@@ -63,8 +63,8 @@ struct PsRwArgs {
     double inv_k;          // 1 / K when K is a power of two (the mean is then an exact scaling), else 0
     float *part_val;       // optional (lm_head): per-CTA partial arg-max of the produced rows, [gridDim.x]
     int *part_idx;
-    PsTpOut tpo;           // tensor parallel: the output rows (or the arg-max partials) are stored into every rank's buffer
-    PsTpIn tpi;            // tensor parallel: the activation vector x is a gathered vector — wait for the peers' shards
+    const PsTpOut *tpo;    // tensor parallel (else null): the output rows (or the arg-max partials) go into every rank's buffer
+    const PsTpIn *tpi;     // tensor parallel (else null): x is a gathered vector — wait for the peers' shards
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
 };
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     do {                                                                                                                 \
         if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
     } while (0)
-    if (a.tpi.n && tid == 0) ps_tp_wait(a.tpi); // the gathered activation vector is complete on this rank
+    if (a.tpi && tid == 0) ps_tp_wait(a.tpi); // the gathered activation vector is complete on this rank
     ps_bar_sync(1, PS_RW_THREADS + 32);         // mbarriers initialised by the helper (and the wait above is over)
     if (a.next_norm_w && blockIdx.x == 0)
         for (int i = tid * 32; i < a.next_norm_n; i += PS_RW_THREADS * 32)
@@ -331,7 +331,8 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             if (q == 0 && row < a.seg[0].row_end) {
                 const float hv = ps_silu_mul(g, u);
                 a.seg[0].dst[row] = hv;
-                for (int p = 0; p < a.tpo.n; p++) a.tpo.peer_dst[p][row] = hv; // all-gather by peer stores
+                if (a.tpo)
+                    for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][row] = hv; // all-gather by peer stores
             }
             if (a.xq_out) {
                 const int i = oct >> 5; // 32 octets per 256-row block
@@ -382,8 +383,8 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             } else if (q == 0 && live) {
                 if (EPI == PS_EPI_RESIDUAL) res = __fadd_rn(a.residual[n], res);
                 a.seg[sg].dst[n] = res;
-                if (EPI == PS_EPI_RESIDUAL || !a.part_val)
-                    for (int p = 0; p < a.tpo.n; p++) a.tpo.peer_dst[p][n] = res; // all-gather by peer stores
+                if (a.tpo && (EPI == PS_EPI_RESIDUAL || !a.part_val))
+                    for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][n] = res; // all-gather by peer stores
                 if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
             }
         }
@@ -405,11 +406,12 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             const int gi = (best_i == 0x7fffffff) ? best_i : best_i + a.idx_offset;
             a.part_val[blockIdx.x] = best_v;
             a.part_idx[blockIdx.x] = gi;
-            for (int p = 0; p < a.tpo.n; p++) { a.tpo.peer_dst[p][blockIdx.x] = best_v; a.tpo.peer_idx[p][blockIdx.x] = gi; }
+            if (a.tpo)
+                for (int p = 0; p < a.tpo->n; p++) { a.tpo->peer_dst[p][blockIdx.x] = best_v; a.tpo->peer_idx[p][blockIdx.x] = gi; }
         }
     }
     ps_bar_sync(2, PS_RW_THREADS);
-    if (a.tpo.n && tid == 0) ps_tp_signal(a.tpo, (int)gridDim.x);
+    if (a.tpo && tid == 0) ps_tp_signal(a.tpo, (int)gridDim.x);
     ps_tl_max(a.tl, 1);
 }
 
