@@ -99,7 +99,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -321,20 +321,26 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     a.tl = tl_slot(ctx);
+    a.cta_tl = a.tl ? ctx->trace_dev + (size_t)256 * 8 : nullptr; // slots 256 .. 256 + grid of the trace buffer
     a.inv_k = (a.K & (a.K - 1)) == 0 ? 1.0 / (double)a.K : 0.0;
     const int nb = a.K / 256, rpt = (epi == PS_EPI_SILU) ? 2 : 1;
     if (nb > 4 * PS_RW_WARPS) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: K=%d too large", a.K);
-    int kb = (rpt == 2) ? 2 : 4;
-    while (nb % kb) kb >>= 1;
     const int grid = std::min(ctx->n_sm, a.n_oct);
     const int per_cta = (a.n_oct + grid - 1) / grid;
-    a.kb = kb;
     a.n_act = std::min(PS_RW_WARPS, per_cta);
-    const size_t stage = (size_t)kb * rpt * PS_RW_OCTET_BLOCK, fixed = (size_t)a.K + (size_t)nb * 32;
-    const size_t budget = 200 * 1024;
-    int ns = (int)((budget - fixed) / ((size_t)a.n_act * (stage + 8)));
-    ns = std::min(ns, PS_RW_MAX_NS);
-    if (ns < 2) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
+    // stage = kb octet-blocks: the largest divisor of nb (<= 16 blocks, option "rw_kb") that leaves every warp a ring of
+    // >= 2 stages; a stage boundary (mbarrier wait + re-arm) costs the consuming warp ~150-250 cycles, so fewer is better
+    const size_t unit = (size_t)rpt * PS_RW_OCTET_BLOCK, fixed = (size_t)a.K + (size_t)nb * 32, budget = 200 * 1024;
+    const int kb_cap = std::max(1, (ctx->opt_kb > 0 ? ctx->opt_kb : 16) / rpt);
+    int kb = 0, ns = 0;
+    for (int c = std::min(nb, kb_cap); c >= 1; c--) {
+        if (nb % c) continue;
+        const int n = std::min((int)((budget - fixed) / ((size_t)a.n_act * ((size_t)c * unit + 8))), PS_RW_MAX_NS);
+        if (n >= 2) { kb = c; ns = n; break; }
+    }
+    if (!kb) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
+    const size_t stage = (size_t)kb * unit;
+    a.kb = kb;
     a.ns = ns;
     const size_t smem = fixed + (size_t)a.n_act * ns * (stage + 8);
     static bool attr[64] = {};
@@ -1403,6 +1409,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
+    else if (!strcmp(name, "rw_kb")) ctx->opt_kb = value; // tuning: cap on the blocks per TMA stage of the row-walker mat-vec
     else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {

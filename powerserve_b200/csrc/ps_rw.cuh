@@ -23,7 +23,9 @@
 
 #define PS_RW_WARPS 16
 #define PS_RW_THREADS (PS_RW_WARPS * 32)
-#define PS_RW_OCTET_BLOCK 1152                 // 8 rows x 144 bytes
+#define PS_RW_OCTET_BLOCK 1184                 // 8 rows x 148 bytes: the 144 bytes of a Q4_K block with its 6-bit scales / mins expanded to bytes
+#define PS_RW_HDR2 128                         // offset of the second header array (mins 4..7, 4 bytes per row)
+#define PS_RW_QS 160                           // offset of the four 256-byte quant groups
 #define PS_RW_MAX_NS 8
 
 enum { PS_RW_OUT_PLAIN = 0, PS_RW_OUT_ROPE = 1, PS_RW_OUT_ROPE_KCACHE = 2, PS_RW_OUT_VCACHE_T = 3 };
@@ -67,6 +69,7 @@ struct PsRwArgs {
     const PsTpIn *tpi;     // tensor parallel (else null): x is a gathered vector — wait for the peers' shards
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
+    long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (option "trace", the pre-quantised-input launches)
 };
 
 // ---------------------------------------------------------------------------------------------------- repack
@@ -75,7 +78,7 @@ struct PsRwArgs {
 __global__ void ps_k_rw_repack(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n_rows, int64_t nb, int64_t oct0, int slot,
                                int n_slots) {
     const int64_t n_oct = (n_rows + 7) / 8;
-    const int64_t total = n_oct * nb * 72; // 16-byte chunks
+    const int64_t total = n_oct * nb * 72; // 16-byte chunks of the source blocks
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
         const int c = (int)(t % 9);
         const int r = (int)((t / 9) % 8);
@@ -85,8 +88,17 @@ __global__ void ps_k_rw_repack(uint8_t *__restrict__ dst, const uint8_t *__restr
         uint4 v = make_uint4(0, 0, 0, 0);
         if (row < n_rows) v = *reinterpret_cast<const uint4 *>(src + (row * nb + i) * PS_Q4_K_BYTES + 16 * c);
         uint8_t *ob = dst + (((oct0 + o) * nb + i) * n_slots + slot) * PS_RW_OCTET_BLOCK;
-        const int off = (c == 0) ? 16 * r : 128 + 256 * ((c - 1) >> 1) + 32 * r + 16 * ((c - 1) & 1);
-        *reinterpret_cast<uint4 *>(ob + off) = v;
+        if (c == 0) {
+            // d | dmin, then the twelve packed bytes as eight scale bytes and eight min bytes: the utmp shuffle of
+            // ggml_vec_dot_q4_K_q8_K (ggml-quants.c:7816-7826) == get_scale_min_k4, done once here instead of per block per token
+            const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
+            const uint32_t scA = v.y & k1, scB = (v.w & k2) | (((v.y >> 6) & k3) << 4);
+            const uint32_t mA = v.z & k1, mB = ((v.w >> 4) & k2) | (((v.z >> 6) & k3) << 4);
+            *reinterpret_cast<uint4 *>(ob + 16 * r) = make_uint4(v.x, scA, scB, mA);
+            *reinterpret_cast<uint32_t *>(ob + PS_RW_HDR2 + 4 * r) = mB;
+        } else {
+            *reinterpret_cast<uint4 *>(ob + PS_RW_QS + 256 * ((c - 1) >> 1) + 32 * r + 16 * ((c - 1) & 1)) = v;
+        }
     }
 }
 
@@ -97,18 +109,27 @@ struct PsRwAcc {
     float a0, a1, am;
 };
 
-PS_D void ps_rw_block(const uint8_t *ob, int r, int q, const uint4 *qa, const uint2 meta, PsRwAcc &acc) {
-    const uint4 h = *reinterpret_cast<const uint4 *>(ob + 16 * r);
-    const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
-    const uint32_t scA = h.y & k1, scB = (h.w & k2) | (((h.y >> 6) & k3) << 4);   // utmp shuffle, :7816-7826
-    const uint32_t mA = h.z & k1, mB = ((h.w >> 4) & k2) | (((h.z >> 6) & k3) << 4);
+// byte k of w as an int (one PRMT)
+PS_D int ps_rw_byte(uint32_t w, int k) { return (int)__byte_perm(w, 0, 0x4440 + k); }
+// offset, inside an octet block, of the 16-bit pair of mins (2q, 2q+1) of row r
+PS_D int ps_rw_mins_off(int r, int q) { return (q < 2) ? 16 * r + 12 + 2 * q : PS_RW_HDR2 + 4 * r + 2 * (q - 2); }
+// prod lane q: mins(2q) * bsums(2q) + mins(2q+1) * bsums(2q+1)  (_mm_madd_epi16(mins, q8s), :7830-7833); exact integers
+PS_D int ps_rw_mins_dot(uint32_t bsums_pair, uint32_t mins_pair) {
+    int d;
+    asm("dp2a.lo.s32.u32 %0, %1, %2, %3;" : "=r"(d) : "r"(bsums_pair), "r"(mins_pair), "r"(0));
+    return d;
+}
+
+PS_D void ps_rw_block(const uint8_t *ob, int r, int q, int moff, const uint4 *qa, const uint2 meta, PsRwAcc &acc) {
+    const uint4 h = *reinterpret_cast<const uint4 *>(ob + 16 * r); // d | dmin, scales 0..3, scales 4..7, mins 0..3
+    const uint32_t mp = *reinterpret_cast<const uint16_t *>(ob + moff);
     int S0 = 0, S1 = 0, H0 = 0, H1 = 0;
 #pragma unroll
     for (int j2 = 0; j2 < 4; j2++) {
-        const uint2 w = *reinterpret_cast<const uint2 *>(ob + 128 + 256 * j2 + 32 * r + 8 * q);
+        const uint2 w = *reinterpret_cast<const uint2 *>(ob + PS_RW_QS + 256 * j2 + 32 * r + 8 * q);
         const uint4 a = qa[j2 * 4 + q];
-        const uint32_t scw = (j2 < 2) ? scA : scB;
-        const int s_lo = (scw >> (16 * (j2 & 1))) & 0xff, s_hi = (scw >> (16 * (j2 & 1) + 8)) & 0xff;
+        const uint32_t scw = (j2 < 2) ? h.y : h.z;
+        const int s_lo = ps_rw_byte(scw, 2 * (j2 & 1)), s_hi = ps_rw_byte(scw, 2 * (j2 & 1) + 1);
         S0 += s_lo * __dp4a((int)(w.x & 0x0f0f0f0fu), (int)a.x, 0);
         S1 += s_lo * __dp4a((int)(w.y & 0x0f0f0f0fu), (int)a.y, 0);
         H0 += s_hi * ps_dp4a_us(w.x & 0xf0f0f0f0u, (int)a.z, 0);   // 16 x the high-nibble dot
@@ -116,9 +137,7 @@ PS_D void ps_rw_block(const uint8_t *ob, int r, int q, const uint4 *qa, const ui
     }
     S0 += H0 >> 4;
     S1 += H1 >> 4;
-    const uint32_t mw = (q < 2) ? mA : mB;
-    const int m0 = (mw >> (16 * (q & 1))) & 0xff, m1 = (mw >> (16 * (q & 1) + 8)) & 0xff;
-    const int P = m0 * (int)(short)(meta.y & 0xffffu) + m1 * (int)(short)(meta.y >> 16);
+    const int P = ps_rw_mins_dot(meta.y, mp);
     const float yd = __uint_as_float(meta.x);
     const float d = __fmul_rn(yd, ps_half_bits_to_float(h.x & 0xffffu));
     const float dm = __fmul_rn(-yd, ps_half_bits_to_float(h.x >> 16));
@@ -300,7 +319,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     uint64_t *my_bar = s_bar + warp * ns;
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
-    int s = 0;
+    int s = 0, slot = 0;
+    uint32_t phase = 0;
+    const int moff = ps_rw_mins_off(r, q);
+    long long wcyc = 0; // trace: cycles this warp spent waiting for weight stages
+    const long long c_begin = a.tl ? clock64() : 0, t_begin = a.tl ? ps_globaltimer() : 0;
 #pragma unroll 1
     for (int m = 0; m < n_mine; m++) {
         const int oct = o0 + warp + m * a.n_act;
@@ -309,8 +332,9 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
         for (int t = 0; t < RPT; t++) acc[t].a0 = acc[t].a1 = acc[t].am = 0.f;
 #pragma unroll 1
         for (int sb = 0; sb < spo; sb++, s++) {
-            const int slot = s % ns;
-            ps_mbar_wait(&my_bar[slot], (s / ns) & 1);
+            const long long c0 = a.tl ? clock64() : 0;
+            ps_mbar_wait(&my_bar[slot], phase);
+            if (a.tl) wcyc += clock64() - c0;
             const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
 #pragma unroll 1
             for (int b = 0; b < kb; b++) {
@@ -318,10 +342,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
                 const uint4 *qa = s_qa + (size_t)i * 16;
                 const uint2 meta = s_meta[i * 4 + q];
 #pragma unroll
-                for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, qa, meta, acc[t]);
+                for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, moff, qa, meta, acc[t]);
             }
             __syncwarp();
             if (lane == 0 && s + ns < n_stages) issue(warp, s + ns); // the slot is drained: re-arm it
+            if (++slot == ns) { slot = 0; phase ^= 1; }
         }
         // ---- epilogue
         const int row = oct * 8 + r;
@@ -388,6 +413,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
                 if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
             }
         }
+    }
+    if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + 7), (unsigned long long)wcyc);
+    if (a.cta_tl && a.xq_in && tid == 0) { // per-CTA stream trace (tools/timeline.py --cta)
+        long long *c = a.cta_tl + (size_t)blockIdx.x * 8;
+        c[0] = t_dep; c[1] = t_begin; c[2] = ps_globaltimer(); c[3] = clock64() - c_begin; c[4] = wcyc; c[5] = n_mine * nb; c[6] = o1 - o0;
     }
     if (EPI == PS_EPI_STORE && a.part_val) { // greedy pick, stage 1: the CTA's best (value, lowest index)
         __shared__ float sv[PS_RW_WARPS];
@@ -509,6 +539,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
 #pragma unroll 1
             for (int sb = 0; sb < spo; sb++, s++) {
                 const int slot = s % ns;
+                const int moff = ps_rw_mins_off(r, q);
                 ps_mbar_wait(&my_bar[slot], (s / ns) & 1);
                 const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
 #pragma unroll 1
@@ -517,22 +548,18 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
                     const uint8_t *ob = st + (size_t)b * PS_RW_OCTET_BLOCK;
                     // ---- unpack the weight block once (see ps_rw_block)
                     const uint4 h = *reinterpret_cast<const uint4 *>(ob + 16 * r);
-                    const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
-                    const uint32_t scA = h.y & k1, scB = (h.w & k2) | (((h.y >> 6) & k3) << 4);
-                    const uint32_t mA = h.z & k1, mB = ((h.w >> 4) & k2) | (((h.z >> 6) & k3) << 4);
+                    const uint32_t mp = *reinterpret_cast<const uint16_t *>(ob + moff);
                     uint32_t lo[8], hi[8];
                     int s_lo[4], s_hi[4];
 #pragma unroll
                     for (int j2 = 0; j2 < 4; j2++) {
-                        const uint2 w = *reinterpret_cast<const uint2 *>(ob + 128 + 256 * j2 + 32 * r + 8 * q);
+                        const uint2 w = *reinterpret_cast<const uint2 *>(ob + PS_RW_QS + 256 * j2 + 32 * r + 8 * q);
                         lo[2 * j2] = w.x & 0x0f0f0f0fu; lo[2 * j2 + 1] = w.y & 0x0f0f0f0fu;
                         hi[2 * j2] = w.x & 0xf0f0f0f0u; hi[2 * j2 + 1] = w.y & 0xf0f0f0f0u;
-                        const uint32_t scw = (j2 < 2) ? scA : scB;
-                        s_lo[j2] = (scw >> (16 * (j2 & 1))) & 0xff;
-                        s_hi[j2] = (scw >> (16 * (j2 & 1) + 8)) & 0xff;
+                        const uint32_t scw = (j2 < 2) ? h.y : h.z;
+                        s_lo[j2] = ps_rw_byte(scw, 2 * (j2 & 1));
+                        s_hi[j2] = ps_rw_byte(scw, 2 * (j2 & 1) + 1);
                     }
-                    const uint32_t mw = (q < 2) ? mA : mB;
-                    const int m0 = (mw >> (16 * (q & 1))) & 0xff, m1 = (mw >> (16 * (q & 1) + 8)) & 0xff;
                     const float xd = ps_half_bits_to_float(h.x & 0xffffu), xmin = ps_half_bits_to_float(h.x >> 16);
                     // ---- every column of the group
 #pragma unroll
@@ -551,7 +578,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
                             }
                             S0 += H0 >> 4;
                             S1 += H1 >> 4;
-                            const int P = m0 * (int)(short)(meta.y & 0xffffu) + m1 * (int)(short)(meta.y >> 16);
+                            const int P = ps_rw_mins_dot(meta.y, mp);
                             const float yd = __uint_as_float(meta.x);
                             const float d = __fmul_rn(yd, xd), dm = __fmul_rn(-yd, xmin);
                             acc[c].a0 = __fmaf_rn(d, __int2float_rn(S0), acc[c].a0);

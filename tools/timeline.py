@@ -24,6 +24,10 @@ m = capi.CudaModel(desc=desc, tensors=tmap)
 m.prefill(synth.random_prompt(shape.vocab_size, ctx_len + 1), 128)
 m.be.set_option("pdl", 0 if "--nopdl" in sys.argv else 1)
 m.be.set_option("graph", 0 if "--nograph" in sys.argv else 1)
+for a in sys.argv[1:]:
+    if a.startswith("--opt="):      # e.g. --opt=ksplit=0
+        k, v = a[6:].split("=")
+        m.be.set_option(k, int(v))
 m.decode_greedy(1, 4)          # graph capture + warm-up
 m.decode_greedy(1, 16)
 ms = m.be.counter("last_device_ns") / 1e6 / 16
@@ -32,6 +36,8 @@ m.decode_greedy(1, 1)
 n = 1 + 6 * shape.n_layers + 2
 buf = np.zeros((n, 8), np.int64)
 m.be._ck(m.be.L.ps_cuda_read_trace(m.be.h, buf.ctypes.data, n))
+big = np.zeros((512, 8), np.int64)
+m.be._ck(m.be.L.ps_cuda_read_trace(m.be.h, big.ctypes.data, 512))
 m.be.set_option("trace", 0)
 names = ["EMBED"] + ["QKV", "ATTN1", "ATTN2", "WO", "GATEUP", "DOWN"] * shape.n_layers + ["LMHEAD", "ARGMAX"]
 t0 = buf[0, 0]
@@ -41,7 +47,7 @@ prev_end = t0
 tot = {}
 for k in range(n):
     s, e, d, p = buf[k][:4]
-    extra = " ".join(f"{v / 1e3:5.2f}" for v in buf[k][4:7]) if buf[k][4:7].any() else ""
+    extra = " ".join(f"{v / 1e3:5.2f}" for v in buf[k][4:8]) if buf[k][4:8].any() else ""
     f = lambda v: (v - t0) / 1e3
     dep = f"{f(d):7.2f}" if d < 2**62 else "      -"
     pro = (f"{f(p):7.2f}" if p > 10**9 else f"{p / 1e3:6.2f}d") if p > 0 else "      -"
@@ -53,5 +59,14 @@ print("per-kernel-kind mean exclusive time (end - max(start, prev end)) and step
 for nm, v in tot.items():
     a = np.array(v)
     print(f"  {nm:7s} n={len(v):3d} excl {a[:, 0].mean():7.2f} us  share-of-step {a[:, 1].sum():8.1f} us")
+if "--cta" in sys.argv:   # per-CTA stream trace of the last pre-quantised-input mat-vec (DOWN of the last layer)
+    c = big[256:256 + 148]
+    dep0 = c[:, 0].min()
+    print("per-CTA DOWN trace: dep(us, rel) begin-dep end-dep loop_kcyc wait_kcyc blocks octets")
+    order = np.argsort(c[:, 2])
+    for i in list(order[:6]) + list(order[-12:]):
+        print(f"  cta {i:3d} dep {(c[i,0]-dep0)/1e3:6.2f} begin {(c[i,1]-c[i,0])/1e3:6.2f} end {(c[i,2]-c[i,0])/1e3:6.2f} loop {c[i,3]/1e3:7.2f} wait {c[i,4]/1e3:6.2f} blocks {c[i,5]} oct {c[i,6]}")
+    print("  mean end-dep", (c[:, 2] - c[:, 0]).mean() / 1e3, "max", (c[:, 2] - c[:, 0]).max() / 1e3, "mean loop kcyc", c[:, 3].mean() / 1e3, "mean wait kcyc", c[:, 4].mean() / 1e3,
+          "cyc/block (excl wait)", ((c[:, 3] - c[:, 4]) / np.maximum(c[:, 5], 1)).mean(), "GHz", (c[:, 3] / np.maximum(c[:, 2] - c[:, 1], 1)).mean())
 print(f"step span {(buf[n - 1, 1] - t0) / 1e3:.1f} us")
 m.close()
