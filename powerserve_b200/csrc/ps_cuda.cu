@@ -393,16 +393,20 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
     const float kq_scale = 1.0f / sqrtf((float)hs);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
-        PS_CK(cudaFuncSetAttribute(ps_k_attn2<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_attn2<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
         attr[ctx->device] = true;
     }
     int rc;
-    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * 2)), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], (const float *)ctx->q,
+    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], (const float *)ctx->q,
                        (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx)))) return rc;
-    const size_t a2smem = (size_t)R2 * (size_t)((d.n_ctx + 31) & ~31) * 4;
-    return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(256), a2smem, ctx->att, (const float *)ctx->kq,
+    // probabilities of the group + (when they fit) the CTA's eight V^T rows, all sized for a full context
+    const size_t row = (size_t)((d.n_ctx + 31) & ~31) * 4;
+    const int v_smem = (R2 + 8) * row <= 200 * 1024 && d.n_ctx % 4 == 0;
+    const size_t a2smem = (size_t)(R2 + (v_smem ? 8 : 0)) * row;
+    if ((size_t)R2 * row > 200 * 1024 || d.n_ctx % 4) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused decode attention: n_ctx = %d does not fit shared memory", d.n_ctx);
+    return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(PS_A2_THREADS), a2smem, ctx->att, (const float *)ctx->kq,
                     (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx),
-                    tp_out(ctx, PS_TP_SLOT_ATT));
+                    tp_out(ctx, PS_TP_SLOT_ATT), v_smem);
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
               bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0,
@@ -1013,7 +1017,8 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
     for (const LayerDev &ld : ctx->layers)
         if (ld.tq != 12 || ld.tk != 12 || ld.tv != 12 || ld.to != 12 || ld.tgate != 12 || ld.tup != 12 || ld.tdown != 12) ctx->fused_ok = false;
     if (d.dim % 256 || d.ffn_dim % 256 || (int64_t)d.n_heads * d.head_size % 256 || d.dim / 256 > 64 || d.ffn_dim / 256 > 64 || d.n_heads / d.n_kv_heads > 8 ||
-        (qdim_l % 8) || (kvd_l % 8) || (d.rope_type & 2) ||
+        (qdim_l % 8) || (kvd_l % 8) || (d.rope_type & 2) || d.n_ctx % 4 ||
+        (size_t)(d.n_heads / d.n_kv_heads) * ((d.n_ctx + 31) & ~31) * 4 > 200 * 1024 || // the soft-max rows of a kv group live in shared memory
         !(d.n_heads / d.n_kv_heads == 1 || d.n_heads / d.n_kv_heads == 2 || d.n_heads / d.n_kv_heads == 4 || d.n_heads / d.n_kv_heads == 8))
         ctx->fused_ok = false;
     if (tp > 1 && !ctx->fused_ok) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "tensor parallelism needs the fused Q4_K decode path (all-Q4_K llama-style model)");

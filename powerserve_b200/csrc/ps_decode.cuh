@@ -266,50 +266,77 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 }
 
 // ATTN2 = softmax_ext + mat_mul(v_view, kq) + permute/cont                    (norm_attention.cpp:133-151)
-// One CTA (8 warps) per (8 output dims d, kv head).  The soft-max rows of the R2 heads of the group are rebuilt in shared
-// memory by all 256 threads at once (256 / R2 threads per head: max, ggml_v_expf on 8-groups / expf tail, double sum,
-// scale: ggml.c:14846-14940, 2814-2868); then each warp streams one V^T row once for all R2 heads (ggml_vec_dot_f32
-// lane order, leftovers in order) with 16 loads in flight per lane.
+// One CTA (8 warps) per (8 output dims d, kv head).  Right after the dependency wait one thread asks the TMA for the R2
+// score rows of the group and (v_smem) the CTA's eight V^T rows, so the whole kernel pays ONE memory latency.  The
+// soft-max rows are rebuilt in shared memory by all 256 threads (256 / R2 threads per head: max, ggml_v_expf on 8-groups
+// / expf tail, double sum, scale: ggml.c:14846-14940, 2814-2868); then each warp walks one V^T row once for all R2 heads
+// (ggml_vec_dot_f32 lane order, leftovers in order).  v_smem = 0 (contexts too long for shared memory) streams the V^T
+// row from global memory with 32 loads in flight per lane instead.
+#define PS_A2_THREADS 256 // 8 warps rebuild the soft-max rows, then each walks one V^T row (512 threads: no faster, and delays the early launch)
 template <int R2>
-__global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
-                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut *tpo) {
-    extern __shared__ float s_p[]; // [R2][stride]
-    __shared__ double shd[8];
-    __shared__ float shf[8];
+__global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut *tpo,
+                                                  int v_smem) {
+    extern __shared__ __align__(128) float s_p[]; // [R2][stride] probabilities, then (v_smem) [8][stride] V^T rows
+    __shared__ double shd[PS_A2_THREADS / 32];
+    __shared__ float shf[PS_A2_THREADS / 32];
+    __shared__ __align__(8) uint64_t bar_s, bar_v;
+    const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    if (tid == 0) {
+        ps_mbar_init(&bar_s, 1);
+        ps_mbar_init(&bar_v, 1);
+        ps_fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
     ps_tl_min(tl, 0);
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(tl, 2);
+    const long long t_dep = (tl && tid == 0) ? ps_globaltimer() : 0;
+#define PS_A2_PROBE(k)                                                                                                   \
+    do {                                                                                                                 \
+        if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
+    } while (0)
     const int64_t n_kv = (int64_t)pos_dev[0] + 1;
-    const int g = blockIdx.y, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    constexpr int TPH = 256 / R2, WPH = TPH / 32;          // threads / warps per head
+    constexpr int TPH = PS_A2_THREADS / R2, WPH = TPH / 32;          // threads / warps per head
     const int hh = tid / TPH, ht = tid % TPH;
     const int64_t stride = (n_kv + 31) & ~(int64_t)31;
     const int64_t n8 = n_kv & ~(int64_t)7;
+    float *s_v = s_p + R2 * stride;
+    const int n_rows = min(8, hs - (int)blockIdx.x * 8);
+    if (tid == 0) { // rows are 16-byte aligned (n_ctx % 4 == 0); a copy may run up to 3 floats past n_kv, still inside its row
+        const uint32_t bytes = (uint32_t)(((n_kv + 3) & ~(int64_t)3) * 4);
+        ps_mbar_expect_tx(&bar_s, bytes * R2);
+#pragma unroll
+        for (int h2 = 0; h2 < R2; h2++) ps_bulk_g2s(s_p + h2 * stride, sc + (int64_t)(g * R2 + h2) * n_ctx, bytes, &bar_s);
+        if (v_smem) {
+            ps_mbar_expect_tx(&bar_v, bytes * n_rows);
+            for (int w = 0; w < n_rows; w++) ps_bulk_g2s(s_v + w * stride, vct + ((int64_t)g * hs + blockIdx.x * 8 + w) * n_ctx, bytes, &bar_v);
+        }
+    }
+    __syncthreads(); // the barrier words are initialised for everybody
+    ps_mbar_wait(&bar_s, 0);
     {
-        const float *wp = sc + (int64_t)(g * R2 + hh) * n_ctx;
         float *pp = s_p + hh * stride;
         float mx = -INFINITY;
-        for (int64_t j = ht; j < n_kv; j += TPH) {
-            const float vv = wp[j];
-            pp[j] = vv;
-            mx = fmaxf(mx, vv);
-        }
+        for (int64_t j = ht; j < n_kv; j += TPH) mx = fmaxf(mx, pp[j]);
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
         if (lane == 0) shf[warp] = mx;
         __syncthreads();
+        PS_A2_PROBE(4);
         mx = shf[hh * WPH];
 #pragma unroll
         for (int t = 1; t < WPH; t++) mx = fmaxf(mx, shf[hh * WPH + t]);
         double s = 0.0;
         for (int64_t gi = ht; gi < n8 / 8; gi += TPH) {
-            float vv[8];
+            float4 *p4 = reinterpret_cast<float4 *>(pp + gi * 8);
+            const float4 xa = p4[0], xb = p4[1];
+            float vv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-            for (int l = 0; l < 8; l++) {
-                vv[l] = ps_v_expf(__fadd_rn(pp[gi * 8 + l], -mx));
-                pp[gi * 8 + l] = vv[l];
-            }
+            for (int l = 0; l < 8; l++) vv[l] = ps_v_expf(__fadd_rn(vv[l], -mx));
+            p4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            p4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
             const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
             s += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
         }
@@ -322,6 +349,7 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
         for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(PS_FULL, s, o);
         if (lane == 0) shd[warp] = s;
         __syncthreads();
+        PS_A2_PROBE(5);
         double sum = shd[hh * WPH];
 #pragma unroll
         for (int t = 1; t < WPH; t++) sum += shd[hh * WPH + t];
@@ -331,34 +359,37 @@ __global__ void __launch_bounds__(256) ps_k_attn2(float *__restrict__ att, const
     __syncthreads();
     ps_tl_max(tl, 3);
     const int d = blockIdx.x * 8 + warp;
-    if (d < hs) {
+    if (warp < 8 && d < hs) { // warps 8.. only help with the soft-max
         const float *vrow = vct + ((int64_t)g * hs + d) * n_ctx;
         const int64_t np = n_kv & ~(int64_t)31;
         float sum[R2];
 #pragma unroll
         for (int h2 = 0; h2 < R2; h2++) sum[h2] = 0.f;
         const int ntail = (int)(n_kv - np);
-        const float vtail = (lane < ntail) ? vrow[np + lane] : 0.f;
-        int64_t s0 = 0;
-        for (; s0 + 512 <= np; s0 += 512) { // 16 independent V loads in flight per lane; the FMA chains stay in position order
-            float vv[16];
+        float vtail;
+        if (v_smem) {
+            ps_mbar_wait(&bar_v, 0);
+            const float *vs = s_v + warp * stride;
+            vtail = (lane < ntail) ? vs[np + lane] : 0.f;
+#pragma unroll 8
+            for (int64_t s0 = 0; s0 < np; s0 += 32) { // the FMA chains stay in position order
+                const float v = vs[s0 + lane];
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = vrow[s0 + 32 * u + lane];
+                for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(v, s_p[h2 * stride + s0 + lane], sum[h2]);
+            }
+        } else {
+            vtail = (lane < ntail) ? vrow[np + lane] : 0.f;
+            for (int64_t s0 = 0; s0 < np; s0 += 1024) { // 32 independent V loads in flight per lane
+                float vv[32];
 #pragma unroll
-            for (int u = 0; u < 16; u++)
+                for (int u = 0; u < 32; u++) vv[u] = (s0 + 32 * u < np) ? __ldcs(vrow + s0 + 32 * u + lane) : 0.f;
 #pragma unroll
-                for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(vv[u], s_p[h2 * stride + s0 + 32 * u + lane], sum[h2]);
-        }
-        if (s0 < np) {
-            float vv[16];
+                for (int u = 0; u < 32; u++)
+                    if (s0 + 32 * u < np) {
 #pragma unroll
-            for (int u = 0; u < 16; u++) vv[u] = (s0 + 32 * u < np) ? vrow[s0 + 32 * u + lane] : 0.f;
-#pragma unroll
-            for (int u = 0; u < 16; u++)
-                if (s0 + 32 * u < np) {
-#pragma unroll
-                    for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(vv[u], s_p[h2 * stride + s0 + 32 * u + lane], sum[h2]);
-                }
+                        for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(vv[u], s_p[h2 * stride + s0 + 32 * u + lane], sum[h2]);
+                    }
+            }
         }
         ps_f32x8_reduce_n<R2>(sum);
         for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order (every lane computes the same chain)
