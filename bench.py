@@ -223,9 +223,26 @@ def main():
     mv_ns, mv_n = model.be.counter("matvec_kernel_ns"), model.be.counter("matvec_kernel_launches")
     model.be.set_option("ktime", 0)
     model.be.kv_rollback(2 + k_steps)
+    # the same launches INSIDE the graph-replayed, PDL-chained step: every kernel stamps %globaltimer at start / end (option
+    # "trace"); a launch's exclusive time is end - max(start, end of the previous launch).  Explains the gap between the
+    # event-timed figure above (serialised launches: + launch latency, no overlap of the weight prefetch) and the step time.
+    in_graph = None
+    if tp == 1:
+        n_l = 1 + 6 * shape.n_layers + 2   # embed, (qkv, attn1, attn2, wo, gate|up, down) x layers, lm_head, arg-max
+        if n_l <= 255:
+            model.be.set_option("trace", 1)
+            model.decode_greedy(tok, 1)
+            tb = np.zeros((n_l, 8), np.int64)
+            model.be._ck(model.be.L.ps_cuda_read_trace(model.be.h, tb.ctypes.data, n_l))
+            model.be.set_option("trace", 0)
+            model.be.kv_rollback(1)
+            excl = np.maximum(tb[1:, 1] - np.maximum(tb[1:, 0], tb[:-1, 1]), 0)   # launch k + 1 vs launch k
+            mv_idx = [6 * L + o for L in range(shape.n_layers) for o in (0, 3, 4, 5)] + [6 * shape.n_layers]  # into excl (launch - 1)
+            att_idx = [6 * L + o for L in range(shape.n_layers) for o in (1, 2)]
+            in_graph = {"matvec_us_per_step": float(excl[mv_idx].sum() / 1e3), "attention_us_per_step": float(excl[att_idx].sum() / 1e3),
+                        "step_span_us": float((tb[-1, 1] - tb[0, 0]) / 1e3), "launches": len(mv_idx)}
     barrier()
     # --- e2e: host token -> ps_cuda_forward -> host logits, every step
-    model.be.kv_rollback(args.steps)
     h0, d0 = model.be.counter("h2d_bytes"), model.be.counter("d2h_bytes")
     t0 = time.perf_counter()
     t = tok
@@ -268,6 +285,11 @@ def main():
                         "step": {"achieved": step_gbs, "frac": step_gbs / hbm_peak,
                                  "what": "whole decode step incl. attention, prologues and launch gaps: weight bytes per token / step time"}},
            "clocks": clk.summary(), "greedy_ids_head": [int(x) for x in ids[:8]]}
+    if in_graph:  # the same kernel inside the graph: algorithmic bytes of the step / summed exclusive time of its mat-vec launches
+        ig_gbs = wbytes_gpu / (in_graph["matvec_us_per_step"] * 1e-6) / 1e9
+        out["roofline"]["in_graph"] = dict(in_graph, achieved=ig_gbs, frac=ig_gbs / hbm_peak,
+                                           what="graph + PDL replay, %globaltimer stamps inside the kernels (option trace): weight bytes per token / "
+                                                "summed exclusive time of the mat-vec launches; the traced step runs ~3 % slower than the timed ones")
     if tp > 1:
         out["tp"] = {"size": tp, "p2p": bool(model.be.counter("tp_p2p")), "peer_wait_error": model.be.counter("tp_error"), "nccl_allgathers_per_step": (model.be.counter("tp_allgathers")) // max(1, model.be.counter("graph_replays") + 1),
                      "note": "row sharding keeps every dot product whole: results are bit-identical to one GPU (tests/test_gpu_tp.py)"}

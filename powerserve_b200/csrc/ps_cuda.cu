@@ -99,7 +99,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -321,7 +321,9 @@ int launch_rw(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 }
 int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     a.tl = tl_slot(ctx);
-    a.cta_tl = a.tl ? ctx->trace_dev + (size_t)256 * 8 : nullptr; // slots 256 .. 256 + grid of the trace buffer
+    // per-CTA trace of one kind of launch (1 Wdown, 2 gate|up, 3 QKV, 4 Wo, 5 lm_head): slots 256 .. 256 + grid of the trace buffer
+    const int kind = epi == PS_EPI_SILU ? 2 : epi == PS_EPI_RESIDUAL ? (a.xq_in ? 1 : 4) : (a.n_seg == 3 ? 3 : 5);
+    a.cta_tl = (a.tl && kind == ctx->opt_cta_trace) ? ctx->trace_dev + (size_t)256 * 8 : nullptr;
     a.inv_k = (a.K & (a.K - 1)) == 0 ? 1.0 / (double)a.K : 0.0;
     const int nb = a.K / 256, rpt = (epi == PS_EPI_SILU) ? 2 : 1;
     if (nb > 4 * PS_RW_WARPS) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: K=%d too large", a.K);
@@ -1414,6 +1416,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
+    else if (!strcmp(name, "cta_trace")) ctx->opt_cta_trace = value;
     else if (!strcmp(name, "rw_kb")) ctx->opt_kb = value; // tuning: cap on the blocks per TMA stage of the row-walker mat-vec
     else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {

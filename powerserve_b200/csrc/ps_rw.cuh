@@ -69,7 +69,7 @@ struct PsRwArgs {
     const PsTpIn *tpi;     // tensor parallel (else null): x is a gathered vector — wait for the peers' shards
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
-    long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (option "trace", the pre-quantised-input launches)
+    long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (options "trace" + "cta_trace" = launch kind)
 };
 
 // ---------------------------------------------------------------------------------------------------- repack
@@ -415,7 +415,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
         }
     }
     if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + 7), (unsigned long long)wcyc);
-    if (a.cta_tl && a.xq_in && tid == 0) { // per-CTA stream trace (tools/timeline.py --cta)
+    if (a.cta_tl && tid == 0) { // per-CTA stream trace of warp 0 (tools/timeline.py --cta=KIND)
         long long *c = a.cta_tl + (size_t)blockIdx.x * 8;
         c[0] = t_dep; c[1] = t_begin; c[2] = ps_globaltimer(); c[3] = clock64() - c_begin; c[4] = wcyc; c[5] = n_mine * nb; c[6] = o1 - o0;
     }

@@ -1,7 +1,6 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_decode.py tests/test_gpu_model.py tests/test_gpu_golden.py -x -q -m gpu 2>&1 | tail -3
-timeout 300 python tools/timeline.py llama-3.1-8b 8 2048 > gpurun_out/p_tl_ctx2048d.txt 2>&1
-head -10 gpurun_out/p_tl_ctx2048d.txt; tail -12 gpurun_out/p_tl_ctx2048d.txt
-timeout 300 python tools/timeline.py llama-3.1-8b 8 64 > gpurun_out/p_tl_ctx64d.txt 2>&1
-head -1 gpurun_out/p_tl_ctx64d.txt; tail -11 gpurun_out/p_tl_ctx64d.txt | head -5
+for k in 2 3 4 5; do
+timeout 300 python tools/timeline.py llama-3.1-8b 8 2048 --opt=cta_trace=$k --cta > gpurun_out/p_cta_$k.txt 2>&1
+echo "== kind $k"; grep -A30 "per-CTA" gpurun_out/p_cta_$k.txt | (head -4; tail -6)
+done

@@ -59,10 +59,10 @@ print("per-kernel-kind mean exclusive time (end - max(start, prev end)) and step
 for nm, v in tot.items():
     a = np.array(v)
     print(f"  {nm:7s} n={len(v):3d} excl {a[:, 0].mean():7.2f} us  share-of-step {a[:, 1].sum():8.1f} us")
-if "--cta" in sys.argv:   # per-CTA stream trace of the last pre-quantised-input mat-vec (DOWN of the last layer)
+if any(a.startswith("--cta") for a in sys.argv):   # per-CTA stream trace of the last launch of the kind chosen with --opt=cta_trace=K (default 1 = Wdown)
     c = big[256:256 + 148]
     dep0 = c[:, 0].min()
-    print("per-CTA DOWN trace: dep(us, rel) begin-dep end-dep loop_kcyc wait_kcyc blocks octets")
+    print("per-CTA trace: dep(us, rel) begin-dep end-dep loop_kcyc wait_kcyc blocks octets")
     order = np.argsort(c[:, 2])
     for i in list(order[:6]) + list(order[-12:]):
         print(f"  cta {i:3d} dep {(c[i,0]-dep0)/1e3:6.2f} begin {(c[i,1]-c[i,0])/1e3:6.2f} end {(c[i,2]-c[i,0])/1e3:6.2f} loop {c[i,3]/1e3:7.2f} wait {c[i,4]/1e3:6.2f} blocks {c[i,5]} oct {c[i,6]}")
