@@ -1,13 +1,10 @@
 #!/bin/bash
 mkdir -p gpurun_out
 ( time timeout 600 python -m pytest tests/test_gpu_tp.py -x -q ) > gpurun_out/tp_pytest.log 2>&1
-grep -v "^$" gpurun_out/tp_pytest.log | tail -12 | cut -c1-250
-for mode in ""; do
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --prompt 256 --steps 64 --warmup 8 $mode > gpurun_out/tp2_bench$mode.json 2> gpurun_out/tp2_bench$mode.err
-cat gpurun_out/tp2_bench$mode.json | python -c "
+grep -v "^$" gpurun_out/tp_pytest.log | tail -8 | cut -c1-250
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 > gpurun_out/tp2_bench.json 2> gpurun_out/tp2_bench.err
+grep "^{" gpurun_out/tp2_bench.json | python -c "
 import sys, json
 for l in sys.stdin:
-    if l.startswith('{'):
-        d=json.loads(l); print('TP2 decode', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d.get('tp'), d['config']['parallelism'])"
-grep -i "error" -A5 gpurun_out/tp2_bench$mode.err | head -20
-done
+    d=json.loads(l); print('TP2 decode', d['value'], 'ms/step', d['ms_per_step'], 'e2e', d['e2e']['value'], d.get('tp'), d['config']['parallelism'], d['scaling'])"
+grep -i "error" -A5 gpurun_out/tp2_bench.err | head -20
