@@ -139,7 +139,8 @@ def main():
     wbytes = weight_bytes_per_token(shape)
     n_cpu = os.cpu_count() or 2
     cpu_threads = args.cpu_threads or max(1, min(n_cpu - 1, 32))
-    cfg = {"workload": f"{args.model} Q4_K synthetic: decode 1 token/step at context {args.prompt}+ (BASELINE configs[2]: prefill {args.prompt} + decode)",
+    which = "configs[1]: 1B decode" if args.model == "llama-3.2-1b" else f"configs[2]: prefill {args.prompt} + decode"
+    cfg = {"workload": f"{args.model} Q4_K synthetic: decode 1 token/step at context {args.prompt}+ (BASELINE {which})",
            "context": args.prompt, "prefill_batch": args.prefill_batch, "weight_bytes_per_token": wbytes,
            "l2": "weights (>= 0.7 GB/token) exceed the 126 MB L2; no explicit flush",
            "parallelism": "1 GPU" if world == 1 else (f"replicas x{world}" if args.replicas else f"tp{world} (row-sharded, " + ("NCCL all-gather)" if args.tp_nccl else "all-gather fused into the kernels as NVLink peer stores)"))}
