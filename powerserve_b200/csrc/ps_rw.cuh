@@ -292,7 +292,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
 #pragma unroll
                 for (int t = 0; t < 8; t++) e0[t] = __fmul_rn(e0[t], __fmul_rn(wv0[t], nscale)); // y = x * (w * scale)
             }
-            if (__float_as_uint(e0[0]) != 0xffc0dead) PS_RW_PROBE(5);
+            PS_RW_PROBE(5);
             ps_rw_quant_store(e0, lane, reinterpret_cast<uint32_t *>(s_qa) + (size_t)warp * 64, s_meta + warp * 4);
         }
 #pragma unroll 1

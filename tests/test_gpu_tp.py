@@ -26,8 +26,10 @@ def n_gpus():
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
 @pytest.mark.parametrize("mode", ["p2p", "nccl"])
-@pytest.mark.parametrize("preset,size", [("tiny-llama", 2), ("slice-1b", 2)])
+@pytest.mark.parametrize("preset,size", [("tiny-llama", 2), ("slice-1b", 2), ("slice-1b", 4)])
 def test_tp_decode_bit_exact(preset, size, mode):
+    if n_gpus() < size:
+        pytest.skip(f"needs {size} GPUs")
     d = M.model_dir(preset)
     n_prompt, n_dec = 19, 12
     with tempfile.TemporaryDirectory() as td:
