@@ -145,7 +145,9 @@ int ps_cuda_tp_init(ps_cuda_ctx *ctx, const void *id128);      /* every rank, af
  * handle of its exchange heap (64 bytes), the host gathers the N handles in rank order and every rank imports them.
  * From then on the producing kernels store their output rows straight into every rank's copy of the gathered vector
  * and publish an epoch flag; the consuming kernels wait on the flags (bounded spin; counter "tp_error").  Option
- * "tp_p2p" = 0 switches back to NCCL all-gathers (same results; tests compare the two). */
+ * "tp_p2p" = 0 switches back to NCCL all-gathers (same results; tests compare the two).  The four per-layer exchanges
+ * carry their flag in band (64-bit {value, epoch} peer stores, polled by the consumer: no fences); option "tp_ll" = 0
+ * makes them use the fence + epoch-flag protocol as well. */
 int ps_cuda_tp_export(ps_cuda_ctx *ctx, void *handle64);
 int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n);
 

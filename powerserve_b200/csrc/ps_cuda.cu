@@ -124,12 +124,14 @@ struct ps_cuda_ctx {
     //   [att_full qdim][x dim][h_full ffn][all_val tp*1024][all_idx tp*1024][flags PS_TP_SLOTS x PS_TP_MAX u32]
     uint8_t *heap = nullptr;
     size_t heap_bytes = 0, off_att = 0, off_x = 0, off_h = 0, off_val = 0, off_idx = 0, off_logits = 0, off_flags = 0;
+    size_t off_ll[4] = {}; // in-band-flag mirrors of the four per-layer exchanges (ATT, X1, H, X2): 8 bytes per element
+    int opt_ll = 1;        // option "tp_ll": per-layer exchanges carry their flag in-band (no fences); 0 = fence + epoch flags
     uint8_t *peer_heap[PS_TP_MAX] = {};
     bool p2p = false;          // peers imported: all-gathers run as peer stores inside the producing kernels
     uint32_t *epoch_dev = nullptr; // [PS_TP_SLOTS] local epoch counters
     int *done_dev = nullptr;       // [PS_TP_SLOTS] local CTA arrival counters
     int *tp_err_dev = nullptr;
-    PsTpOut *tpo_dev = nullptr; // [PS_TP_SLOTS] link tables of the peer-store exchange
+    PsTpOut *tpo_dev = nullptr; // [2][PS_TP_SLOTS] link tables of the peer-store exchange ([1]: with the in-band-flag pointers)
     PsTpIn *tpi_dev = nullptr;
     float *tp_rows = nullptr;  // logits of a token-by-token tensor-parallel batch, [max_batch][vocab] (allocated on first use)
     int64_t n_gather = 0;      // all-gathers enqueued (counter "tp_allgathers")
@@ -360,8 +362,16 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
 // the four mat-vecs of a layer + lm_head on the row-walker kernel
 // peer-store all-gather links of one phase (`slot`), resident in device memory (built once by ps_cuda_tp_import): where
 // the producer's rows land on every rank, and what the consumer waits for.  Null when the exchange is not peer-to-peer.
-const PsTpOut *tp_out(ps_cuda_ctx *ctx, int slot) { return ctx->p2p ? ctx->tpo_dev + slot : nullptr; }
-const PsTpIn *tp_in(ps_cuda_ctx *ctx, int slot) { return ctx->p2p ? ctx->tpi_dev + slot : nullptr; }
+bool tp_ll(ps_cuda_ctx *ctx, int slot) { return ctx->p2p && ctx->opt_ll && slot <= PS_TP_SLOT_X2; }
+const PsTpOut *tp_out(ps_cuda_ctx *ctx, int slot) { return ctx->p2p ? ctx->tpo_dev + (tp_ll(ctx, slot) ? PS_TP_SLOTS : 0) + slot : nullptr; }
+const PsTpIn *tp_in(ps_cuda_ctx *ctx, int slot) { return (ctx->p2p && !tp_ll(ctx, slot)) ? ctx->tpi_dev + slot : nullptr; }
+// consumer side of an in-band-flag exchange: the (value, epoch) mirror of the gathered vector replaces `x` and the flag wait
+void tp_ll_in(ps_cuda_ctx *ctx, int slot, PsRwArgs &a) {
+    if (!tp_ll(ctx, slot)) return;
+    a.x_ll = reinterpret_cast<const unsigned long long *>(ctx->heap + ctx->off_ll[slot]);
+    a.x_epoch = ctx->epoch_dev + slot;
+    a.tp_err = ctx->tp_err_dev;
+}
 
 // all-gather over the tensor-parallel group (NCCL on the context stream; capturable into the decode graph)
 int tp_all_gather(ps_cuda_ctx *ctx, const void *send, void *recv, size_t count, bool is_int = false, bool always = false) {
@@ -380,6 +390,7 @@ int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     const int qdim = ctx->nh_l * d.head_size, kvd = ctx->nkv_l * d.head_size;
     PsRwArgs a{};
     a.tpi = L > 0 ? tp_in(ctx, PS_TP_SLOT_X2) : nullptr;
+    if (L > 0) tp_ll_in(ctx, PS_TP_SLOT_X2, a);
     a.w = ld.rw_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = d.dim; a.n_seg = 3;
     a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim, PS_RW_OUT_ROPE};
     a.seg[1] = {ctx->kc[L], d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd, PS_RW_OUT_ROPE_KCACHE};
@@ -412,9 +423,10 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
               bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0,
-              const PsTpIn *tpi = nullptr, const PsTpOut *tpo = nullptr) {
+              const PsTpIn *tpi = nullptr, const PsTpOut *tpo = nullptr, int in_slot = -1) {
     PsRwArgs a{};
     a.tpi = tpi; a.tpo = tpo;
+    if (in_slot >= 0) tp_ll_in(ctx, in_slot, a);
     a.xq_in = xq_in;
     a.next_norm_w = next_norm_w; a.next_norm_n = ctx->d.dim;
     if (partial_argmax) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; a.idx_offset = idx_offset; }
@@ -430,6 +442,7 @@ int rw_gate_up(ps_cuda_ctx *ctx, const LayerDev &ld) {
     a.seg[0] = {ctx->g_part, nullptr, 0, ctx->ffn_l, 0};
     a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps;
     a.tpi = tp_in(ctx, PS_TP_SLOT_X1);
+    tp_ll_in(ctx, PS_TP_SLOT_X1, a);
     a.tpo = tp_out(ctx, PS_TP_SLOT_H);
     if (ctx->tp == 1) { a.xq_out = ctx->hq; a.blk_cnt = ctx->blk_cnt; } // the Q8_K hand-off needs the whole vector on one GPU
     return launch_rw(ctx, a, PS_EPI_SILU);
@@ -504,21 +517,25 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
         if ((rc = tp_all_gather(ctx, ctx->att, ctx->att_full, (size_t)qdim / tp))) return rc;
         const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
         // x[rows of this rank] += Wo[rows] . att
-        if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, ctx->x + (size_t)rank * dim_l, false, nullptr, ld.ffn_norm, 0,
-                            tp_in(ctx, PS_TP_SLOT_ATT), tp_out(ctx, PS_TP_SLOT_X1)))) return rc;
+        // in-band-flag exchange: the gathered x only exists as (value, epoch) words, so the residual input is this rank's own
+        // plain copy - x_part, updated in place (layer 0: the embedding row every rank computed for itself)
+        const float *res_o = (tp_ll(ctx, PS_TP_SLOT_X2) && L > 0) ? ctx->x_part : ctx->x + (size_t)rank * dim_l;
+        const float *res_d = tp_ll(ctx, PS_TP_SLOT_X1) ? ctx->x_part : ctx->x + (size_t)rank * dim_l;
+        if ((rc = rw_single(ctx, ld.rw_o, dim_l, qdim, ctx->x_part, ctx->att_full, nullptr, res_o, false, nullptr, ld.ffn_norm, 0,
+                            tp_in(ctx, PS_TP_SLOT_ATT), tp_out(ctx, PS_TP_SLOT_X1), PS_TP_SLOT_ATT))) return rc;
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
         if ((rc = rw_gate_up(ctx, ld))) return rc;                                                        // g = silu(Wg.xn) * (Wu.xn)
         if ((rc = tp_all_gather(ctx, ctx->g_part, ctx->h_full, (size_t)ctx->ffn_l))) return rc;
-        if ((rc = rw_single(ctx, ld.rw_down, dim_l, ffn, ctx->x_part, ctx->h_full, nullptr, ctx->x + (size_t)rank * dim_l, false,
+        if ((rc = rw_single(ctx, ld.rw_down, dim_l, ffn, ctx->x_part, ctx->h_full, nullptr, res_d, false,
                             tp == 1 ? ctx->hq : nullptr, norm_after, 0, tp_in(ctx, PS_TP_SLOT_H),
-                            tp_out(ctx, PS_TP_SLOT_X2)))) return rc;     // x[rows] += Wdown[rows] . g
+                            tp_out(ctx, PS_TP_SLOT_X2), PS_TP_SLOT_H))) return rc;     // x[rows] += Wdown[rows] . g
         if ((rc = tp_all_gather(ctx, ctx->x_part, ctx->x, (size_t)dim_l))) return rc;
     }
     if (lm_head) {
         const int n_part = std::min(ctx->n_sm, (ctx->vocab_l + 7) / 8);
         if ((rc = rw_single(ctx, ctx->rw_out, ctx->vocab_l, dim, ctx->logits_part, ctx->x, ctx->w_out_norm, nullptr, pick, nullptr, nullptr,
                             rank * ctx->vocab_l, tp_in(ctx, PS_TP_SLOT_X2),
-                            pick ? tp_out(ctx, PS_TP_SLOT_PART) : tp_out(ctx, PS_TP_SLOT_LOGITS)))) return rc;
+                            pick ? tp_out(ctx, PS_TP_SLOT_PART) : tp_out(ctx, PS_TP_SLOT_LOGITS), PS_TP_SLOT_X2))) return rc;
         if (pick) {
             const float *pv = ctx->part_val;
             const int *pi = ctx->part_idx;
@@ -652,7 +669,11 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         ctx->off_idx = up(ctx->off_val + 4 * 1024 * (size_t)tp);
         ctx->off_logits = up(ctx->off_idx + 4 * 1024 * (size_t)tp);
         ctx->off_flags = up(ctx->off_logits + 4 * (size_t)d.vocab_size);
-        ctx->heap_bytes = up(ctx->off_flags + 4 * PS_TP_SLOTS * PS_TP_MAX);
+        ctx->off_ll[PS_TP_SLOT_ATT] = up(ctx->off_flags + 4 * PS_TP_SLOTS * PS_TP_MAX);
+        ctx->off_ll[PS_TP_SLOT_X1] = up(ctx->off_ll[PS_TP_SLOT_ATT] + 8 * (size_t)qdim);
+        ctx->off_ll[PS_TP_SLOT_H] = up(ctx->off_ll[PS_TP_SLOT_X1] + 8 * (size_t)dim);
+        ctx->off_ll[PS_TP_SLOT_X2] = up(ctx->off_ll[PS_TP_SLOT_H] + 8 * (size_t)d.ffn_dim);
+        ctx->heap_bytes = up(ctx->off_ll[PS_TP_SLOT_X2] + 8 * (size_t)dim);
         PS_AL(ctx->heap, ctx->heap_bytes);
         PS_CKC(cudaMemsetAsync(ctx->heap, 0, ctx->heap_bytes, ctx->stream));
         PS_AL(ctx->epoch_dev, 4 * PS_TP_SLOTS);
@@ -681,6 +702,7 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->part_val, 4 * 1024);
     PS_AL(ctx->part_idx, 4 * 1024);
     { int v = 148; if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device) == cudaSuccess) ctx->n_sm = v; }
+    if (const char *e = getenv("PS_CUDA_TP_LL")) ctx->opt_ll = atoi(e) != 0; // A-B runs of the two peer-store protocols
     ctx->kc.resize(d.n_layers);
     ctx->vct.resize(d.n_layers);
     for (int L = 0; L < d.n_layers; L++) {
@@ -1365,7 +1387,7 @@ int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n) {
         const size_t off[PS_TP_SLOTS] = {ctx->off_att, ctx->off_x, ctx->off_h, ctx->off_x, ctx->off_val, ctx->off_logits};
         const size_t mine[PS_TP_SLOTS] = {(size_t)ctx->rank * ctx->nh_l * d.head_size, (size_t)ctx->rank * ctx->dim_l, (size_t)ctx->rank * ctx->ffn_l,
                                           (size_t)ctx->rank * ctx->dim_l, (size_t)ctx->rank * n_part, (size_t)ctx->rank * ctx->vocab_l};
-        PsTpOut to[PS_TP_SLOTS];
+        PsTpOut to[2 * PS_TP_SLOTS]; // [0..): fence + epoch flags; [PS_TP_SLOTS..): the same links with the in-band-flag mirrors
         PsTpIn ti[PS_TP_SLOTS];
         memset(to, 0, sizeof to);
         memset(ti, 0, sizeof ti);
@@ -1378,6 +1400,10 @@ int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n) {
             }
             to[s].epoch = ctx->epoch_dev + s;
             to[s].done = ctx->done_dev + s;
+            to[PS_TP_SLOTS + s] = to[s];
+            if (s <= PS_TP_SLOT_X2)
+                for (int p = 0; p < ctx->tp; p++)
+                    to[PS_TP_SLOTS + s].peer_ll[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->off_ll[s]) + mine[s];
             ti[s].flags = reinterpret_cast<const uint32_t *>(ctx->heap + ctx->off_flags) + s * PS_TP_MAX;
             ti[s].epoch = ctx->epoch_dev + s;
             ti[s].err = ctx->tp_err_dev;
@@ -1418,6 +1444,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
     else if (!strcmp(name, "cta_trace")) ctx->opt_cta_trace = value;
     else if (!strcmp(name, "rw_kb")) ctx->opt_kb = value; // tuning: cap on the blocks per TMA stage of the row-walker mat-vec
+    else if (!strcmp(name, "tp_ll")) ctx->opt_ll = value;
     else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {

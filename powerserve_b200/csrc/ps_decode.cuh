@@ -67,6 +67,7 @@ PS_D int ps_dp4a_us(uint32_t a, int b, int c) { // unsigned bytes of a  x  signe
 // write happen after all of its readers are done ("tensor parallelism").
 #define PS_TP_MAX 8
 struct PsTpOut {
+    unsigned long long *peer_ll[PS_TP_MAX]; // in-band-flag exchange (else null): (value, epoch) words on every rank, already offset
     float *peer_dst[PS_TP_MAX];      // where this kernel's output goes on every rank (own rank included), already offset
     int *peer_idx[PS_TP_MAX];        // lm_head partial arg-max only: the index array next to the value array
     uint32_t *peer_flag[PS_TP_MAX];  // &flags[slot][my_rank] on every rank
@@ -114,6 +115,32 @@ PS_D void ps_tp_signal(const PsTpOut *outp, int n_ctas) {
         for (int p = 0; p < out.n; p++) ps_st_release_sys(out.peer_flag[p], e);
     }
 }
+
+// ---- in-band flags (the per-layer exchanges): every peer store is ONE naturally aligned 64-bit word {value bits, epoch},
+// single-copy atomic, so the producer needs no fence, no arrival flag and no system-scope release - the consumer polls
+// the very words it is about to read until they carry the epoch of this phase.  The epoch counter of the slot is local
+// and advances once per kernel instance (last CTA, plain gpu-scope bookkeeping), in lock step on every rank.
+PS_D uint32_t ps_tp_ll_epoch(const PsTpOut *outp) { return *reinterpret_cast<const volatile uint32_t *>(outp->epoch) + 1; }
+PS_D void ps_tp_ll_store(const PsTpOut *outp, int64_t idx, float v, uint32_t e) {
+    const unsigned long long w = ((unsigned long long)e << 32) | (unsigned long long)__float_as_uint(v);
+    for (int p = 0; p < outp->n; p++) asm volatile("st.relaxed.sys.global.b64 [%0], %1;" ::"l"(outp->peer_ll[p] + idx), "l"(w) : "memory");
+}
+// producer: ONE thread of every CTA, after the CTA's stores were issued (no ordering needed: the data carries the flag)
+PS_D void ps_tp_ll_done(const PsTpOut *outp, int n_ctas, uint32_t e) {
+    if (atomicAdd(outp->done, 1) == n_ctas - 1) {
+        *outp->done = 0;
+        *outp->epoch = e; // read by the consumer kernel after its grid-dependency wait
+    }
+}
+// consumer: two adjacent words (16 bytes, each half single-copy atomic); returns false while either is stale
+PS_D bool ps_tp_ll_load2(const unsigned long long *p, uint32_t e, float &v0, float &v1) {
+    unsigned long long a, b;
+    asm volatile("ld.relaxed.sys.global.v2.b64 {%0, %1}, [%2];" : "=l"(a), "=l"(b) : "l"(p) : "memory");
+    v0 = __uint_as_float((uint32_t)a);
+    v1 = __uint_as_float((uint32_t)b);
+    return (uint32_t)(a >> 32) == e && (uint32_t)(b >> 32) == e;
+}
+#define PS_TP_LL_SPINS (1 << 22) // bounded: a dead peer yields garbage + the tp_error counter, never a hung GPU
 
 // stand-alone consumer wait (before a device-to-host copy of a gathered vector)
 __global__ void ps_k_tp_wait(const PsTpIn *tpi) {
@@ -292,6 +319,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(tl, 2);
+    const uint32_t ll_epoch = (tpo && tpo->peer_ll[0]) ? ps_tp_ll_epoch(tpo) : 0;
     const long long t_dep = (tl && tid == 0) ? ps_globaltimer() : 0;
 #define PS_A2_PROBE(k)                                                                                                   \
     do {                                                                                                                 \
@@ -403,13 +431,20 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
             for (int h2 = 1; h2 < R2; h2++)
                 if (lane == h2) v = sum[h2];
             att[(int64_t)(g * R2 + lane) * hs + d] = v;
-            if (tpo)
-                for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v; // all-gather by peer stores
+            if (tpo) { // all-gather by peer stores
+                if (tpo->peer_ll[0]) ps_tp_ll_store(tpo, (int64_t)(g * R2 + lane) * hs + d, v, ll_epoch);
+                else
+                    for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v;
+            }
         }
     }
     if (tpo) {
-        __syncthreads();
-        if (tid == 0) ps_tp_signal(tpo, (int)(gridDim.x * gridDim.y));
+        if (tpo->peer_ll[0]) {
+            if (tid == 0) ps_tp_ll_done(tpo, (int)(gridDim.x * gridDim.y), ll_epoch);
+        } else {
+            __syncthreads();
+            if (tid == 0) ps_tp_signal(tpo, (int)(gridDim.x * gridDim.y));
+        }
     }
     ps_tl_max(tl, 1);
 }

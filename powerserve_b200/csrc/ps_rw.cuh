@@ -67,6 +67,9 @@ struct PsRwArgs {
     int *part_idx;
     const PsTpOut *tpo;    // tensor parallel (else null): the output rows (or the arg-max partials) go into every rank's buffer
     const PsTpIn *tpi;     // tensor parallel (else null): x is a gathered vector — wait for the peers' shards
+    const unsigned long long *x_ll; // tensor parallel, in-band flags (else null): x as (value, epoch) words; replaces `x` and `tpi`
+    const uint32_t *x_epoch;        //   the epoch those words must carry (local counter of the producing slot)
+    int *tp_err;                    //   set to 1 if a poll gave up
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
     long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (options "trace" + "cta_trace" = launch kind)
@@ -176,6 +179,17 @@ __device__ __noinline__ void ps_rw_quant_store(const float *e, int lane, uint32_
     if (lane < 4) meta[lane] = make_uint2(__float_as_uint(yd), bsp4);
 }
 
+// the same eight elements from an in-band-flag vector: poll until all eight words carry epoch `ep`
+PS_D void ps_rw_load8_ll(const unsigned long long *p, int lane, float e[8], uint32_t ep, int *err) {
+    const unsigned long long *p0 = p + 4 * lane, *p1 = p + 128 + 4 * lane;
+    int spins = 0;
+    for (;;) {
+        const bool ok = ps_tp_ll_load2(p0, ep, e[0], e[1]) & ps_tp_ll_load2(p0 + 2, ep, e[2], e[3]) & ps_tp_ll_load2(p1, ep, e[4], e[5]) &
+                        ps_tp_ll_load2(p1 + 2, ep, e[6], e[7]);
+        if (ok) break;
+        if (++spins > PS_TP_LL_SPINS || ((spins & 1023) == 0 && *reinterpret_cast<volatile int *>(err))) { *err = 1; break; } // one give-up ends them all
+    }
+}
 PS_D void ps_rw_load8(const float *p, int lane, float e[8]) {
     const float4 v0 = *reinterpret_cast<const float4 *>(p + 4 * lane);
     const float4 v1 = *reinterpret_cast<const float4 *>(p + 128 + 4 * lane);
@@ -244,6 +258,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
         if (a.tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(a.tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
     } while (0)
     if (a.tpi && tid == 0) ps_tp_wait(a.tpi); // the gathered activation vector is complete on this rank
+    const uint32_t ll_epoch = (a.tpo && a.tpo->peer_ll[0]) ? ps_tp_ll_epoch(a.tpo) : 0; // in-band-flag exchange: this launch's epoch (never 0)
     ps_bar_sync(1, PS_RW_THREADS + 32);         // mbarriers initialised by the helper (and the wait above is over)
     if (a.next_norm_w && blockIdx.x == 0)
         for (int i = tid * 32; i < a.next_norm_n; i += PS_RW_THREADS * 32)
@@ -261,7 +276,12 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     } else { // (RMSNorm) + quantize_row_q8_K, one warp per 256-block
         float e0[8];
         const bool have0 = warp < nb;
-        if (have0) ps_rw_load8(a.x + warp * 256, lane, e0);
+        const uint32_t x_ep = a.x_ll ? *reinterpret_cast<const volatile uint32_t *>(a.x_epoch) : 0;
+        auto load_x = [&](int i, float (&e)[8]) {
+            if (a.x_ll) ps_rw_load8_ll(a.x_ll + (size_t)i * 256, lane, e, x_ep, a.tp_err);
+            else ps_rw_load8(a.x + i * 256, lane, e);
+        };
+        if (have0) load_x(warp, e0);
         float nscale = 1.f;
         if (a.norm_w) {
             double ss = 0.0;
@@ -272,7 +292,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
 #pragma unroll 1
             for (int i = warp + PS_RW_WARPS; i < nb; i += PS_RW_WARPS) {
                 float e[8];
-                ps_rw_load8(a.x + i * 256, lane, e);
+                load_x(i, e);
 #pragma unroll
                 for (int t = 0; t < 8; t++) ss += (double)__fmul_rn(e[t], e[t]);
             }
@@ -298,7 +318,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
 #pragma unroll 1
         for (int i = warp + PS_RW_WARPS; i < nb; i += PS_RW_WARPS) {
             float e[8];
-            ps_rw_load8(a.x + i * 256, lane, e);
+            load_x(i, e);
             if (a.norm_w) {
                 float wv[8];
                 ps_rw_load8(a.norm_w + i * 256, lane, wv);
@@ -356,8 +376,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             if (q == 0 && row < a.seg[0].row_end) {
                 const float hv = ps_silu_mul(g, u);
                 a.seg[0].dst[row] = hv;
-                if (a.tpo)
-                    for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][row] = hv; // all-gather by peer stores
+                if (a.tpo) { // all-gather by peer stores
+                    if (ll_epoch) ps_tp_ll_store(a.tpo, row, hv, ll_epoch);
+                    else
+                        for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][row] = hv;
+                }
             }
             if (a.xq_out) {
                 const int i = oct >> 5; // 32 octets per 256-row block
@@ -408,8 +431,11 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             } else if (q == 0 && live) {
                 if (EPI == PS_EPI_RESIDUAL) res = __fadd_rn(a.residual[n], res);
                 a.seg[sg].dst[n] = res;
-                if (a.tpo && (EPI == PS_EPI_RESIDUAL || !a.part_val))
-                    for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][n] = res; // all-gather by peer stores
+                if (a.tpo && (EPI == PS_EPI_RESIDUAL || !a.part_val)) { // all-gather by peer stores
+                    if (ll_epoch) ps_tp_ll_store(a.tpo, n, res, ll_epoch);
+                    else
+                        for (int p = 0; p < a.tpo->n; p++) a.tpo->peer_dst[p][n] = res;
+                }
                 if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
             }
         }
@@ -441,7 +467,10 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
         }
     }
     ps_bar_sync(2, PS_RW_THREADS);
-    if (a.tpo && tid == 0) ps_tp_signal(a.tpo, (int)gridDim.x);
+    if (a.tpo && tid == 0) {
+        if (ll_epoch) ps_tp_ll_done(a.tpo, (int)gridDim.x, ll_epoch);
+        else ps_tp_signal(a.tpo, (int)gridDim.x);
+    }
     ps_tl_max(a.tl, 1);
 }
 

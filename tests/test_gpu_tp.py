@@ -25,7 +25,7 @@ def n_gpus():
 
 
 @pytest.mark.skipif(n_gpus() < 2, reason="needs 2 GPUs")
-@pytest.mark.parametrize("mode", ["p2p", "nccl"])
+@pytest.mark.parametrize("mode", ["p2p", "p2p_fence", "nccl"])
 @pytest.mark.parametrize("preset,size", [("tiny-llama", 2), ("slice-1b", 2), ("slice-1b", 4)])
 def test_tp_decode_bit_exact(preset, size, mode):
     if n_gpus() < size:
@@ -52,6 +52,6 @@ def test_tp_decode_bit_exact(preset, size, mode):
         L.assert_bit_equal(r["logits"], lg_o, "tensor-parallel logits vs oracle")
         assert list(r["dev_ids"]) == ids_long
         assert int(r["tp_error"]) == 0
-        assert int(r["p2p"]) == (1 if mode == "p2p" else 0)
+        assert int(r["p2p"]) == (1 if mode.startswith("p2p") else 0)
         if mode == "nccl":
             assert int(r["gathers"]) > 0

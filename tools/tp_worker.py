@@ -5,7 +5,8 @@ weights, prefills a prompt, decodes greedily on the device, and dumps ids (+ the
 
 The 128-byte NCCL id travels through <id_file> (rank 0 writes it), the 64-byte CUDA-IPC handles of the exchange heaps
 through <id_file>.ipc<rank>; any other transport works as well.  Mode `p2p` (default) = all-gathers fused into the
-producing kernels as peer stores; `nccl` = NCCL all-gathers between the kernels.
+producing kernels as peer stores (`p2p_fence`: with the fence + epoch-flag protocol everywhere); `nccl` = NCCL all-gathers
+between the kernels.
 """
 import os
 import sys
@@ -31,7 +32,7 @@ else:
     nid = open(id_file, "rb").read()
 mode = sys.argv[8] if len(sys.argv) > 8 else "p2p"
 m = capi.CudaModel(model_dir, max_batch=32, device=rank, tp_rank=rank, tp_size=size, nccl_id=nid)
-if mode == "p2p":
+if mode.startswith("p2p"):
     with open(f"{id_file}.ipc{rank}.tmp", "wb") as f:
         f.write(m.tp_export())
     os.replace(f"{id_file}.ipc{rank}.tmp", f"{id_file}.ipc{rank}")
@@ -44,6 +45,8 @@ if mode == "p2p":
             time.sleep(0.05)
         handles.append(open(f"{id_file}.ipc{r}", "rb").read())
     m.tp_import(handles)
+    if mode == "p2p_fence":   # the fence + epoch-flag protocol for every exchange (default: in-band flags for the per-layer ones)
+        m.be.set_option("tp_ll", 0)
 prompt = synth.random_prompt(m.vocab, n_prompt, seed=11)
 ids, logits = m.generate(prompt, 4, batch_size=16)            # host-driven steps: logits gathered on every rank
 m.reset()
