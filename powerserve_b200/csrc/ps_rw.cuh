@@ -5,16 +5,16 @@
 // it (ggml.c:12667-12721, ggml-quants.c:3799-3837) as prologue and the bias / residual / SiLU*up ops after it
 // (ggml.c:10042-10112, src/backend/ggml/ggml.cpp:115-129) as epilogue.  Bit-identical to the table-op kernels.
 //
-// Why this shape (B200): the op is an HBM stream of 144-byte blocks with ~250 integer instructions of work per block —
+// Why this shape (B200): the op is an HBM stream of 144-byte blocks with ~85 warp instructions of work per 8 row-blocks -
 // at 6.5 TB/s an SM must retire a block every ~6 cycles, so the kernel is as much issue-bound as bandwidth-bound.  The
 // earlier design (one thread per block, shared-memory hand-off to separate fp32 chain threads, CTA-wide barriers per
 // tile, 8 warps) measured 20-27 % issue utilisation and 3x instruction overhead (profiles/r01b_*).  Here:
 //   * FOUR threads own one weight row: thread q of the quad owns AVX lanes 2q, 2q+1 of the reference's __m256 accumulator
 //     (and lane q of the __m128 mins accumulator) and walks the row's super-blocks IN ORDER, so the fp32 FMA chains of
 //     the reference live in three registers per thread — no hand-off, no chain phase, no barrier inside the stream.
-//   * a warp owns an OCTET of rows.  Weights are re-laid at bind time (same bytes, permuted) so that the eight rows'
-//     16-byte headers and 32-byte quant groups of one super-block are adjacent: a warp's LDS are conflict-free and a
-//     pipeline stage (kb super-blocks of an octet) is ONE contiguous bulk copy.
+//   * a warp owns an OCTET of rows.  Weights are re-laid at bind time (quant bytes permuted, the 6-bit scales / mins
+//     expanded to bytes once) so that the eight rows' 16-byte headers and 32-byte quant groups of one super-block are
+//     adjacent: a warp's LDS are conflict-free and a pipeline stage (kb super-blocks of an octet) is ONE contiguous bulk copy.
 //   * every warp runs its own TMA ring (cp.async.bulk + mbarrier, lane 0 re-arms a slot right after the warp drained
 //     it), so warps never wait for each other; the first slots are requested before griddepcontrol.wait, i.e. while the
 //     previous kernel in the PDL chain is still draining.
@@ -38,7 +38,7 @@ struct PsRwSeg {
 };
 
 struct PsRwArgs {
-    const uint8_t *w;      // repacked weights: [n_oct][nb][rpt][1152]
+    const uint8_t *w;      // repacked weights: [n_oct][nb][rpt][1184]
     int n_oct;             // row octets (pairs of octets when rpt == 2)
     int K;                 // contraction length, multiple of 256
     int kb;                // super-blocks per pipeline stage
@@ -76,7 +76,7 @@ struct PsRwArgs {
 };
 
 // ---------------------------------------------------------------------------------------------------- repack
-// GGUF rows [n_rows][nb][144] -> [octet][block][slot][1152] where 1152 = 8 headers (16 B) + 4 groups x 8 rows x 32 B.
+// GGUF rows [n_rows][nb][144] -> [octet][block][slot][1184] where 1184 = 8 headers (16 B) + 8 x 4 B (mins 4..7) + 4 groups x 8 rows x 32 B.
 // `slot`/`n_slots` interleave several matrices per octet-block (gate | up).  Rows beyond n_rows are zero blocks.
 __global__ void ps_k_rw_repack(uint8_t *__restrict__ dst, const uint8_t *__restrict__ src, int64_t n_rows, int64_t nb, int64_t oct0, int slot,
                                int n_slots) {
@@ -481,7 +481,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
 // group, whose Q8_K images sit in shared memory.  The CTA's weight slice is re-streamed (from L2) once per column group.
 // ====================================================================================================================
 struct PsRwmArgs {
-    const uint8_t *w;      // repacked weights: [n_oct][nb][n_slots][1152]
+    const uint8_t *w;      // repacked weights: [n_oct][nb][n_slots][1184]
     int n_oct, K, kb, ns, n_act;
     int slot, n_slots;     // which interleaved matrix of the buffer (gate | up)
     PsRwSeg seg[3];        // dst of a segment is [bs][rows of the segment]; mode unused
