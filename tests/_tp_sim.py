@@ -12,6 +12,39 @@ from powerserve_b200 import gguf, tp
 from tests import _libs as L
 
 
+class InbandExchange:
+    """CPU model of the in-band-flag exchange of the CUDA path (ps_tp_ll_store / ps_tp_ll_done / ps_rw_load8_ll in
+    powerserve_b200/csrc): every rank stores its shard into EVERY rank's mirror of the gathered vector as naturally
+    aligned 64-bit words {value bits, epoch}; nobody fences or signals; the consumer polls the words it is about to read
+    until all of them carry the epoch of this phase.  One epoch counter per phase (`slot`), local, advanced once per
+    exchange, in lock step on every rank; x-after-Wo and x-after-Wdown use separate mirrors because their epochs are
+    equal numbers.  `mirrors[slot][p]` is rank p's mirror (np.uint64 view of memory shared by all ranks)."""
+    SLOTS = ("att", "x1", "h", "x2", "logits")
+
+    def __init__(self, rank: int, size: int, mirrors):
+        self.rank, self.size, self.mirrors = rank, size, mirrors
+        self.epoch = {s: 0 for s in self.SLOTS}
+        self.polls = 0
+
+    def __call__(self, a, slot):
+        import time
+        a32 = np.ascontiguousarray(a, np.float32)
+        e = np.uint64(self.epoch[slot] + 1)
+        words = (e << np.uint64(32)) | a32.view(np.uint32).astype(np.uint64)
+        off = self.rank * a32.size
+        for p in range(self.size):                                   # peer stores, own rank included
+            self.mirrors[slot][p][off:off + a32.size] = words
+        self.epoch[slot] = int(e)
+        mine, n, t0 = self.mirrors[slot][self.rank], a32.size * self.size, time.time()
+        while True:                                                  # the consumer's poll
+            w = mine[:n].copy()
+            self.polls += 1
+            if np.all((w >> np.uint64(32)) == e):
+                return (w & np.uint64(0xffffffff)).astype(np.uint32).view(np.float32)
+            if time.time() - t0 > 120:
+                raise RuntimeError(f"in-band flag wait gave up (slot {slot}, epoch {int(e)})")
+
+
 class ShardedOracle:
     def __init__(self, path: str, rank: int, size: int, all_gather):
         self.o = L.oracle()
@@ -89,22 +122,22 @@ class ShardedOracle:
             o.ps_or_softmax_ext(L.fptr(pr), L.fptr(kq), L.fptr(mask), n_kv, 1, self.nh_l, 1.0 / np.sqrt(np.float32(hs)))
             att = np.zeros(self.nh_l * hs, np.float32)
             o.ps_or_attn_pv(L.fptr(att), L.fptr(self.vct[l]), L.fptr(pr), hs, self.nh_l, self.nkv_l, n_kv, self.n_ctx, 1)
-            att_full = self.all_gather(att)                                         # gather 1: attention output
+            att_full = self.all_gather(att, "att")                                  # gather 1: attention output
             d0, d1 = tp.row_range(self.dim, r, self.size)
             xs = np.zeros(d1 - d0, np.float32)
             wo = self._matmul(p + "attn_output.weight", att_full)
             o.ps_or_add(L.fptr(xs), L.fptr(np.ascontiguousarray(x[d0:d1])), L.fptr(wo), d1 - d0, d1 - d0)
-            x = self.all_gather(xs)                                                 # gather 2: x after Wo
+            x = self.all_gather(xs, "x1")                                           # gather 2: x after Wo
             xn = self._rmsnorm(x, p + "ffn_norm.weight")
             g, u = self._matmul(p + "ffn_gate.weight", xn), self._matmul(p + "ffn_up.weight", xn)
             h = np.zeros_like(g)
             o.ps_or_silu_hadamard(L.fptr(h), L.fptr(g), L.fptr(u), g.size)
-            h_full = self.all_gather(h)                                             # gather 3: FFN hidden
+            h_full = self.all_gather(h, "h")                                        # gather 3: FFN hidden
             dn = self._matmul(p + "ffn_down.weight", h_full)
             o.ps_or_add(L.fptr(xs), L.fptr(np.ascontiguousarray(x[d0:d1])), L.fptr(dn), d1 - d0, d1 - d0)
-            x = self.all_gather(xs)                                                 # gather 4: x after Wdown
+            x = self.all_gather(xs, "x2")                                           # gather 4: x after Wdown
         self.pos += 1
         if not lm_head:
             return None
         xn = self._rmsnorm(x, "output_norm.weight")
-        return self.all_gather(self._matmul(self.out_name, xn, lm_head=True))       # logits (or arg-max partials on the GPU)
+        return self.all_gather(self._matmul(self.out_name, xn, lm_head=True), "logits")  # logits (or arg-max partials on the GPU)

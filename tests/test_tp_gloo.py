@@ -21,7 +21,7 @@ def _worker(rank, size, port, model_dir, prompt, out_dir):
     dist.init_process_group("gloo", rank=rank, world_size=size)
     from tests._tp_sim import ShardedOracle
 
-    def all_gather(a):
+    def all_gather(a, slot=None):
         t = torch.from_numpy(np.ascontiguousarray(a))
         outs = [torch.empty_like(t) for _ in range(size)]
         dist.all_gather(outs, t)
@@ -52,6 +52,60 @@ def test_row_sharded_forward_is_bit_identical(preset):
         mp.spawn(_worker, args=(2, port, d, prompt, td), nprocs=2, join=True)
         for r in range(2):
             L.assert_bit_equal(np.load(os.path.join(td, f"logits{r}.npy")), ref, f"{preset}: rank {r} sharded logits vs unsharded oracle")
+
+
+def _inband_worker(rank, size, names, n_words, model_dir, prompt, out_dir):
+    from multiprocessing import shared_memory
+
+    from tests._tp_sim import InbandExchange, ShardedOracle
+    shms = {s: [shared_memory.SharedMemory(name=names[s][p]) for p in range(size)] for s in InbandExchange.SLOTS}
+    mirrors = {s: [np.ndarray((n_words,), np.uint64, buffer=m.buf) for m in shms[s]] for s in InbandExchange.SLOTS}
+    ex = InbandExchange(rank, size, mirrors)
+    m = ShardedOracle(model_dir, rank, size, ex)
+    logits = []
+    for tok in prompt[:-1]:
+        m.step(int(tok), lm_head=False)
+    tok = int(prompt[-1])
+    for _ in range(3):
+        lg = m.step(tok)
+        logits.append(lg)
+        tok = int(np.argmax(lg))
+    np.save(os.path.join(out_dir, f"logits{rank}.npy"), np.stack(logits))
+    del mirrors, ex, m
+    for s in shms.values():
+        for h in s:
+            h.close()
+
+
+def test_inband_flag_exchange_model():
+    """The fence-free exchange of the CUDA tensor-parallel path, modelled on CPU with real concurrency: two processes,
+    64-bit {value, epoch} words in shared memory, no barrier anywhere - the only synchronisation is the consumer's poll."""
+    from multiprocessing import shared_memory
+
+    from tests._tp_sim import InbandExchange
+    preset = "tiny-llama"
+    d = M.model_dir(preset)
+    sh = synth.PRESETS[preset]
+    prompt = synth.random_prompt(sh.vocab_size, 7, seed=21)
+    om = M.OracleModel(d)
+    _, ref = om.generate(prompt, 3, batch_size=1)
+    om.close()
+    n_words = max(sh.ffn_dim, sh.vocab_size, sh.dim)
+    shms = {s: [shared_memory.SharedMemory(create=True, size=8 * n_words) for _ in range(2)] for s in InbandExchange.SLOTS}
+    try:
+        for s in shms.values():
+            for h in s:
+                np.ndarray((n_words,), np.uint64, buffer=h.buf)[:] = 0
+        names = {s: [h.name for h in v] for s, v in shms.items()}
+        with tempfile.TemporaryDirectory() as td:
+            mp.spawn(_inband_worker, args=(2, names, n_words, d, prompt, td), nprocs=2, join=True)
+            for r in range(2):
+                L.assert_bit_equal(np.load(os.path.join(td, f"logits{r}.npy")), ref, f"rank {r}: in-band-flag exchange vs unsharded oracle")
+    finally:
+        for s in shms.values():
+            for h in s:
+                h.close()
+                h.unlink()
 
 
 def test_sharding_plan():
