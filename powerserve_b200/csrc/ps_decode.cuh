@@ -140,7 +140,7 @@ PS_D bool ps_tp_ll_load2(const unsigned long long *p, uint32_t e, float &v0, flo
     v1 = __uint_as_float((uint32_t)b);
     return (uint32_t)(a >> 32) == e && (uint32_t)(b >> 32) == e;
 }
-#define PS_TP_LL_SPINS (1 << 22) // bounded: a dead peer yields garbage + the tp_error counter, never a hung GPU
+#define PS_TP_LL_SPINS (1 << 25) // bounded (~a minute; ranks may enter their first step seconds apart): a dead peer yields garbage + the tp_error counter, never a hung GPU
 
 // stand-alone consumer wait (before a device-to-host copy of a gathered vector)
 __global__ void ps_k_tp_wait(const PsTpIn *tpi) {
