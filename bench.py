@@ -134,7 +134,9 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     shape = synth.PRESETS[args.model]
-    shape.n_ctx = max(shape.n_ctx, 4096)
+    # context capacity: the default run fits 4096 (the attention kernel then keeps its V^T rows in shared memory); a longer
+    # --steps / --prompt grows it (every leg below rolls the KV position back to prompt + warmup before it starts)
+    shape.n_ctx = max(shape.n_ctx, 4096, -(-(args.prompt + 1 + args.warmup + args.steps + 32) // 256) * 256)
     hbm_peak, peak_src = peaks()
     wbytes = weight_bytes_per_token(shape)
     n_cpu = os.cpu_count() or 2
