@@ -159,3 +159,8 @@ def case_small_ops(be):
 
 
 OP_CASES = {"quantize": case_quantize, "matmul": case_matmul, "small": case_small_ops}
+
+# (gguf-py type name, ggml type id, block elements, rows, blocks per row, seed, scale) for make_golden_gguf_py.py: the
+# reference's Python dequantisers (pinned against libggml by its own gguf-py/tests/test_quants.py) on seeded random blocks
+GGUF_PY_CASES = [("Q4_K", L.Q4_K, 256, 24, 4, 101, 1.0), ("Q4_K", L.Q4_K, 256, 3, 56, 102, 0.02), ("Q6_K", L.Q6_K, 256, 24, 4, 103, 1.0),
+                 ("Q4_0", L.Q4_0, 32, 24, 16, 104, 1.0), ("Q8_0", L.Q8_0, 32, 24, 16, 105, 1.0), ("Q8_0", L.Q8_0, 32, 5, 152, 106, 30.0)]
