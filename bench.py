@@ -90,28 +90,84 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons, "samples": len(sm)}
 
 
-def cpu_reference_run(shape, tensors, prompt, n_decode, n_threads, batch_size=128):
-    """Time the reference's own CPU implementation (oracle/_ref/ps_ref_run) on the SAME weights; falls back to the
-    oracle port when the compiled reference did not travel.  Returns (dict, kind)."""
-    ref_exe = os.path.join(ROOT, "oracle", "_ref", "ps_ref_run")
-    if os.path.exists(ref_exe):
-        with tempfile.TemporaryDirectory(dir=os.environ.get("PS_BENCH_TMP", None)) as td:
-            os.makedirs(os.path.join(td, "ggml"))
-            json.dump(synth.model_json(shape), open(os.path.join(td, "model.json"), "w"))
-            gguf.write_gguf(os.path.join(td, "ggml", "weights.gguf"), tensors, arch=shape.arch)
-            pf = os.path.join(td, "prompt.txt")
-            open(pf, "w").write(" ".join(str(int(t)) for t in prompt))
-            r = subprocess.run([ref_exe, td, str(n_threads), str(batch_size), pf, str(n_decode), os.path.join(td, "out")],
-                               capture_output=True, text=True, timeout=3000)
-            if r.returncode != 0:
-                raise RuntimeError("ps_ref_run failed: " + r.stderr[-1000:])
-            tm = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
-            ids = [int(x) for x in open(os.path.join(td, "out.ids")).read().split()]
-            return {"decode_tok_s": tm["decode_tok_s"], "prefill_tok_s": tm["prefill_tok_s"], "ids": ids}, "reference"
-    # port: the oracle restatement (single process, its own thread pool)
-    sys.path.insert(0, ROOT)
-    from tests import _model as M  # noqa: F401  (test infrastructure; allowed for the cpu_baseline leg only)
-    raise RuntimeError("oracle/_ref not present and in-memory oracle baseline not wired for bench; run `make -C oracle ref`")
+def cpu_isa_v4() -> bool:
+    try:
+        flags = open("/proc/cpuinfo").read().split("flags", 1)[1].split("\n", 1)[0].split()
+    except Exception:
+        return False
+    return all(f in flags for f in ("avx512f", "avx512bw", "avx512cd", "avx512dq", "avx512vl"))
+
+
+def ref_binary(timing: bool):
+    """The compiled reference driver: the AVX2 build (GGML_NATIVE=OFF flags, the one parity is pinned on) or, for TIMING on a
+    host with AVX-512, the x86-64-v4 build (what GGML_NATIVE=ON would select there)."""
+    v4 = os.path.join(ROOT, "oracle", "_ref", "v4", "ps_ref_run")
+    if timing and os.path.exists(v4) and cpu_isa_v4():
+        return v4, "x86-64-v4 (AVX-512) timing build"
+    return os.path.join(ROOT, "oracle", "_ref", "ps_ref_run"), "AVX2+FMA+F16C build (GGML_NATIVE=OFF flags)"
+
+
+class RefModelDir:
+    """The synthetic model written once as a PowerServe model directory (model.json + ggml/weights.gguf) for the CPU legs."""
+
+    def __init__(self, shape, tensors):
+        self.td = tempfile.TemporaryDirectory(dir=os.environ.get("PS_BENCH_TMP", None))
+        d = self.td.name
+        os.makedirs(os.path.join(d, "ggml"))
+        json.dump(synth.model_json(shape), open(os.path.join(d, "model.json"), "w"))
+        gguf.write_gguf(os.path.join(d, "ggml", "weights.gguf"), tensors, arch=shape.arch)
+        self.path = d
+
+    def close(self):
+        self.td.cleanup()
+
+
+def cpu_reference_run(mdir: str, vocab: int, prompt, n_decode, n_threads, batch_size=128, timing=False, forced=None, dump_logits=0):
+    """Run the reference's own CPU implementation (oracle/_ref/ps_ref_run: PowerServe's model -> graph -> executor ->
+    GGMLBackend -> vendored ggml, compiled from /root/reference by oracle/Makefile) on the SAME weights."""
+    exe, isa = ref_binary(timing)
+    if not os.path.exists(exe):
+        raise RuntimeError("oracle/_ref/ps_ref_run is missing: run `make -C oracle ref` where /root/reference exists")
+    pf = os.path.join(mdir, "prompt.txt")
+    open(pf, "w").write(" ".join(str(int(t)) for t in prompt))
+    cmd = [exe, mdir, str(n_threads), str(batch_size), pf, str(n_decode), os.path.join(mdir, "out")]
+    if forced is not None:
+        ff = os.path.join(mdir, "forced.txt")
+        open(ff, "w").write(" ".join(str(int(t)) for t in forced))
+        cmd += ["--force", ff]
+    if dump_logits:
+        cmd += ["--dump-logits", str(dump_logits)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=3000)
+    if r.returncode != 0:
+        raise RuntimeError("ps_ref_run failed: " + r.stderr[-1000:])
+    tm = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    ids = [int(x) for x in open(os.path.join(mdir, "out.ids")).read().split()]
+    logits = np.fromfile(os.path.join(mdir, "out.logits"), dtype=np.float32).reshape(-1, vocab) if dump_logits else None
+    return {"decode_tok_s": tm["decode_tok_s"], "prefill_tok_s": tm["prefill_tok_s"], "ids": ids, "logits": logits, "isa": isa}
+
+
+PARITY_PROMPT, PARITY_STEPS = 17, 9
+
+
+def parity_inputs(shape):
+    return synth.random_prompt(shape.vocab_size, PARITY_PROMPT, seed=1234), synth.random_prompt(shape.vocab_size, PARITY_STEPS, seed=4321)
+
+
+def gpu_parity_leg(model, shape):
+    """Teacher-forced parity sample on the benchmarked weights: 17-token prompt fed with batch_size 1 (the chunking every
+    parallelism mode shares), then 9 steps whose inputs are FORCED random ids (so the ids are not a fixed point).
+    Returns the greedy ids and a hash of the logits bits; 1 GPU, tensor-parallel and the CPU reference must agree."""
+    import hashlib
+    cp, forced = parity_inputs(shape)
+    ids, lg = model.generate(cp, PARITY_STEPS, batch_size=1, forced=forced)
+    return [int(x) for x in ids], hashlib.sha256(np.ascontiguousarray(lg).tobytes()).hexdigest()[:16]
+
+
+def cpu_parity_leg(mdir, shape, cpu_threads):
+    import hashlib
+    cp, forced = parity_inputs(shape)
+    res = cpu_reference_run(mdir, shape.vocab_size, cp, PARITY_STEPS, cpu_threads, batch_size=1, forced=forced, dump_logits=PARITY_STEPS)
+    return res, hashlib.sha256(np.ascontiguousarray(res["logits"]).tobytes()).hexdigest()[:16]
 
 
 def main():
@@ -151,17 +207,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return 0
+        # like for like: the SAME prompt length and decode steps as our arm (a 2048-token CPU prefill is about a minute);
+        # only the step count is bounded (<= 64 timed tokens) and the real numbers are what the line states
+        n_timed = max(2, min(args.steps, 64))
+        n_warm = max(1, min(args.warmup, 4))   # ps_ref_run's decode clock already excludes the first token (run.cpp:96-154)
         tensors = synth.generate_tensors(shape, args.seed)
-        prompt = synth.random_prompt(shape.vocab_size, 17, seed=1234)
-        n_dec = max(2, min(args.steps, 9))
+        prompt = synth.random_prompt(shape.vocab_size, args.prompt + 1, seed=1234)
         t0 = time.time()
-        res, kind = cpu_reference_run(shape, tensors, prompt, n_dec + min(args.warmup, 1), cpu_threads)
+        md = RefModelDir(shape, tensors)
+        try:
+            res = cpu_reference_run(md.path, shape.vocab_size, prompt, n_warm + n_timed, cpu_threads, batch_size=args.prefill_batch, timing=True)
+        finally:
+            md.close()
+        cfg["reference_isa"] = res["isa"]
         out = {"impl": "reference", "metric": "decode_tok_s", "value": res["decode_tok_s"], "unit": "tok/s", "n_gpus": args.gpus,
-               "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 / max(res["decode_tok_s"], 1e-9),
+               "steps": n_timed + n_warm - 1, "warmup": 1, "steps_requested": args.steps, "ms_per_step": 1000.0 / max(res["decode_tok_s"], 1e-9),
                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int8xint4 dot, fp32 accumulate", "data": "synthetic",
                "config": cfg, "prefill": {"value": res["prefill_tok_s"], "unit": "tok/s", "tokens": len(prompt) - 1},
-               "cpu_baseline": {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": kind,
-                                "sample": f"{len(prompt)}-token prompt + {n_dec} greedy decode tokens of the full model, wall clock like app/run/run.cpp:96-154"},
+               "cpu_baseline": {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": "reference",
+                                "sample": f"{len(prompt) - 1}-token prefill (batch {args.prefill_batch}) + {n_warm + n_timed} greedy decode tokens at context "
+                                          f"{args.prompt}+ of the full model, wall clock like app/run/run.cpp:96-154 (first decode token excluded); {res['isa']}"},
                "e2e": {"value": res["decode_tok_s"], "unit": "tok/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                "wall_s": time.time() - t0}
         print(json.dumps(out))
@@ -296,18 +361,29 @@ def main():
     if tp > 1:
         out["tp"] = {"size": tp, "p2p": bool(model.be.counter("tp_p2p")), "peer_wait_error": model.be.counter("tp_error"), "nccl_allgathers_per_step": (model.be.counter("tp_allgathers")) // max(1, model.be.counter("graph_replays") + 1),
                      "note": "row sharding keeps every dot product whole: results are bit-identical to one GPU (tests/test_gpu_tp.py)"}
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+    # --- parity on the benchmarked weights (every N): teacher-forced sample, ids + logits-bits hash; rank 0 checks them against
+    # the compiled CPU reference (AVX2 build) run on the same weights and inputs
+    gp_ids, gp_hash = gpu_parity_leg(model, shape)
+    out["parity"] = {"sample": f"{PARITY_PROMPT}-token prompt (batch 1) + {PARITY_STEPS} teacher-forced steps", "greedy_ids": gp_ids, "logits_sha256_16": gp_hash}
+    if world > 1:
+        hs = [None] * world
+        dist.all_gather_object(hs, gp_hash)
+        out["parity"]["all_ranks_equal"] = len(set(hs)) == 1
+    if rank == 0 and not args.no_cpu_baseline:
         try:
-            cp = synth.random_prompt(shape.vocab_size, 17, seed=1234)
-            res, kind = cpu_reference_run(shape, tensors, cp, 9, cpu_threads)
-            out["cpu_baseline"] = {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": kind,
-                                   "sample": "17-token prompt + 9 greedy decode tokens of the full model (same weights)",
-                                   "prefill_tok_s": res["prefill_tok_s"]}
-            # parity spot check on the same weights: the GPU must produce the same greedy ids as the CPU reference
-            model.reset()
-            model.prefill(cp, 128)
-            gi = [int(x) for x in model.decode_greedy(int(cp[-1]), 9)]
-            out["cpu_baseline"]["greedy_ids_match"] = gi == res["ids"]
+            md = RefModelDir(shape, tensors)
+            try:
+                pres, chash = cpu_parity_leg(md.path, shape, cpu_threads)
+                out["parity"].update({"cpu_logits_sha256_16": chash, "logits_bit_exact": chash == gp_hash, "greedy_ids_match": pres["ids"] == gp_ids})
+                if world == 1:
+                    cp = synth.random_prompt(shape.vocab_size, 17, seed=1234)
+                    res = cpu_reference_run(md.path, shape.vocab_size, cp, 9, cpu_threads)
+                    out["cpu_baseline"] = {"value": res["decode_tok_s"], "unit": "tok/s", "cores": cpu_threads, "kind": "reference",
+                                           "sample": "17-token prompt + 9 greedy decode tokens of the full model (same weights), " + res["isa"] +
+                                                     "; the like-for-like CPU number (same context and steps) is `bench.py --impl reference`",
+                                           "prefill_tok_s": res["prefill_tok_s"], "greedy_ids_match": out["parity"]["greedy_ids_match"]}
+            finally:
+                md.close()
         except Exception as e:  # the baseline is a report, never a reason to lose the GPU number
             out["cpu_baseline"] = {"value": None, "unit": "tok/s", "cores": cpu_threads, "kind": "unavailable", "sample": str(e)[:200]}
     model.close()

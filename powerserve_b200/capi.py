@@ -226,7 +226,28 @@ class CudaBackend:
     def attn_pv(self, out, v_cache_t, p, hs, n_heads, n_kv_heads, n_kv, n_ctx, bs):
         self._ck(self.L.ps_cuda_attn_pv(self.h, out.ptr, v_cache_t.ptr, p.ptr, hs, n_heads, n_kv_heads, n_kv, n_ctx, bs))
 
+    def copy_2d(self, dst, ds0, ds1, src, ss0, ss1, ne0, ne1):
+        """GGMLBackend::copy / cont on 2-D fp32 views (byte strides; powerserve_compute_forward_dup)."""
+        self._ck(self.L.ps_cuda_copy_2d(self.h, dst.ptr, ds0, ds1, src.ptr, ss0, ss1, ne0, ne1))
+
+    def read_device(self, dev_ptr: int, n_floats: int, dtype=np.float32) -> np.ndarray:
+        out = np.empty(n_floats, dtype=dtype)
+        self._ck(self.L.ps_cuda_memcpy_d2h(self.h, out.ctypes.data, dev_ptr, out.nbytes))
+        return out
+
     # ---- kv
+    def kv_advance(self, n: int):
+        self._ck(self.L.ps_cuda_kv_advance(self.h, n))
+
+    def kv_k(self, layer: int) -> int:
+        return self.L.ps_cuda_kv_k(self.h, layer)
+
+    def kv_v(self, layer: int) -> int:
+        return self.L.ps_cuda_kv_v(self.h, layer)
+
+    def logits_dev(self) -> int:
+        return self.L.ps_cuda_logits_dev(self.h)
+
     @property
     def kv_position(self) -> int:
         return self.L.ps_cuda_kv_position(self.h)

@@ -92,6 +92,7 @@ struct ps_cuda_ctx {
     int64_t maxK = 0;
     float *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *qr = nullptr, *kr = nullptr, *att = nullptr;
     float *g = nullptr, *u = nullptr, *kq = nullptr, *logits = nullptr;
+    const float *logits_last = nullptr; // where the last forward left its [bs][vocab] logits (ps_cuda_logits_dev)
     uint32_t *aqs = nullptr, *absp = nullptr;
     float *ad = nullptr;
     int32_t *tokens_dev = nullptr, *pos_dev = nullptr, *ids_dev = nullptr;
@@ -103,7 +104,10 @@ struct ps_cuda_ctx {
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
-    int *tc_err_dev = nullptr; // pipeline time-out flag of the tcgen05 GEMM (counter "tc_error")
+    int *err_dev = nullptr;    // device-detected failures, [0] tcgen05 pipeline time-out, [1] peer wait gave up, [2] step-kernel barrier time-out
+    int err_seen[3] = {};      // sticky host copy of the flags (counters "tc_error" / "tp_error" / "step_error")
+    int *h_err = nullptr;      // pinned mirror, read after every forward / decode (a set flag becomes PS_CUDA_ERR_CUDA)
+    int *tc_err_dev = nullptr; // = err_dev + 0 (counter "tc_error")
     int64_t n_tc = 0;          // tcgen05 GEMM launches (counter "tc_gemm_launches")
     std::vector<cudaEvent_t> kt_events; // option "ktime": event pairs around every row-walker mat-vec launch
     size_t kt_used = 0;
@@ -181,6 +185,21 @@ int dev_alloc(ps_cuda_ctx *ctx, void **p, size_t bytes) {
     cudaError_t e = cudaMalloc(p, bytes);
     if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_OOM, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
     ctx->owned.push_back(*p);
+    return 0;
+}
+
+// Failures detected on the device (tcgen05 pipeline time-out, a peer wait or a grid barrier that gave up) become a C-ABI
+// status: the flags ride along with the call's final device-to-host copy.  Call with work enqueued; synchronises.
+int sync_and_check(ps_cuda_ctx *ctx) {
+    PS_CK(cudaMemcpyAsync(ctx->h_err, ctx->err_dev, 16, cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    if (ctx->h_err[0] | ctx->h_err[1] | ctx->h_err[2]) {
+        const int tc = ctx->h_err[0], tp = ctx->h_err[1], st = ctx->h_err[2];
+        for (int k = 0; k < 3; k++) ctx->err_seen[k] |= ctx->h_err[k];
+        PS_CK(cudaMemsetAsync(ctx->err_dev, 0, 16, ctx->stream));
+        return fail(ctx, PS_CUDA_ERR_CUDA, "device-side failure:%s%s%s (results of this call are invalid)", tc ? " tcgen05 pipeline time-out" : "",
+                    tp ? " tensor-parallel peer wait gave up" : "", st ? " decode-step barrier gave up" : "");
+    }
     return 0;
 }
 
@@ -660,6 +679,11 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
+    PS_AL(ctx->err_dev, 16);
+    PS_CKC(cudaMemsetAsync(ctx->err_dev, 0, 16, ctx->stream));
+    ctx->tc_err_dev = ctx->err_dev;
+    ctx->tp_err_dev = ctx->err_dev + 1;
+    PS_CKC(cudaMallocHost(&ctx->h_err, 16));
     if (tp > 1) {
         auto up = [](size_t v) { return (v + 255) & ~(size_t)255; };
         ctx->off_att = 0;
@@ -678,10 +702,8 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         PS_CKC(cudaMemsetAsync(ctx->heap, 0, ctx->heap_bytes, ctx->stream));
         PS_AL(ctx->epoch_dev, 4 * PS_TP_SLOTS);
         PS_AL(ctx->done_dev, 4 * PS_TP_SLOTS);
-        PS_AL(ctx->tp_err_dev, 4);
         PS_CKC(cudaMemsetAsync(ctx->epoch_dev, 0, 4 * PS_TP_SLOTS, ctx->stream));
         PS_CKC(cudaMemsetAsync(ctx->done_dev, 0, 4 * PS_TP_SLOTS, ctx->stream));
-        PS_CKC(cudaMemsetAsync(ctx->tp_err_dev, 0, 4, ctx->stream));
         // the gathered vectors live in the heap (x replaces the workspace x allocated above for the decode path)
         ctx->att_full = reinterpret_cast<float *>(ctx->heap + ctx->off_att);
         ctx->x = reinterpret_cast<float *>(ctx->heap + ctx->off_x);
@@ -738,6 +760,7 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
     if (ctx->h_pos) cudaFreeHost(ctx->h_pos);
     if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
+    if (ctx->h_err) cudaFreeHost(ctx->h_err);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
     if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
@@ -895,8 +918,8 @@ int ps_cuda_get_mask(ps_cuda_ctx *ctx, float *mask, int64_t n_kv, int64_t bs, co
 int ps_cuda_softmax_ext(ps_cuda_ctx *ctx, float *dst, const float *x, const float *mask, int64_t ne0, int64_t ne1, int64_t ne2, float scale) {
     if (!mask) return fail(ctx, PS_CUDA_ERR_INVALID, "softmax_ext: mask is required (use get_mask)");
     if (ne0 * 4 > 160 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "softmax_ext: row of %lld exceeds shared memory", (long long)ne0);
-    static bool attr = false;
-    if (!attr) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[ctx->device] = true; }
     ps_k_softmax_ext<<<(unsigned)(ne1 * ne2), 256, (size_t)ne0 * 4, ctx->stream>>>(dst, x, mask, nullptr, ne0, ne1, scale);
     PS_LAUNCH_CK();
     return 0;
@@ -1090,8 +1113,6 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
                 if ((rc = dev_alloc(ctx, (void **)&ctx->tc_b, bb))) return rc;
                 PS_CK(cudaMemsetAsync(ctx->tc_b, 0, bb, ctx->stream)); // the mins tiles are zero outside each lane's four K positions
                 ctx->tc_b_bytes = bb;
-                if ((rc = dev_alloc(ctx, (void **)&ctx->tc_err_dev, 4))) return rc;
-                PS_CK(cudaMemsetAsync(ctx->tc_err_dev, 0, 4, ctx->stream));
                 ctx->tc_ok = true;
             }
         }
@@ -1117,8 +1138,8 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
     int rc;
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
     PS_LAUNCH_CK();
-    static bool attr = false;
-    if (!attr) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[ctx->device] = true; }
     for (int L = 0; L < d.n_layers; L++) {
         const LayerDev &ld = ctx->layers[L];
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
@@ -1161,8 +1182,8 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
         if (bs > 1 && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
-            static bool pv_attr = false;
-            if (!pv_attr) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr = true; }
+            static bool pv_attr[64] = {};
+            if (!pv_attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr[ctx->device] = true; }
             ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
                 ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
         } else {
@@ -1246,9 +1267,11 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += (int64_t)bs * 8;
     PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ctx->logits_last = ctx->logits;
     if (ctx->tp > 1 && bs > 1) {
-        // tensor parallel: the sharded path exists for the fused single-token step only; a batch is fed token by token
-        // (bit-identical to a batched pass — every column of the reference's batched ops is independent)
+        // tensor parallel: the sharded path exists for the fused single-token step only; a batch is fed token by token, i.e.
+        // it equals the reference run with batch_size = 1 (NOT a batched pass: the reference's soft-max row length and its
+        // SIMD / libm exp split depend on the chunking)
         for (int i = 0; i < bs && !rc; i++) {
             PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens + i, 4, cudaMemcpyHostToDevice, ctx->stream));
             PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos + i, 4, cudaMemcpyHostToDevice, ctx->stream));
@@ -1258,7 +1281,7 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
                 PS_CK(cudaMemcpyAsync(ctx->tp_rows + (size_t)i * ctx->d.vocab_size, ctx->logits, (size_t)ctx->d.vocab_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
             }
         }
-        if (!rc && lm_head) PS_CK(cudaMemcpyAsync(ctx->logits, ctx->tp_rows, (size_t)bs * ctx->d.vocab_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+        if (lm_head) ctx->logits_last = ctx->tp_rows; // the single-token logits slot of the exchange heap holds ONE row: batches are read from tp_rows
     } else if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
         if (lm_head) rc = run_step(ctx, false);
         else rc = decode_step_fused(ctx, false, false);
@@ -1276,12 +1299,12 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
             PS_CK(cudaMallocHost(&ctx->h_logits, bytes));
             ctx->h_logits_cap = bytes;
         }
-        PS_CK(cudaMemcpyAsync(ctx->h_logits, ctx->logits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-        PS_CK(cudaStreamSynchronize(ctx->stream));
+        PS_CK(cudaMemcpyAsync(ctx->h_logits, ctx->logits_last, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_and_check(ctx))) return rc;
         memcpy(logits_host, ctx->h_logits, bytes);
         ctx->d2h += (int64_t)bytes;
     } else {
-        PS_CK(cudaStreamSynchronize(ctx->stream));
+        if ((rc = sync_and_check(ctx))) return rc;
     }
     { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     ctx->position = pos[0] + bs; // m_kv->advance(batch_size), llama_model.cpp:109
@@ -1314,7 +1337,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         }
         PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
         PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
-        PS_CK(cudaStreamSynchronize(ctx->stream));
+        { int rc = sync_and_check(ctx); if (rc) return rc; }
         if (ctx->opt_ktime) {
             ctx->kt_ms = 0.0;
             for (size_t i = 0; i + 1 < ctx->kt_used; i += 2) {
@@ -1344,7 +1367,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     }
     PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n_steps * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    PS_CK(cudaStreamSynchronize(ctx->stream));
+    { int rc = sync_and_check(ctx); if (rc) return rc; }
     { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
     ctx->d2h += (int64_t)n_steps * 4;
@@ -1352,7 +1375,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     return 0;
 }
 
-const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx) { return ctx->logits; }
+const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx) { return ctx->logits_last ? ctx->logits_last : ctx->logits; }
 
 int ps_cuda_tp_unique_id(void *out128) {
     if (!out128 || !nccl_load()) return PS_CUDA_ERR_UNSUPPORTED;
@@ -1438,7 +1461,10 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
     if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
     if (!strcmp(name, "graph")) ctx->opt_graph = value;
-    else if (!strcmp(name, "fused")) ctx->opt_fused = value;
+    else if (!strcmp(name, "fused")) {
+        if (!value && ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "option fused = 0: the table-op path is not sharded; tensor-parallel contexts run the fused path only");
+        ctx->opt_fused = value;
+    }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
@@ -1478,13 +1504,13 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "tc_error")) {
         int v = 0;
         if (ctx->tc_err_dev) { cudaStreamSynchronize(ctx->stream); cudaMemcpy(&v, ctx->tc_err_dev, 4, cudaMemcpyDeviceToHost); }
-        return v;
+        return v | ctx->err_seen[0];
     }
     if (!strcmp(name, "tp_p2p")) return ctx->p2p ? 1 : 0;
     if (!strcmp(name, "tp_error")) { // 1 if a peer wait gave up (bounded spin)
         int v = 0;
         if (ctx->tp_err_dev) { cudaStreamSynchronize(ctx->stream); cudaMemcpy(&v, ctx->tp_err_dev, 4, cudaMemcpyDeviceToHost); }
-        return v;
+        return v | ctx->err_seen[1];
     } // CUDA-event time of the last forward / decode
     return -1;
 }

@@ -63,6 +63,9 @@ PRESETS: Dict[str, ModelShape] = {
     # real per-layer shapes of the BASELINE models with few layers / small vocab (exercise nb = 8/32 and 16/56 paths)
     "slice-1b": ModelShape("slice-1b", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),
     "slice-8b": ModelShape("slice-8b", "llama", 4096, 14336, 1, 32, 8, 128, 2048, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),
+    # the same slices with room for the benchmarked context (2048+) and beyond the shared-memory-resident attention range
+    "slice-1b-long": ModelShape("slice-1b-long", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=8192),
+    "slice-8b-long": ModelShape("slice-8b-long", "llama", 4096, 14336, 1, 32, 8, 128, 2048, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=8192),
     "tiny-mixed": ModelShape("tiny-mixed", "llama", 512, 1024, 2, 8, 4, 64, 768, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256,
                              output_type=GGML_Q6_K),
 }

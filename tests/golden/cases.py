@@ -11,6 +11,8 @@ from tests import _libs as L
 
 QTYPES = {"q4_K": (L.Q4_K, 256), "q6_K": (L.Q6_K, 256), "q4_0": (L.Q4_0, 32), "q8_0": (L.Q8_0, 32)}
 MODEL_CASES = [("tiny-llama", 20, 8, 8), ("tiny-qwen2", 20, 8, 8), ("tiny-q8", 41, 128, 6), ("tiny-mixed", 1, 128, 6), ("tiny-llama-hs128", 41, 128, 6)]
+# long-context cases (tests/golden/long_ctx.npz, make_golden_long.py): (preset, prompt tokens, prefill batch, decode steps)
+LONG_CASES = [("slice-8b-long", 2100, 128, 10), ("slice-1b-long", 2100, 128, 10), ("slice-1b-long", 4400, 128, 6)]
 
 
 def act(seed, n, kind="normal"):

@@ -46,11 +46,15 @@ def test_tp_decode_bit_exact(preset, size, mode):
     om = M.OracleModel(d)
     ids_o, lg_o = om.generate(prompt, 4, batch_size=1)
     ids_long, _ = om.generate(prompt, n_dec, batch_size=1)
+    om.reset()
+    rows_o = np.stack([om.forward([int(t)])[0] for t in prompt[:6]])   # a tensor-parallel batch == the same tokens one by one
     om.close()
     for r in res:
         assert list(r["ids"]) == ids_o
         L.assert_bit_equal(r["logits"], lg_o, "tensor-parallel logits vs oracle")
         assert list(r["dev_ids"]) == ids_long
+        L.assert_bit_equal(r["batch_logits"], rows_o, "tensor-parallel batch with lm_head (verify shape)")
+        L.assert_bit_equal(r["batch_dev"], rows_o, "ps_cuda_logits_dev after a tensor-parallel batch")
         assert int(r["tp_error"]) == 0
         assert int(r["p2p"]) == (1 if mode.startswith("p2p") else 0)
         if mode == "nccl":

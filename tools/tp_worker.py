@@ -52,7 +52,10 @@ ids, logits = m.generate(prompt, 4, batch_size=16)            # host-driven step
 m.reset()
 m.prefill(prompt, 16)
 dev_ids = m.decode_greedy(int(prompt[-1]), n_decode)           # graph-replayed device loop
-np.savez(f"{out}.rank{rank}.npz", ids=np.asarray(ids, np.int32), logits=logits, dev_ids=dev_ids,
+m.reset()
+batch_logits = m.forward(prompt[:6], lm_head=True)                # a batch WITH lm_head (the speculative-verify shape)
+batch_dev = m.be.read_device(m.be.logits_dev(), 6 * m.vocab).reshape(6, m.vocab)
+np.savez(f"{out}.rank{rank}.npz", ids=np.asarray(ids, np.int32), logits=logits, dev_ids=dev_ids, batch_logits=batch_logits, batch_dev=batch_dev,
          gathers=m.be.counter("tp_allgathers"), p2p=m.be.counter("tp_p2p"), tp_error=m.be.counter("tp_error"),
          ms=m.be.counter("last_device_ns") / 1e6 / n_decode)
 m.close()
