@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libps_cuda.so")
 SOURCES = ["ps_cuda.cu"]
-HEADERS = ["ps_tc.cuh", "ps_rw.cuh", "ps_decode.cuh", "ps_kernels.cuh", "ps_math.cuh", os.path.join("..", "..", "include", "ps_cuda.h")]
+HEADERS = ["ps_step.cuh", "ps_tc.cuh", "ps_rw.cuh", "ps_decode.cuh", "ps_kernels.cuh", "ps_math.cuh", os.path.join("..", "..", "include", "ps_cuda.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
+    extra = os.environ.get("PS_NVCC_EXTRA", "").split()   # e.g. PS_NVCC_EXTRA=-DPS_ST_DEBUG=1 (ring-protocol assertions in the step kernel)
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + [os.path.join(CSRC, s) for s in SOURCES] + ["-o", LIB]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + r.stdout + r.stderr)

@@ -4,6 +4,7 @@
 #include "ps_decode.cuh"
 #include "ps_rw.cuh"
 #include "ps_tc.cuh"
+#include "ps_step.cuh"
 
 #include <dlfcn.h>
 
@@ -145,6 +146,17 @@ struct ps_cuda_ctx {
     float *part_val = nullptr; // per-CTA partial arg-max of the lm_head kernel (greedy pick, stage 1)
     int *part_idx = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
+    // persistent per-step kernel (ps_step.cuh)
+    int opt_persist = 1;
+    int opt_attn_chunk = 0;         // testing: cap on the soft-max positions resident in shared memory (forces the chunked attention path)
+    bool step_ok = false;           // the model / geometry qualifies for ps_k_step
+    PsStLayer *st_layers = nullptr; // device table
+    PsStPeers *st_peers = nullptr;  // device table of the exchanged vectors on every rank
+    unsigned long long *st_ll[5] = {}; // this rank's (value, epoch) vectors: x, x1, att, hq image, best
+    size_t st_off[5] = {};          // tensor parallel: their offsets inside the exchange heap
+    unsigned *st_sync = nullptr;    // [0] barrier counter, [1] finish counter, [2] step serial
+    int smem_optin = 0, st_static = -1;
+    int64_t n_step = 0;             // step-kernel launches (counter "step_launches")
     long long *trace_dev = nullptr; // debug: per-launch timeline of the fused decode step (option "trace"), PS_TL_SLOTS x 4
     int trace_launch = 0;
     int64_t n_launch = 0, n_graph = 0, h2d = 0, d2h = 0;
@@ -197,8 +209,8 @@ int sync_and_check(ps_cuda_ctx *ctx) {
         const int tc = ctx->h_err[0], tp = ctx->h_err[1], st = ctx->h_err[2];
         for (int k = 0; k < 3; k++) ctx->err_seen[k] |= ctx->h_err[k];
         PS_CK(cudaMemsetAsync(ctx->err_dev, 0, 16, ctx->stream));
-        return fail(ctx, PS_CUDA_ERR_CUDA, "device-side failure:%s%s%s (results of this call are invalid)", tc ? " tcgen05 pipeline time-out" : "",
-                    tp ? " tensor-parallel peer wait gave up" : "", st ? " decode-step barrier gave up" : "");
+        return fail(ctx, PS_CUDA_ERR_CUDA, "device-side failure:%s%s%s (wait site %d; results of this call are invalid)", tc ? " tcgen05 pipeline time-out" : "",
+                    tp ? " tensor-parallel peer wait gave up" : "", st ? " decode-step wait gave up" : "", st);
     }
     return 0;
 }
@@ -574,8 +586,120 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     return 0;
 }
 
+// ---- persistent per-step kernel (ps_step.cuh): the whole decode step in ONE cooperative launch
+bool step_usable(ps_cuda_ctx *ctx) { return ctx->opt_persist && ctx->opt_fused && ctx->fused_ok && ctx->step_ok && (ctx->tp == 1 || ctx->p2p); }
+
+template <int R2> int step_static_smem(ps_cuda_ctx *ctx, int *out) {
+    cudaFuncAttributes fa;
+    PS_CK(cudaFuncGetAttributes(&fa, ps_k_step<R2>));
+    *out = (int)fa.sharedSizeBytes;
+    return 0;
+}
+template <int R2> int launch_step_r(ps_cuda_ctx *ctx, const PsStArgs &a, int img_bytes, size_t smem) {
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_step<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, ctx->smem_optin - ctx->st_static));
+        attr[ctx->device] = true;
+    }
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3((unsigned)ctx->n_sm);
+    cfg.blockDim = dim3(PS_ST_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeCooperative; // all CTAs resident together (the kernel's device-wide barriers depend on it)
+    at[0].val.cooperative = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ps_k_step<R2>, a, img_bytes);
+    ctx->n_launch++;
+    ctx->n_step++;
+    if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "step kernel launch failed: %s", cudaGetErrorString(e));
+    return 0;
+}
+
+// one decode step on the token in tokens_dev[0] at position pos_dev[0]; n_kv_max = the longest soft-max row this launch may see
+int launch_step(ps_cuda_ctx *ctx, int mode, int n_kv_max) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int r2 = d.n_heads / d.n_kv_heads;
+    PsStArgs a{};
+    a.layers = ctx->st_layers; a.peers = ctx->st_peers;
+    a.n_layers = d.n_layers; a.dim = d.dim; a.qdim = d.n_heads * d.head_size; a.ffn = d.ffn_dim; a.hs = d.head_size; a.n_ctx = d.n_ctx;
+    a.qdim_l = ctx->nh_l * d.head_size; a.kvd_l = ctx->nkv_l * d.head_size; a.ffn_l = ctx->ffn_l; a.vocab_l = ctx->vocab_l; a.nkv_l = ctx->nkv_l;
+    a.tp = ctx->tp; a.rank = ctx->rank;
+    a.eps = d.norm_eps; a.kq_scale = 1.0f / sqrtf((float)d.head_size);
+    a.w_embd = ctx->w_embd; a.w_out = ctx->rw_out; a.out_norm = ctx->w_out_norm; a.rope_table = ctx->rope_table;
+    a.tokens_dev = ctx->tokens_dev; a.pos_dev = ctx->pos_dev; a.ids_dev = ctx->ids_dev; a.ctr_dev = ctx->ctr_dev;
+    a.x_ll = ctx->st_ll[0]; a.x1_ll = ctx->st_ll[1]; a.att_ll = ctx->st_ll[2]; a.hq_ll = ctx->st_ll[3]; a.best_ll = ctx->st_ll[4];
+    a.q = ctx->q; a.sc = ctx->kq; a.h = ctx->g_part; a.logits = ctx->logits_part;
+    a.blk_cnt = ctx->blk_cnt; a.part_val = ctx->part_val; a.part_idx = ctx->part_idx;
+    a.bar_ctr = ctx->st_sync; a.done_ctr = ctx->st_sync + 1; a.serial = ctx->st_sync + 2;
+    a.err = ctx->err_dev + 2;
+    a.tpo_logits = (ctx->tp > 1 && (mode & PS_ST_MODE_LMHEAD) && !(mode & PS_ST_MODE_PICK)) ? ctx->tpo_dev + PS_TP_SLOT_LOGITS : nullptr;
+    auto kb_of = [](int nb, int cap) { int kb = cap; while (nb % kb) kb >>= 1; return kb; };
+    a.kb_dim = kb_of(a.dim / 256, 4); a.kb_gu = kb_of(a.dim / 256, 2); a.kb_q = kb_of(a.qdim / 256, 4); a.kb_ffn = kb_of(a.ffn / 256, 4);
+    a.mode = mode;
+    a.timeout_ns = ctx->tp > 1 ? 30000000000LL : 2000000000LL;
+    a.tl = ctx->trace_dev;
+    // P.V work split: halve the dims per CTA while fewer than half of the SMs would have an item
+    a.dpc = 8;
+    while (a.dpc > 1 && a.nkv_l * (a.hs / a.dpc) * 2 <= ctx->n_sm) a.dpc >>= 1;
+    // shared memory: [activation image | soft-max rows][two rings]
+    if (ctx->st_static < 0) { // the kernel's static shared memory comes out of the same opt-in limit
+        int rc0, v = 0;
+        switch (r2) {
+        case 1: rc0 = step_static_smem<1>(ctx, &v); break;
+        case 2: rc0 = step_static_smem<2>(ctx, &v); break;
+        case 4: rc0 = step_static_smem<4>(ctx, &v); break;
+        default: rc0 = step_static_smem<8>(ctx, &v); break;
+        }
+        if (rc0) return rc0;
+        ctx->st_static = (v + 127) & ~127;
+    }
+    const int budget = ctx->smem_optin - ctx->st_static;
+    const int img_need = std::max(std::max(a.dim + a.dim / 8, a.qdim + a.qdim / 8), a.ffn + a.ffn / 8);
+    int ch = std::min((n_kv_max + 255) & ~255, std::max(256, (64 * 1024 / (4 * r2)) & ~255));
+    if (ctx->opt_attn_chunk > 0) ch = std::min(ch, std::max(256, ctx->opt_attn_chunk & ~255));
+    int img_bytes = 0, nsp = 0;
+    for (;;) {
+        img_bytes = (std::max(img_need, r2 * ch * 4) + 127) & ~127;
+        nsp = (budget - img_bytes) / (PS_ST_PROD * (PS_ST_SLOT + 16));
+        if (nsp >= 14 || ch <= 256) break;
+        ch = std::max(256, (ch / 2 + 255) & ~255); // long contexts: keep the weight rings deep, rebuild the soft-max rows in chunks
+    }
+    if (nsp < 4) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "step kernel: no room for the weight rings (image %d bytes)", img_bytes);
+    nsp = std::min(nsp, 64);
+    a.nsp = nsp; a.attn_chunk = ch;
+    const size_t smem = (size_t)img_bytes + (size_t)PS_ST_PROD * nsp * (PS_ST_SLOT + 16);
+    int rc;
+    switch (r2) {
+    case 1: rc = launch_step_r<1>(ctx, a, img_bytes, smem); break;
+    case 2: rc = launch_step_r<2>(ctx, a, img_bytes, smem); break;
+    case 4: rc = launch_step_r<4>(ctx, a, img_bytes, smem); break;
+    default: rc = launch_step_r<8>(ctx, a, img_bytes, smem); break;
+    }
+    if (rc) return rc;
+    if (a.tpo_logits) return launch_k(ctx, ps_k_tp_wait, dim3(1), dim3(32), 0, tp_in(ctx, PS_TP_SLOT_LOGITS)); // every rank's logits rows have landed
+    return 0;
+}
+
 // capture one step into a graph (lazily), then replay it
-int run_step(ps_cuda_ctx *ctx, bool pick) {
+int run_step(ps_cuda_ctx *ctx, bool pick, int n_kv_max) {
+    if (step_usable(ctx)) {
+        const int mode = PS_ST_MODE_LMHEAD | (pick ? PS_ST_MODE_PICK : 0);
+        if (!ctx->opt_ktime) return launch_step(ctx, mode, n_kv_max);
+        // kernel timing pass: CUDA events on the launching stream around every step launch
+        while (ctx->kt_events.size() < ctx->kt_used + 2) {
+            cudaEvent_t e;
+            PS_CK(cudaEventCreate(&e));
+            ctx->kt_events.push_back(e);
+        }
+        PS_CK(cudaEventRecord(ctx->kt_events[ctx->kt_used], ctx->stream));
+        const int rc = launch_step(ctx, mode, n_kv_max);
+        PS_CK(cudaEventRecord(ctx->kt_events[ctx->kt_used + 1], ctx->stream));
+        ctx->kt_used += 2;
+        return rc;
+    }
     if (!ctx->opt_graph || ctx->opt_ktime) return decode_step_fused(ctx, true, pick);
     cudaGraphExec_t &ge = pick ? ctx->g_step : ctx->g_fwd;
     if (!ge) {
@@ -679,8 +803,8 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
     PS_AL(ctx->pos_dev, 4 * B);
     PS_AL(ctx->ids_dev, 4 * 4096);
     PS_AL(ctx->ctr_dev, 16);
-    PS_AL(ctx->err_dev, 16);
-    PS_CKC(cudaMemsetAsync(ctx->err_dev, 0, 16, ctx->stream));
+    PS_AL(ctx->err_dev, 128); // [0..2] flags, [3..] debug record of the step kernel (PS_ST_DEBUG builds)
+    PS_CKC(cudaMemsetAsync(ctx->err_dev, 0, 128, ctx->stream));
     ctx->tc_err_dev = ctx->err_dev;
     ctx->tp_err_dev = ctx->err_dev + 1;
     PS_CKC(cudaMallocHost(&ctx->h_err, 16));
@@ -697,8 +821,13 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         ctx->off_ll[PS_TP_SLOT_X1] = up(ctx->off_ll[PS_TP_SLOT_ATT] + 8 * (size_t)qdim);
         ctx->off_ll[PS_TP_SLOT_H] = up(ctx->off_ll[PS_TP_SLOT_X1] + 8 * (size_t)dim);
         ctx->off_ll[PS_TP_SLOT_X2] = up(ctx->off_ll[PS_TP_SLOT_H] + 8 * (size_t)d.ffn_dim);
-        ctx->heap_bytes = up(ctx->off_ll[PS_TP_SLOT_X2] + 8 * (size_t)dim);
+        // (value, epoch) vectors of the persistent step kernel (ps_step.cuh): x, x1, att, Q8_K image of the FFN hidden vector, best
+        const size_t st_words[5] = {(size_t)dim, (size_t)dim, (size_t)qdim, (size_t)(d.ffn_dim / 256 + 1) * 72, 2 * PS_TP_MAX};
+        ctx->st_off[0] = up(ctx->off_ll[PS_TP_SLOT_X2] + 8 * (size_t)dim);
+        for (int k = 1; k < 5; k++) ctx->st_off[k] = up(ctx->st_off[k - 1] + 8 * st_words[k - 1]);
+        ctx->heap_bytes = up(ctx->st_off[4] + 8 * st_words[4]);
         PS_AL(ctx->heap, ctx->heap_bytes);
+        for (int k = 0; k < 5; k++) ctx->st_ll[k] = reinterpret_cast<unsigned long long *>(ctx->heap + ctx->st_off[k]);
         PS_CKC(cudaMemsetAsync(ctx->heap, 0, ctx->heap_bytes, ctx->stream));
         PS_AL(ctx->epoch_dev, 4 * PS_TP_SLOTS);
         PS_AL(ctx->done_dev, 4 * PS_TP_SLOTS);
@@ -716,7 +845,22 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         PS_AL(ctx->logits_part, 4 * (int64_t)ctx->vocab_l);
     } else {
         ctx->att_full = ctx->att; ctx->h_full = ctx->g; ctx->x_part = ctx->x; ctx->g_part = ctx->g; ctx->logits_part = ctx->logits;
+        const size_t st_words[5] = {(size_t)dim, (size_t)dim, (size_t)qdim, (size_t)(d.ffn_dim / 256 + 1) * 72, 2 * PS_TP_MAX};
+        for (int k = 0; k < 5; k++) {
+            PS_AL(ctx->st_ll[k], 8 * st_words[k]);
+            PS_CKC(cudaMemsetAsync(ctx->st_ll[k], 0, 8 * st_words[k], ctx->stream));
+        }
     }
+    PS_AL(ctx->st_sync, 16);
+    PS_CKC(cudaMemsetAsync(ctx->st_sync, 0, 16, ctx->stream));
+    PS_AL(ctx->st_peers, sizeof(PsStPeers));
+    {   // until ps_cuda_tp_import: only this rank's own copies (a single-GPU context never needs more)
+        PsStPeers pe;
+        memset(&pe, 0, sizeof pe);
+        pe.x[ctx->rank] = ctx->st_ll[0]; pe.x1[ctx->rank] = ctx->st_ll[1]; pe.att[ctx->rank] = ctx->st_ll[2]; pe.hq[ctx->rank] = ctx->st_ll[3]; pe.best[ctx->rank] = ctx->st_ll[4];
+        PS_CKC(cudaMemcpy(ctx->st_peers, &pe, sizeof pe, cudaMemcpyHostToDevice));
+    }
+    { int v = 0; if (cudaDeviceGetAttribute(&v, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess) ctx->smem_optin = v; }
     PS_AL(ctx->ximg, (size_t)B * ((size_t)ctx->maxK + (size_t)(ctx->maxK / 256 + 1) * 32));
     PS_AL(ctx->hq, (size_t)d.ffn_dim + (size_t)(d.ffn_dim / 256 + 1) * 32);
     PS_AL(ctx->blk_cnt, 4 * (size_t)(d.ffn_dim / 256 + 1));
@@ -1118,6 +1262,18 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
         }
         if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(vocab_l, dim, 1)))) return rc;
         if ((rc = rw_repack(ctx, ctx->rw_out, ctx->w_out, vocab_l, dim, 0, 0, 1))) return rc;
+        {   // the persistent step kernel's per-layer table
+            std::vector<PsStLayer> tab(d.n_layers);
+            for (int L = 0; L < d.n_layers; L++) {
+                const LayerDev &ld = ctx->layers[L];
+                tab[L] = PsStLayer{ld.rw_qkv, ld.rw_o, ld.rw_gu, ld.rw_down, ld.attn_norm, ld.ffn_norm, d.qkv_bias ? ld.q_bias : nullptr,
+                                   d.qkv_bias ? ld.k_bias : nullptr, d.qkv_bias ? ld.v_bias : nullptr, ctx->kc[L], ctx->vct[L]};
+            }
+            if (!ctx->st_layers && (rc = dev_alloc(ctx, (void **)&ctx->st_layers, sizeof(PsStLayer) * (size_t)d.n_layers))) return rc;
+            PS_CK(cudaMemcpyAsync(ctx->st_layers, tab.data(), sizeof(PsStLayer) * (size_t)d.n_layers, cudaMemcpyHostToDevice, ctx->stream));
+            PS_CK(cudaStreamSynchronize(ctx->stream)); // `tab` dies at the end of this scope
+            ctx->step_ok = (d.head_size == 64 || d.head_size == 128) && ffn_l % 256 == 0 && d.vocab_size / 8 >= 1 && ctx->smem_optin >= 160 * 1024;
+        }
         PS_CK(cudaStreamSynchronize(ctx->stream));
     }
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
@@ -1275,7 +1431,7 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
         for (int i = 0; i < bs && !rc; i++) {
             PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens + i, 4, cudaMemcpyHostToDevice, ctx->stream));
             PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos + i, 4, cudaMemcpyHostToDevice, ctx->stream));
-            rc = decode_step_fused(ctx, lm_head != 0, false);
+            rc = step_usable(ctx) ? launch_step(ctx, lm_head ? PS_ST_MODE_LMHEAD : 0, pos[i] + 1) : decode_step_fused(ctx, lm_head != 0, false);
             if (!rc && lm_head) {
                 if (!ctx->tp_rows) { int rc2 = dev_alloc(ctx, (void **)&ctx->tp_rows, (size_t)ctx->d.max_batch * ctx->d.vocab_size * 4); if (rc2) return rc2; }
                 PS_CK(cudaMemcpyAsync(ctx->tp_rows + (size_t)i * ctx->d.vocab_size, ctx->logits, (size_t)ctx->d.vocab_size * 4, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -1283,8 +1439,8 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
         }
         if (lm_head) ctx->logits_last = ctx->tp_rows; // the single-token logits slot of the exchange heap holds ONE row: batches are read from tp_rows
     } else if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
-        if (lm_head) rc = run_step(ctx, false);
-        else rc = decode_step_fused(ctx, false, false);
+        if (lm_head) rc = run_step(ctx, false, pos[0] + 1);
+        else rc = step_usable(ctx) ? launch_step(ctx, 0, pos[0] + 1) : decode_step_fused(ctx, false, false);
     } else {
         rc = forward_ops(ctx, bs, lm_head, pos[0]);
     }
@@ -1332,7 +1488,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         ctx->kt_used = 0;
         PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
         for (int s = 0; s < n_steps; s++) {
-            int rc = run_step(ctx, true);
+            int rc = run_step(ctx, true, ctx->position + n_steps);
             if (rc) return rc;
         }
         PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -1438,6 +1594,16 @@ int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n) {
         }
         PS_CK(cudaMemcpy(ctx->tpo_dev, to, sizeof to, cudaMemcpyHostToDevice));
         PS_CK(cudaMemcpy(ctx->tpi_dev, ti, sizeof ti, cudaMemcpyHostToDevice));
+        PsStPeers pe; // the step kernel's exchanged vectors on every rank
+        memset(&pe, 0, sizeof pe);
+        for (int p = 0; p < ctx->tp; p++) {
+            pe.x[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->st_off[0]);
+            pe.x1[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->st_off[1]);
+            pe.att[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->st_off[2]);
+            pe.hq[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->st_off[3]);
+            pe.best[p] = reinterpret_cast<unsigned long long *>(ctx->peer_heap[p] + ctx->st_off[4]);
+        }
+        PS_CK(cudaMemcpy(ctx->st_peers, &pe, sizeof pe, cudaMemcpyHostToDevice));
     }
     ctx->p2p = true;
     if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; }
@@ -1466,6 +1632,8 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         ctx->opt_fused = value;
     }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "attn_chunk")) ctx->opt_attn_chunk = value; // testing: soft-max positions resident in shared memory (multiple of 256)
+    else if (!strcmp(name, "persist")) ctx->opt_persist = value; // 1 (default): the whole decode step as ONE persistent kernel (ps_step.cuh); 0: one kernel per phase
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
     else if (!strcmp(name, "cta_trace")) ctx->opt_cta_trace = value;
@@ -1493,6 +1661,22 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
 int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "kernel_launches")) return ctx->n_launch;
     if (!strcmp(name, "graph_replays")) return ctx->n_graph;
+    if (!strcmp(name, "step_launches")) return ctx->n_step;          // persistent step-kernel launches
+    if (!strcmp(name, "step_ok")) return ctx->step_ok ? 1 : 0;
+    if (!strcmp(name, "step_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the step-kernel launches
+    if (!strcmp(name, "step_kernel_launches")) return ctx->kt_launches;
+    if (!strncmp(name, "step_dbg", 8)) { // PS_ST_DEBUG builds: word k of the step kernel's debug record
+        int v[32] = {};
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(v, ctx->err_dev, 128, cudaMemcpyDeviceToHost);
+        return v[3 + atoi(name + 8)];
+    }
+    if (!strcmp(name, "step_error")) {
+        int v = 0;
+        cudaStreamSynchronize(ctx->stream);
+        cudaMemcpy(&v, ctx->err_dev + 2, 4, cudaMemcpyDeviceToHost);
+        return v | ctx->err_seen[2];
+    }
     if (!strcmp(name, "h2d_bytes")) return ctx->h2d;
     if (!strcmp(name, "d2h_bytes")) return ctx->d2h;
     if (!strcmp(name, "last_device_ns")) return (int64_t)(ctx->last_ms * 1e6);

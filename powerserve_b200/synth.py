@@ -66,6 +66,9 @@ PRESETS: Dict[str, ModelShape] = {
     # the same slices with room for the benchmarked context (2048+) and beyond the shared-memory-resident attention range
     "slice-1b-long": ModelShape("slice-1b-long", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=8192),
     "slice-8b-long": ModelShape("slice-8b-long", "llama", 4096, 14336, 1, 32, 8, 128, 2048, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=8192),
+    # many row octets per CTA (several rounds per compute warp in the persistent step kernel) / many layers
+    "tiny-bigvocab": ModelShape("tiny-bigvocab", "llama", 512, 1536, 2, 8, 2, 64, 40000, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256),
+    "tiny-deep": ModelShape("tiny-deep", "llama", 512, 4096 + 2048, 9, 8, 2, 64, 1024, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256),
     "tiny-mixed": ModelShape("tiny-mixed", "llama", 512, 1024, 2, 8, 4, 64, 768, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256,
                              output_type=GGML_Q6_K),
 }

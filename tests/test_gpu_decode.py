@@ -11,10 +11,12 @@ from tests import _model as M
 pytestmark = pytest.mark.gpu
 
 
-def run(cm, prompt, n_dec, fused, graph, pdl=1):
+def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0):
     cm.be.set_option("fused", fused)
     cm.be.set_option("graph", graph)
     cm.be.set_option("pdl", pdl)
+    cm.be.set_option("persist", persist)     # 1 = the whole step as ONE persistent kernel (ps_step.cuh)
+    cm.be.set_option("attn_chunk", attn_chunk)
     return cm.generate(prompt, n_dec, batch_size=16)
 
 
@@ -38,6 +40,15 @@ def test_fused_equals_table_ops_and_oracle(preset):
     ids_d = list(cm.decode_greedy(int(prompt[-1]), n_dec))
     assert ids_d == ids_u
     assert cm.be.counter("graph_replays") >= n_dec
+    # the persistent step kernel: host-driven steps (logits) and the device-resident loop
+    assert cm.be.counter("step_ok") == 1
+    n0 = cm.be.counter("step_launches")
+    ids_s, lg_s = run(cm, prompt, n_dec, fused=1, graph=1, persist=1)
+    L.assert_bit_equal(lg_s, lg_u, f"{preset}: persistent step kernel vs table ops")
+    assert ids_s == ids_u and cm.be.counter("step_launches") >= n0 + n_dec
+    cm.reset(); cm.prefill(prompt, 16)
+    assert list(cm.decode_greedy(int(prompt[-1]), n_dec)) == ids_u
+    assert cm.be.counter("step_error") == 0
     cm.close()
     om = M.OracleModel(d)
     ids_o, lg_o = om.generate(prompt, n_dec, batch_size=16)
@@ -55,4 +66,20 @@ def test_fused_long_context_matches_table_ops():
     ids_g, lg_g = run(cm, prompt, 40, fused=1, graph=1)
     L.assert_bit_equal(lg_g, lg_u, "long context")
     assert ids_g == ids_u
+    ids_s, lg_s = run(cm, prompt, 40, fused=1, graph=1, persist=1)
+    L.assert_bit_equal(lg_s, lg_u, "long context, persistent step kernel")
+    assert ids_s == ids_u
+    cm.close()
+
+
+def test_step_kernel_chunked_attention():
+    """soft-max rows longer than the shared-memory-resident chunk (forced down to 256 positions): the three-pass path of
+    the persistent kernel's attention phase, n_kv crossing chunk, 32- and 8-element boundaries."""
+    d = M.model_dir("tiny-llama")
+    prompt = synth.random_prompt(1024, 250, seed=9)
+    cm = capi.CudaModel(d, max_batch=64)
+    ids_u, lg_u = run(cm, prompt, 24, fused=0, graph=0)
+    ids_s, lg_s = run(cm, prompt, 24, fused=1, graph=1, persist=1, attn_chunk=256)
+    L.assert_bit_equal(lg_s, lg_u, "chunked attention")
+    assert ids_s == ids_u and cm.be.counter("step_error") == 0
     cm.close()
