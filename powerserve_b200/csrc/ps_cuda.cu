@@ -147,7 +147,8 @@ struct ps_cuda_ctx {
     int *part_idx = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
     // persistent per-step kernel (ps_step.cuh)
-    int opt_persist = 1;
+    int opt_persist = 0;            // 1: the whole decode step as ONE persistent kernel (ps_step.cuh); bit-exact and tested, but 2x slower than the per-phase kernels so far
+    int opt_l2_ahead = 96;          // stages (4736 B) per CTA the L2 look-ahead warp stays ahead of the shared-memory rings (0 = off)
     int opt_attn_chunk = 0;         // testing: cap on the soft-max positions resident in shared memory (forces the chunked attention path)
     bool step_ok = false;           // the model / geometry qualifies for ps_k_step
     PsStLayer *st_layers = nullptr; // device table
@@ -639,6 +640,7 @@ int launch_step(ps_cuda_ctx *ctx, int mode, int n_kv_max) {
     auto kb_of = [](int nb, int cap) { int kb = cap; while (nb % kb) kb >>= 1; return kb; };
     a.kb_dim = kb_of(a.dim / 256, 4); a.kb_gu = kb_of(a.dim / 256, 2); a.kb_q = kb_of(a.qdim / 256, 4); a.kb_ffn = kb_of(a.ffn / 256, 4);
     a.mode = mode;
+    a.l2_ahead = ctx->opt_l2_ahead;
     a.timeout_ns = ctx->tp > 1 ? 30000000000LL : 2000000000LL;
     a.tl = ctx->trace_dev;
     // P.V work split: halve the dims per CTA while fewer than half of the SMs would have an item
@@ -1632,8 +1634,9 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         ctx->opt_fused = value;
     }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "l2_ahead")) ctx->opt_l2_ahead = value;     // tuning: L2 look-ahead of the step kernel's weight stream, in 4736-byte stages per CTA
     else if (!strcmp(name, "attn_chunk")) ctx->opt_attn_chunk = value; // testing: soft-max positions resident in shared memory (multiple of 256)
-    else if (!strcmp(name, "persist")) ctx->opt_persist = value; // 1 (default): the whole decode step as ONE persistent kernel (ps_step.cuh); 0: one kernel per phase
+    else if (!strcmp(name, "persist")) ctx->opt_persist = value; // 1: the whole decode step as ONE persistent kernel (ps_step.cuh); 0 (default): one kernel per phase
     else if (!strcmp(name, "ktime")) ctx->opt_ktime = value;
     else if (!strcmp(name, "tc")) ctx->opt_tc = value;
     else if (!strcmp(name, "cta_trace")) ctx->opt_cta_trace = value;

@@ -22,10 +22,10 @@
 #include "ps_rw.cuh"
 
 #define PS_ST_WARPS 16                      // compute warps
-#define PS_ST_PROD 2                        // producer warps; producer p feeds the compute warps w with w % PS_ST_PROD == p
+#define PS_ST_PROD 4                        // producer warps; producer p feeds the compute warps w with w % PS_ST_PROD == p
 #define PS_ST_WPP (PS_ST_WARPS / PS_ST_PROD)
 #define PS_ST_CT (PS_ST_WARPS * 32)         // compute threads
-#define PS_ST_THREADS ((PS_ST_WARPS + PS_ST_PROD) * 32)
+#define PS_ST_THREADS ((PS_ST_WARPS + PS_ST_PROD) * 32)      // 20 warps: one more would cost 16 registers per thread (warp allocation granularity)
 #define PS_ST_SLOT 4736                     // ring slot: four 1184-byte octet blocks
 #ifndef PS_ST_DEBUG
 #define PS_ST_DEBUG 0
@@ -81,21 +81,27 @@ struct PsStCtl {
     long long timeout_ns;
     volatile uint32_t *dbg_rel; // PS_ST_DEBUG: [slot] index of the stage whose consumer last released the slot, [nsp + slot] that warp
 };
-#define PS_ST_SPIN_UNTIL(ctl, cond, site)                                                                   \
+// every 256 failed attempts: has anybody given up, or is it time to give up?  Out of line on purpose: the step kernel is one
+// large body of code shared by twenty warps in different phases, and its instruction-cache footprint is a first-order cost.
+__device__ __noinline__ bool ps_st_spin_check(int *abort, int *err, long long timeout_ns, long long *t0, int site) {
+    if (*reinterpret_cast<volatile int *>(abort)) return true;
+    const long long now = ps_globaltimer();
+    if (!*t0) *t0 = now;
+    else if (now - *t0 > timeout_ns) {
+        *reinterpret_cast<volatile int *>(abort) = 1;
+        *reinterpret_cast<volatile int *>(err) = site;
+        return true;
+    }
+    return false;
+}
+#define PS_ST_SPIN_UNTIL(ctl, cond, site) PS_ST_SPIN_UNTIL_S(ctl, cond, site, 0)
+#define PS_ST_SPIN_UNTIL_S(ctl, cond, site, sleep_ns)                                                 \
     do {                                                                                              \
         long long t0_ = 0;                                                                            \
         uint32_t it_ = 0;                                                                             \
         while (!(cond)) {                                                                             \
-            if ((++it_ & 255u) == 0) {                                                                \
-                if (*reinterpret_cast<volatile int *>((ctl).abort)) break;                            \
-                const long long now_ = ps_globaltimer();                                              \
-                if (!t0_) t0_ = now_;                                                                 \
-                else if (now_ - t0_ > (ctl).timeout_ns) {                                             \
-                    *reinterpret_cast<volatile int *>((ctl).abort) = 1;                               \
-                    *reinterpret_cast<volatile int *>((ctl).err) = (site);                            \
-                    break;                                                                            \
-                }                                                                                     \
-            }                                                                                         \
+            if ((sleep_ns) > 0) __nanosleep(sleep_ns); /* polls back off: spinning warps take issue slots and L2 bandwidth */ \
+            if ((++it_ & 255u) == 0 && ps_st_spin_check((ctl).abort, (ctl).err, (ctl).timeout_ns, &t0_, (site))) break; \
         }                                                                                             \
     } while (0)
 
@@ -110,7 +116,20 @@ PS_D bool ps_st_mbar_try(uint64_t *bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+PS_D bool ps_st_mbar_test(uint64_t *bar, uint32_t parity) { // non-blocking
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(ps_smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 PS_D void ps_st_mbar_wait(const PsStCtl &ctl, uint64_t *bar, uint32_t parity, int site) { PS_ST_SPIN_UNTIL(ctl, ps_st_mbar_try(bar, parity), site); }
+// the same with a back-off between attempts: producer warps wait for a slot far more often than not, and must not take issue slots from the compute warps
+PS_D void ps_st_mbar_wait_idle(const PsStCtl &ctl, uint64_t *bar, uint32_t parity, int site) { PS_ST_SPIN_UNTIL_S(ctl, ps_st_mbar_try(bar, parity), site, 64); }
 
 PS_D unsigned ps_st_ld_acquire_gpu(const unsigned *p) {
     unsigned v;
@@ -125,7 +144,7 @@ PS_D void ps_st_grid_barrier(const PsStCtl &ctl, unsigned *ctr, unsigned target)
     if (threadIdx.x == 0) {
         __threadfence();
         asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(ctr) : "memory");
-        PS_ST_SPIN_UNTIL(ctl, ps_st_ld_acquire_gpu(ctr) >= target, 1);
+        PS_ST_SPIN_UNTIL_S(ctl, ps_st_ld_acquire_gpu(ctr) >= target, 1, 20);
         __threadfence();
     }
     ps_bar_sync(2, PS_ST_CT);
@@ -149,12 +168,19 @@ PS_D bool ps_st_ll_load2(const unsigned long long *p, uint32_t ep, uint32_t &b0,
     b1 = (uint32_t)b;
     return (uint32_t)(a >> 32) == ep && (uint32_t)(b >> 32) == ep;
 }
-// eight elements of a 256-block (4*lane .. +3, 128 + 4*lane .. +3), polled until they carry epoch `ep`
+// eight elements of a 256-block (4*lane .. +3, 128 + 4*lane .. +3), polled until they carry epoch `ep`.  While the block
+// is not there yet only ONE lane polls ONE 16-byte pair (with a back-off): 2000 warps re-reading their 2 KB every 100 ns
+// saturated the L2 (10 TB/s of poll traffic) and slowed every other memory access of the step several-fold.
 PS_D void ps_st_load8_ll(const PsStCtl &ctl, const unsigned long long *p, int lane, float e[8], uint32_t ep) {
     const unsigned long long *p0 = p + 4 * lane, *p1 = p + 128 + 4 * lane;
     uint32_t b[8];
-    PS_ST_SPIN_UNTIL(ctl, (ps_st_ll_load2(p0, ep, b[0], b[1]) & ps_st_ll_load2(p0 + 2, ep, b[2], b[3]) & ps_st_ll_load2(p1, ep, b[4], b[5]) &
-                           ps_st_ll_load2(p1 + 2, ep, b[6], b[7])), 2);
+    if (lane == 0) {
+        uint32_t t0, t1;
+        PS_ST_SPIN_UNTIL_S(ctl, ps_st_ll_load2(p + 254, ep, t0, t1), 2, 100); // the block's last pair
+    }
+    __syncwarp();
+    PS_ST_SPIN_UNTIL_S(ctl, __all_sync(PS_FULL, ps_st_ll_load2(p0, ep, b[0], b[1]) & ps_st_ll_load2(p0 + 2, ep, b[2], b[3]) & ps_st_ll_load2(p1, ep, b[4], b[5]) &
+                                               ps_st_ll_load2(p1 + 2, ep, b[6], b[7])), 2, 200);
 #pragma unroll
     for (int t = 0; t < 8; t++) e[t] = __uint_as_float(b[t]);
 }
@@ -196,7 +222,10 @@ PS_D void ps_st_produce(const PsStCtl &ctl, const PsStMv mv, int p, int lane, ui
         for (int sb = 0; sb < spo; sb++) {
             const uint8_t *src = mv.w + (size_t)(o0 + m0 + p) * oct_bytes + (size_t)sb * stage_bytes;
             for (int w = p; w < n_m; w += PS_ST_PROD, src += oct_bytes * PS_ST_PROD) {
-                ps_st_mbar_wait(ctl, empty + slot, par ^ 1, 4);
+                // ONE lane polls, without parking in the barrier unit (threads parked in try_wait slowed every shared-memory
+                // operation of the compute warps several-fold), the others wait at the warp barrier
+                if (lane == 0) PS_ST_SPIN_UNTIL_S(ctl, ps_st_mbar_test(empty + slot, par ^ 1), 4, 100);
+                __syncwarp();
                 if (*reinterpret_cast<volatile int *>(ctl.abort)) return; // a wait gave up somewhere: stop feeding (an un-waited expect_tx would over-arrive and trap)
 #if PS_ST_DEBUG
                 if (lane == 0 && issued >= (uint32_t)nsp && !ps_st_mbar_try(full + slot, par ^ 1)) { // the slot's previous round has not even landed, yet its empty barrier let us through
@@ -224,48 +253,86 @@ PS_D void ps_st_produce(const PsStCtl &ctl, const PsStMv mv, int p, int lane, ui
 
 // compute side: walk this warp's octets of the phase; `epi(oct_index_in_matrix, acc[])` consumes a finished octet.
 // `base` = stages this warp's producer has issued before the phase (advanced here).
-template <int RPT, class Epi>
-PS_D void ps_st_walk(const PsStCtl &ctl, const PsStMv mv, uint32_t &base, const volatile uint32_t *s_issued, int nsp, uint8_t *ring, uint64_t *full,
-                     uint64_t *empty, const uint4 *s_qa, const uint2 *s_meta, int warp, int lane, Epi epi) {
+struct PsStNoIdle {
+    PS_D void operator()(int, int) const {}
+};
+struct PsStRing { // one compute warp's view of its producer's ring
+    const volatile uint32_t *s_issued;
+    uint8_t *ring;
+    uint64_t *full, *empty;
+    const uint4 *s_qa;
+    const uint2 *s_meta;
+    int nsp;
+};
+// all stages of ONE row octet (stage indices g, g + n_lw, ...), out of line: one copy of the block loop per RPT in the
+// whole kernel.  Returns the cycles spent waiting for weight stages (trace only).
+template <int RPT>
+__device__ __noinline__ long long ps_st_octet(int *abort, int *err, long long timeout_ns, const PsStRing rg, uint32_t g, int n_lw, int spo, int kb, int lane, bool timed,
+                                              PsRwAcc *out) {
+    const PsStCtl ctl{abort, err, timeout_ns, nullptr};
+    const int r = lane >> 2, q = lane & 3, moff = ps_rw_mins_off(r, q);
+    uint32_t slot = g % (uint32_t)rg.nsp, par = (g / (uint32_t)rg.nsp) & 1;
+    long long wcyc = 0;
+    PsRwAcc acc[RPT];
+#pragma unroll
+    for (int t = 0; t < RPT; t++) acc[t].a0 = acc[t].a1 = acc[t].am = 0.f;
+#pragma unroll 1
+    for (int sb = 0; sb < spo; sb++) {
+        const long long c0_ = timed ? clock64() : 0;
+        // A parity wait is only unambiguous once the stage has been ISSUED (a warp may run more than a ring revolution ahead
+        // of the slowest one): first the producer's issue count, then the barrier.  One lane polls, the warp reconverges.
+        if (lane == 0) {
+            PS_ST_SPIN_UNTIL_S(ctl, *rg.s_issued > g, 5, 32);
+            PS_ST_SPIN_UNTIL_S(ctl, ps_st_mbar_test(rg.full + slot, par), 6, 20);
+        }
+        __syncwarp(); // lane 0 observed the phase completion (acquire); the warp barrier orders the other lanes' reads after it
+        if (timed) wcyc += clock64() - c0_;
+        const uint8_t *st = rg.ring + (size_t)slot * PS_ST_SLOT;
+#pragma unroll 1
+        for (int b = 0; b < kb; b++) {
+            const int i = sb * kb + b;
+            const uint4 *qa = rg.s_qa + (size_t)i * 16;
+            const uint2 meta = rg.s_meta[i * 4 + q];
+#pragma unroll
+            for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, moff, qa, meta, acc[t]);
+        }
+        __syncwarp();
+        if (lane == 0) ps_mbar_arrive(rg.empty + slot);
+        g += n_lw;
+        slot += n_lw;
+        if (slot >= (uint32_t)rg.nsp) { slot -= rg.nsp; par ^= 1; }
+    }
+#pragma unroll
+    for (int t = 0; t < RPT; t++) out[t] = acc[t];
+    return wcyc;
+}
+
+// compute side: walk this warp's octets of the phase; `epi(oct_index_in_matrix, acc[])` consumes a finished octet;
+// `idle(k, n)` runs on the warps that own no octet of this phase (k = 0 .. n-1).
+// `base` = stages this warp's producer has issued before the phase (advanced here).
+template <int RPT, class Epi, class Idle = PsStNoIdle>
+PS_D void ps_st_walk(const PsStCtl &ctl, const PsStMv mv, uint32_t &base, const PsStRing &rg, int warp, int lane, Epi epi, Idle idle = Idle(), long long *tl = nullptr) {
     const int G = gridDim.x, bid = blockIdx.x;
     const int o0 = (int)(((long long)bid * mv.n_oct) / G), o1 = (int)(((long long)(bid + 1) * mv.n_oct) / G);
-    const int n_mine = o1 - o0, spo = mv.nb / mv.kb, kb = mv.kb;
+    const int n_mine = o1 - o0, spo = mv.nb / mv.kb;
     const int p = warp % PS_ST_PROD, lw = warp / PS_ST_PROD;
-    const int r = lane >> 2, q = lane & 3, moff = ps_rw_mins_off(r, q);
+    if (warp >= n_mine) idle(warp - n_mine, PS_ST_WARPS - n_mine);
+    long long wcyc = 0, ecyc = 0;
+    const long long c_begin = tl ? clock64() : 0;
 #pragma unroll 1
     for (int m0 = 0, m = 0; m0 + warp < n_mine; m0 += PS_ST_WARPS, m++) {
         const int n_m = min(PS_ST_WARPS, n_mine - m0);
         const int n_lw = (n_m - p + PS_ST_PROD - 1) / PS_ST_PROD; // warps of my producer active in this round
-        uint32_t g = base + (uint32_t)m * spo * PS_ST_WPP + lw;
-        uint32_t slot = g % (uint32_t)nsp, par = (g / (uint32_t)nsp) & 1;
         PsRwAcc acc[RPT];
-#pragma unroll
-        for (int t = 0; t < RPT; t++) acc[t].a0 = acc[t].a1 = acc[t].am = 0.f;
-#pragma unroll 1
-        for (int sb = 0; sb < spo; sb++) {
-            // A parity wait is only unambiguous once the stage has been ISSUED (a warp may run more than a ring revolution ahead
-            // of the slowest one, and bulk copies may land out of order): first the producer's issue count, then the barrier.
-            PS_ST_SPIN_UNTIL(ctl, *s_issued > g, 5);
-            ps_st_mbar_wait(ctl, full + slot, par, 6);
-            const uint8_t *st = ring + (size_t)slot * PS_ST_SLOT;
-#pragma unroll 1
-            for (int b = 0; b < kb; b++) {
-                const int i = sb * kb + b;
-                const uint4 *qa = s_qa + (size_t)i * 16;
-                const uint2 meta = s_meta[i * 4 + q];
-#pragma unroll
-                for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, moff, qa, meta, acc[t]);
-            }
-            __syncwarp();
-#if PS_ST_DEBUG
-            if (lane == 0) { ctl.dbg_rel[slot] = g; ctl.dbg_rel[nsp + slot] = (uint32_t)warp; }
-#endif
-            if (lane == 0) ps_mbar_arrive(empty + slot);
-            g += n_lw;
-            slot += n_lw;
-            if (slot >= (uint32_t)nsp) { slot -= nsp; par ^= 1; }
-        }
+        wcyc += ps_st_octet<RPT>(ctl.abort, ctl.err, ctl.timeout_ns, rg, base + (uint32_t)m * spo * PS_ST_WPP + lw, n_lw, spo, mv.kb, lane, tl != nullptr, acc);
+        const long long ce_ = tl ? clock64() : 0;
         epi(o0 + m0 + warp, acc);
+        if (tl) ecyc += clock64() - ce_;
+    }
+    if (tl && lane == 0 && warp < n_mine) { // trace: slowest warp's walk, the most any warp waited for weight stages / spent in epilogues (cycles)
+        atomicMax(reinterpret_cast<unsigned long long *>(tl + 5), (unsigned long long)(clock64() - c_begin));
+        atomicMax(reinterpret_cast<unsigned long long *>(tl + 6), (unsigned long long)wcyc);
+        atomicMax(reinterpret_cast<unsigned long long *>(tl + 7), (unsigned long long)ecyc);
     }
     base += (uint32_t)ps_st_cnt(n_mine, p) * spo;
 }
@@ -273,7 +340,7 @@ PS_D void ps_st_walk(const PsStCtl &ctl, const PsStMv mv, uint32_t &base, const 
 // ---------------------------------------------------------------------------------------------------- prologues
 // Q8_K image of an exchanged fp32 vector (K elements as (value, epoch) words), optionally through RMSNorm
 // (ggml.c:12667-12721 + ggml-quants.c:3799-3837): one warp per 256-block, exactly the prologue of ps_k_rw_matvec.
-PS_D void ps_st_prologue_vec(const PsStCtl &ctl, const unsigned long long *v_ll, uint32_t ep, int K, const float *norm_w, float eps, uint4 *s_qa, uint2 *s_meta,
+__device__ __noinline__ void ps_st_prologue_vec(const PsStCtl &ctl, const unsigned long long *v_ll, uint32_t ep, int K, const float *norm_w, float eps, uint4 *s_qa, uint2 *s_meta,
                              double *sh_red, int warp, int lane, long long *tl) {
     const int nb = K / 256;
     const double inv_k = (K & (K - 1)) == 0 ? 1.0 / (double)K : 0.0;
@@ -333,13 +400,19 @@ PS_D void ps_st_prologue_vec(const PsStCtl &ctl, const unsigned long long *v_ll,
 }
 
 // the Q8_K image the gate|up epilogue produced (words [nb x 64 quants][nb x 8 meta] as (value, epoch) pairs) -> shared memory
-PS_D void ps_st_prologue_img(const PsStCtl &ctl, const unsigned long long *img_ll, uint32_t ep, int K, uint32_t *s_img, int tid, long long *tl) {
+__device__ __noinline__ void ps_st_prologue_img(const PsStCtl &ctl, const unsigned long long *img_ll, uint32_t ep, int K, uint32_t *s_img, int tid, long long *tl) {
     const int n_pairs = (K / 256) * 36;
     ps_bar_sync(2, PS_ST_CT); // everybody is done with the previous phase's image
-    for (int t = tid; t < n_pairs; t += PS_ST_CT) {
+    for (int t0 = (tid & ~31); t0 < n_pairs; t0 += PS_ST_CT) { // warp-uniform trip count
+        const int t = t0 + (tid & 31);
+        if ((tid & 31) == 0) { // while the words are not there only one lane polls one pair (see ps_st_load8_ll)
+            uint32_t u0, u1;
+            PS_ST_SPIN_UNTIL_S(ctl, ps_st_ll_load2(img_ll + 2 * min(t0 + 31, n_pairs - 1), ep, u0, u1), 3, 100);
+        }
+        __syncwarp();
         uint32_t b0 = 0, b1 = 0;
-        PS_ST_SPIN_UNTIL(ctl, ps_st_ll_load2(img_ll + 2 * t, ep, b0, b1), 3);
-        *reinterpret_cast<uint2 *>(s_img + 2 * t) = make_uint2(b0, b1);
+        PS_ST_SPIN_UNTIL_S(ctl, __all_sync(PS_FULL, t >= n_pairs || ps_st_ll_load2(img_ll + 2 * t, ep, b0, b1)), 3, 200);
+        if (t < n_pairs) *reinterpret_cast<uint2 *>(s_img + 2 * t) = make_uint2(b0, b1);
     }
     if (tl && threadIdx.x == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + 3), (unsigned long long)ps_globaltimer());
     ps_bar_sync(2, PS_ST_CT);
@@ -394,7 +467,12 @@ __device__ __noinline__ void ps_st_scores(const float *__restrict__ kc, const fl
 // scores and the exponentials are recomputed chunk by chunk - the FMA chains of the P.V product stay in position order).
 template <int R2>
 __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, const float *__restrict__ vct, int n_kv, float *s_p, double *shd, float *shf,
-                                      uint32_t ep, int tid) {
+                                      uint32_t ep, int tid, long long *tl) {
+    const long long t_in = tl ? ps_globaltimer() : 0;
+#define PS_PV_PROBE(k)                                                                                                     \
+    do {                                                                                                                   \
+        if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_in)); \
+    } while (0)
     const int warp = tid >> 5, lane = tid & 31;
     const int hs = a.hs, dpc = a.dpc, CH = a.attn_chunk;
     const int n_items = a.nkv_l * (hs / dpc);
@@ -409,12 +487,33 @@ __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, con
         const int g = it / (hs / dpc), d = (it % (hs / dpc)) * dpc + dd;
         const float *srow = a.sc + (size_t)(g * R2 + hh) * a.n_ctx;
         float *pp = s_p + (size_t)hh * CH;
+        // the V^T row of this warp: 16 loads per lane in flight before the soft-max is rebuilt (they do not depend on it)
+        const float *vrow = vct + ((size_t)g * hs + d) * a.n_ctx;
+        const bool pv_warp = h_lo < R2;
+        const int ntail = n_kv - np;
+        auto load_v = [&](float (&v)[16], int s0, int c_end) {
+#pragma unroll
+            for (int u = 0; u < 16; u++) v[u] = (s0 + 32 * u < c_end) ? __ldcs(vrow + s0 + 32 * u + lane) : 0.f;
+        };
+        float cur[16];
+        if (pv_warp) load_v(cur, 0, min(min(CH, n_kv), np));
+        const float vtail = (pv_warp && lane < ntail) ? __ldcs(vrow + np + lane) : 0.f;
         // ---- pass 1: row maximum (a single chunk also lands in shared memory)
         float mx = -INFINITY;
-        for (int j = ht; j < n_kv; j += TPH) {
-            const float v = __ldcg(srow + j);
-            if (n_chunks == 1) pp[j] = v;
-            mx = fmaxf(mx, v);
+        {   // rows are 16-byte aligned (n_ctx % 4 == 0): four scores per load, several loads in flight
+            const int n4 = n_kv >> 2;
+#pragma unroll 4
+            for (int j4 = ht; j4 < n4; j4 += TPH) {
+                const float4 v = __ldcg(reinterpret_cast<const float4 *>(srow) + j4);
+                if (n_chunks == 1) reinterpret_cast<float4 *>(pp)[j4] = v;
+                mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+            }
+            const int j = (n4 << 2) + ht;
+            if (j < n_kv) {
+                const float v = __ldcg(srow + j);
+                if (n_chunks == 1) pp[j] = v;
+                mx = fmaxf(mx, v);
+            }
         }
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
@@ -423,15 +522,22 @@ __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, con
         mx = shf[hh * WPH];
 #pragma unroll
         for (int t = 1; t < WPH; t++) mx = fmaxf(mx, shf[hh * WPH + t]);
+        PS_PV_PROBE(3);
         // exponentials of chunk c into shared memory (ggml_v_expf on full 8-groups of the ROW, libm expf on its tail); returns this thread's partial sum
         auto exp_chunk = [&](int c0, int cn, bool load) -> double {
-            if (load) {
-                for (int j = ht; j < cn; j += TPH) pp[j] = __ldcg(srow + c0 + j);
+            if (load) { // c0 % 4 == 0
+                const int n4 = cn >> 2;
+#pragma unroll 4
+                for (int j4 = ht; j4 < n4; j4 += TPH) reinterpret_cast<float4 *>(pp)[j4] = __ldcg(reinterpret_cast<const float4 *>(srow + c0) + j4);
+                const int j = (n4 << 2) + ht;
+                if (j < cn) pp[j] = __ldcg(srow + c0 + j);
                 ps_bar_sync(2, PS_ST_CT);
             }
             double s = 0.0;
             const int g_end = (min(c0 + cn, n8) - c0) >> 3; // full 8-groups of this chunk (c0 % 8 == 0)
+            int it_no = 0;
             for (int gi = ht; gi < g_end; gi += TPH) {
+                const long long cc0 = tl ? clock64() : 0;
                 float4 *p4 = reinterpret_cast<float4 *>(pp + gi * 8);
                 const float4 xa = p4[0], xb = p4[1];
                 float vv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -441,6 +547,8 @@ __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, con
                 p4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
                 const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
                 s += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
+                if (tl && (tid & 31) == 0 && it_no < 2) atomicMax(reinterpret_cast<unsigned long long *>(tl + 6 + it_no), (unsigned long long)(clock64() - cc0)); // trace: 1st / 2nd trip through the same code
+                it_no++;
             }
             for (int j = max(n8 - c0, 0) + ht; j < cn; j += TPH) { // scalar tail of the row: libm expf
                 const float vv = ps_expf_glibc(__fadd_rn(pp[j], -mx));
@@ -464,14 +572,11 @@ __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, con
 #pragma unroll
         for (int t = 1; t < WPH; t++) sum += shd[hh * WPH + t];
         const float inv = (float)(1.0 / sum);
-        // ---- pass 3: P.V
+        PS_PV_PROBE(4);
+        // ---- pass 3: P.V  (the first 16 V loads of the row were issued before the soft-max; batches are double-buffered in registers)
         float acc[R2];
 #pragma unroll
         for (int h2 = 0; h2 < R2; h2++) acc[h2] = 0.f;
-        const float *vrow = vct + ((size_t)g * hs + d) * a.n_ctx;
-        const bool pv_warp = h_lo < R2;
-        const int ntail = n_kv - np;
-        const float vtail = (pv_warp && lane < ntail) ? __ldcs(vrow + np + lane) : 0.f;
         int c0_last = 0;
         for (int c = 0; c < n_chunks; c++) {
             const int c0 = c * CH, cn = min(CH, n_kv - c0);
@@ -485,20 +590,23 @@ __device__ __noinline__ void ps_st_pv(const PsStCtl &ctl, const PsStArgs &a, con
             ps_bar_sync(2, PS_ST_CT);
             if (pv_warp) {
                 const int c_end = min(c0 + cn, np);
-                for (int s0 = c0; s0 < c_end; s0 += 512) { // 16 independent V loads in flight per lane; the chains stay in position order
-                    float vv[16];
-#pragma unroll
-                    for (int u = 0; u < 16; u++) vv[u] = (s0 + 32 * u < c_end) ? __ldcs(vrow + s0 + 32 * u + lane) : 0.f;
+                if (c > 0) load_v(cur, c0, c_end);
+                for (int s0 = c0; s0 < c_end; s0 += 512) { // the FMA chains stay in position order
+                    float nxt[16];
+                    if (s0 + 512 < c_end) load_v(nxt, s0 + 512, c_end);
 #pragma unroll
                     for (int u = 0; u < 16; u++)
                         if (s0 + 32 * u < c_end) {
 #pragma unroll
                             for (int h2 = 0; h2 < R2; h2++)
-                                if (h2 < hpw && h_lo + h2 < R2) acc[h2] = __fmaf_rn(vv[u], s_p[(size_t)(h_lo + h2) * CH + (s0 - c0) + 32 * u + lane], acc[h2]);
+                                if (h2 < hpw && h_lo + h2 < R2) acc[h2] = __fmaf_rn(cur[u], s_p[(size_t)(h_lo + h2) * CH + (s0 - c0) + 32 * u + lane], acc[h2]);
                         }
+#pragma unroll
+                    for (int u = 0; u < 16; u++) cur[u] = nxt[u];
                 }
             }
         }
+        PS_PV_PROBE(5);
         if (pv_warp) {
             ps_f32x8_reduce_n<R2>(acc);
             for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order (every lane computes the same chain)
@@ -525,6 +633,18 @@ template <int R2> PS_D void ps_st_scores_dispatch(const PsStArgs &a, const float
     else ps_st_scores<R2, 4>(kc, a.q, a.sc, n_kv, a.nkv_l, a.n_ctx, a.kq_scale, warp, lane);
 }
 
+// pull the first n_kv positions of a layer's K cache and transposed V cache into L2 (126 MB) ahead of its attention phases:
+// thread `t` of `n_t` chip-wide takes every n_t-th 128-byte line
+PS_D void ps_st_prefetch_kv(const float *kc, const float *vct, int n_kv, int kvd, int n_ctx, int t, int n_t) {
+    const int k_lines = (int)(((size_t)n_kv * kvd * 4 + 127) >> 7);
+    for (int i = t; i < k_lines; i += n_t) asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(kc) + ((size_t)i << 7)));
+    const int row_lines = (n_kv * 4 + 127) >> 7, v_lines = kvd * row_lines;
+    for (int i = t; i < v_lines; i += n_t) {
+        const int row = i / row_lines, l = i - row * row_lines;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(reinterpret_cast<const char *>(vct + (size_t)row * n_ctx) + ((size_t)l << 7)));
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------- timeline
 PS_D void ps_st_tl_enter(long long *tl) {
     if (tl && threadIdx.x == 0) atomicMin(reinterpret_cast<unsigned long long *>(tl), (unsigned long long)ps_globaltimer());
@@ -536,7 +656,7 @@ PS_D void ps_st_tl_exit(long long *tl) {
 // ---------------------------------------------------------------------------------------------------- the kernel
 // Dynamic shared memory: [image / soft-max scratch: img_bytes][rings: PS_ST_PROD x nsp x 4736][full / empty barriers]
 template <int R2>
-__global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, const int img_bytes) {
+__global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const __grid_constant__ PsStArgs a, const int img_bytes) {
     extern __shared__ __align__(128) uint8_t ps_st_smem[];
     __shared__ double sh_red[PS_ST_WARPS];
     __shared__ float sh_f[PS_ST_WARPS];
@@ -578,14 +698,18 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
 #if PS_ST_DEBUG
         ctl.dbg_rel = s_dbg_rel[p];
 #endif
-        for (int L = 0; L < n_layers; L++) {
-            const PsStLayer &ly = a.layers[L];
-            ps_st_produce(ctl, PsStMv{ly.w_qkv, n_qkv / 8, dim / 256, a.kb_dim, 1}, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
-            ps_st_produce(ctl, PsStMv{ly.w_o, dim / 8 / a.tp, a.qdim / 256, a.kb_q, 1}, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
-            ps_st_produce(ctl, PsStMv{ly.w_gu, (a.ffn_l + 7) / 8, dim / 256, a.kb_gu, 2}, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
-            ps_st_produce(ctl, PsStMv{ly.w_down, dim / 8 / a.tp, a.ffn / 256, a.kb_ffn, 1}, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
+        const int n_phases = 4 * n_layers + (lm_head ? 1 : 0);
+#pragma unroll 1
+        for (int k = 0; k < n_phases; k++) { // the phases in execution order: (q|k|v, o, gate|up, down) per layer, lm_head
+            const int L = k >> 2, t = k & 3;
+            PsStMv mv;
+            if (L == n_layers) mv = PsStMv{a.w_out, (a.vocab_l + 7) / 8, dim / 256, a.kb_dim, 1};
+            else if (t == 0) mv = PsStMv{a.layers[L].w_qkv, n_qkv / 8, dim / 256, a.kb_dim, 1};
+            else if (t == 1) mv = PsStMv{a.layers[L].w_o, dim / 8 / a.tp, a.qdim / 256, a.kb_q, 1};
+            else if (t == 2) mv = PsStMv{a.layers[L].w_gu, (a.ffn_l + 7) / 8, dim / 256, a.kb_gu, 2};
+            else mv = PsStMv{a.layers[L].w_down, dim / 8 / a.tp, a.ffn / 256, a.kb_ffn, 1};
+            ps_st_produce(ctl, mv, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
         }
-        if (lm_head) ps_st_produce(ctl, PsStMv{a.w_out, (a.vocab_l + 7) / 8, dim / 256, a.kb_dim, 1}, p, lane, slot, par, issued, iss, nsp, ring, full, empty);
         return;
     }
 
@@ -643,7 +767,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         long long *t_ = PS_ST_TL(1 + 6 * L);
         ps_st_tl_enter(t_);
         ps_st_prologue_vec(ctl, a.x_ll, ep, dim, ly.attn_norm, a.eps, s_qa, s_meta, sh_red, warp, lane, t_);
-        ps_st_walk<1>(ctl, PsStMv{ly.w_qkv, n_qkv / 8, nb, a.kb_dim, 1}, base, s_issued + p, nsp, ring, full, empty, s_qa, s_meta, warp, lane, [&](int oct, PsRwAcc *acc) {
+        ps_st_walk<1>(ctl, PsStMv{ly.w_qkv, n_qkv / 8, nb, a.kb_dim, 1}, base, PsStRing{s_issued + p, ring, full, empty, s_qa, s_meta, nsp}, warp, lane, [&](int oct, PsRwAcc *acc) {
             float res = ps_rw_row_result(acc[0]);
             const int row = oct * 8 + r;
             // segments are octet-aligned: the branch is warp-uniform
@@ -667,7 +791,10 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
                 if (ly.v_bias) res = __fadd_rn(res, ly.v_bias[n]);
                 if (q == 0) ly.vct[(size_t)n * a.n_ctx + pos] = res; // V cache is stored transposed
             }
-        });
+        }, [&](int k, int) { // the warps without a row octet pull this layer's K / V cache into L2: the attention phases come next
+            const int n_fix = PS_ST_WARPS - (n_qkv / 8 + G - 1) / G; // idle warps EVERY CTA has in this phase
+            if (k < n_fix) ps_st_prefetch_kv(ly.kc, ly.vct, pos, a.kvd_l, a.n_ctx, ((int)blockIdx.x * n_fix + k) * 32 + lane, G * n_fix * 32);
+        }, t_);
         ps_st_tl_exit(t_);
         bar_target += G;
         ps_st_grid_barrier(ctl, a.bar_ctr, bar_target);
@@ -681,7 +808,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         // ---------------------------------------------------------------- soft-max + P.V -> attention output (exchanged)
         t_ = PS_ST_TL(3 + 6 * L);
         ps_st_tl_enter(t_);
-        ps_st_pv<R2>(ctl, a, ly.vct, n_kv, reinterpret_cast<float *>(ps_st_smem), sh_red, sh_f, ep, tid);
+        ps_st_pv<R2>(ctl, a, ly.vct, n_kv, reinterpret_cast<float *>(ps_st_smem), sh_red, sh_f, ep, tid, t_);
         ps_st_tl_exit(t_);
         // ---------------------------------------------------------------- Wo + residual: x1 = x + Wo . att
         t_ = PS_ST_TL(4 + 6 * L);
@@ -689,14 +816,14 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         nb = a.qdim / 256;
         s_meta = reinterpret_cast<uint2 *>(ps_st_smem + a.qdim);
         ps_st_prologue_vec(ctl, a.att_ll, ep, a.qdim, nullptr, 0.f, s_qa, s_meta, sh_red, warp, lane, t_);
-        ps_st_walk<1>(ctl, PsStMv{ly.w_o, dim_l / 8, nb, a.kb_q, 1}, base, s_issued + p, nsp, ring, full, empty, s_qa, s_meta, warp, lane, [&](int oct, PsRwAcc *acc) {
+        ps_st_walk<1>(ctl, PsStMv{ly.w_o, dim_l / 8, nb, a.kb_q, 1}, base, PsStRing{s_issued + p, ring, full, empty, s_qa, s_meta, nsp}, warp, lane, [&](int oct, PsRwAcc *acc) {
             float res = ps_rw_row_result(acc[0]);
             if (q == 0) {
                 const int64_t n = (int64_t)a.rank * dim_l + oct * 8 + r;
                 res = __fadd_rn(ps_st_ll_value(a.x_ll + n), res);
                 ps_st_ll_store(a.peers->x1, a.tp, n, __float_as_uint(res), ep);
             }
-        });
+        }, PsStNoIdle(), t_);
         ps_st_tl_exit(t_);
         // ---------------------------------------------------------------- gate | up + SiLU: h = silu(Wg . xn) * (Wu . xn), quantised by its producers
         t_ = PS_ST_TL(5 + 6 * L);
@@ -707,7 +834,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         {
             const int n_oct_gu = (a.ffn_l + 7) / 8;
             const int nbf = a.ffn / 256;
-            ps_st_walk<2>(ctl, PsStMv{ly.w_gu, n_oct_gu, nb, a.kb_gu, 2}, base, s_issued + p, nsp, ring, full, empty, s_qa, s_meta, warp, lane, [&](int oct, PsRwAcc *acc) {
+            ps_st_walk<2>(ctl, PsStMv{ly.w_gu, n_oct_gu, nb, a.kb_gu, 2}, base, PsStRing{s_issued + p, ring, full, empty, s_qa, s_meta, nsp}, warp, lane, [&](int oct, PsRwAcc *acc) {
                 const float gv = ps_rw_row_result(acc[0]);
                 const float uv = ps_rw_row_result(acc[1]);
                 const int row = oct * 8 + r;
@@ -737,7 +864,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
                     }
                     if (lane == 0) a.blk_cnt[i] = 0;
                 }
-            });
+            }, PsStNoIdle(), t_);
         }
         ps_st_tl_exit(t_);
         // ---------------------------------------------------------------- down + residual: x = x1 + Wdown . h
@@ -746,14 +873,14 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         nb = a.ffn / 256;
         s_meta = reinterpret_cast<uint2 *>(ps_st_smem + a.ffn);
         ps_st_prologue_img(ctl, a.hq_ll, ep, a.ffn, reinterpret_cast<uint32_t *>(ps_st_smem), tid, t_);
-        ps_st_walk<1>(ctl, PsStMv{ly.w_down, dim_l / 8, nb, a.kb_ffn, 1}, base, s_issued + p, nsp, ring, full, empty, s_qa, s_meta, warp, lane, [&](int oct, PsRwAcc *acc) {
+        ps_st_walk<1>(ctl, PsStMv{ly.w_down, dim_l / 8, nb, a.kb_ffn, 1}, base, PsStRing{s_issued + p, ring, full, empty, s_qa, s_meta, nsp}, warp, lane, [&](int oct, PsRwAcc *acc) {
             float res = ps_rw_row_result(acc[0]);
             if (q == 0) {
                 const int64_t n = (int64_t)a.rank * dim_l + oct * 8 + r;
                 res = __fadd_rn(ps_st_ll_value(a.x1_ll + n), res);
                 ps_st_ll_store(a.peers->x, a.tp, n, __float_as_uint(res), ep + 1);
             }
-        });
+        }, PsStNoIdle(), t_);
         ps_st_tl_exit(t_);
     }
 
@@ -766,7 +893,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
         const int nb = dim / 256;
         uint2 *s_meta = reinterpret_cast<uint2 *>(ps_st_smem + dim);
         ps_st_prologue_vec(ctl, a.x_ll, ep0 + n_layers, dim, a.out_norm, a.eps, s_qa, s_meta, sh_red, warp, lane, t_);
-        ps_st_walk<1>(ctl, PsStMv{a.w_out, (a.vocab_l + 7) / 8, nb, a.kb_dim, 1}, base, s_issued + p, nsp, ring, full, empty, s_qa, s_meta, warp, lane, [&](int oct, PsRwAcc *acc) {
+        ps_st_walk<1>(ctl, PsStMv{a.w_out, (a.vocab_l + 7) / 8, nb, a.kb_dim, 1}, base, PsStRing{s_issued + p, ring, full, empty, s_qa, s_meta, nsp}, warp, lane, [&](int oct, PsRwAcc *acc) {
             const float res = ps_rw_row_result(acc[0]);
             const int n = oct * 8 + r;
             if (q == 0 && n < a.vocab_l) {
@@ -775,7 +902,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
                     for (int pr = 0; pr < a.tpo_logits->n; pr++) a.tpo_logits->peer_dst[pr][n] = res;
                 if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
             }
-        });
+        }, PsStNoIdle(), t_);
         ps_st_tl_exit(t_);
     }
     // -------------------------------------------------------------------- finish: per-CTA partial, last CTA picks and does the step bookkeeping
@@ -823,7 +950,7 @@ __global__ void __launch_bounds__(PS_ST_THREADS, 1) ps_k_step(const PsStArgs a, 
                     bi = 0x7fffffff;
                     for (int rk = 0; rk < a.tp; rk++) {
                         uint32_t b0 = 0, b1 = 0;
-                        PS_ST_SPIN_UNTIL(ctl, ps_st_ll_load2(a.best_ll + 2 * rk, epb, b0, b1), 7);
+                        PS_ST_SPIN_UNTIL_S(ctl, ps_st_ll_load2(a.best_ll + 2 * rk, epb, b0, b1), 7, 100);
                         const float v = __uint_as_float(b0);
                         const int i = (int)b1;
                         if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }

@@ -26,15 +26,17 @@ def _model(preset, n_ctx, max_batch=128):
     return capi.CudaModel(desc=desc, tensors=g.tensors), g
 
 
+@pytest.mark.parametrize("persist", [0, 1], ids=["per-phase-kernels", "persistent-step-kernel"])
 @pytest.mark.parametrize("n_ctx", [4096, 8192])
 @pytest.mark.parametrize("case", cases.LONG_CASES, ids=lambda c: f"{c[0]}-{c[1]}")
-def test_long_context_decode_matches_reference(case, n_ctx):
+def test_long_context_decode_matches_reference(case, n_ctx, persist):
     preset, n_prompt, batch, n_dec = case
     if n_prompt + n_dec + 1 > n_ctx:
         pytest.skip("prompt does not fit this n_ctx")
     gold = np.load(G)
     key = f"{preset}/{n_prompt}/{batch}"
     cm, keep = _model(preset, n_ctx)
+    cm.be.set_option("persist", persist)
     prompt = long_prompt(preset, n_prompt)
     ids, lg = cm.generate(prompt, n_dec, batch_size=batch)              # host-driven steps: logits of every step
     assert ids == list(gold[key + "/ids"])
@@ -42,5 +44,6 @@ def test_long_context_decode_matches_reference(case, n_ctx):
     cm.reset(); cm.prefill(prompt, batch)
     dev_ids = list(cm.decode_greedy(int(prompt[-1]), n_dec))             # device-resident greedy loop (graph replay)
     assert dev_ids == ids
-    assert cm.be.counter("tc_error") == 0
+    assert cm.be.counter("tc_error") == 0 and cm.be.counter("step_error") == 0
+    assert (cm.be.counter("step_launches") > 0) == bool(persist)
     cm.close()

@@ -48,11 +48,15 @@ for k in range(n):
     excl = (e - max(prev_end, t0)) / 1e3
     if k < 14 or k >= n - 2:
         print(f"{k:3d} {names[k]:7s} {f(s):9.2f} {(f(inp) if inp else float('nan')):8.2f} {(f(img) if img else float('nan')):8.2f} {f(e):9.2f} {(e - s) / 1e3:7.2f} {excl:7.2f}")
-    tot.setdefault(names[k], []).append((excl, (inp - prev_end) / 1e3 if inp else 0.0, (img - inp) / 1e3 if inp else 0.0, (e - img) / 1e3 if img else 0.0))
+    tot.setdefault(names[k], []).append((excl, (inp - prev_end) / 1e3 if inp else 0.0, (img - inp) / 1e3 if inp else 0.0, (e - img) / 1e3 if img else 0.0,
+                                         buf[k][5] / 1e3, buf[k][6] / 1e3, buf[k][3] / 1e3, buf[k][4] / 1e3, buf[k][7] / 1e3))
     prev_end = e
 print("per phase kind: mean exclusive time (last exit - previous phase's last exit) | wait for inputs | build image | walk")
 for nm, v in tot.items():
     a = np.array(v)
-    print(f"  {nm:7s} n={len(v):3d} excl {a[:, 0].mean():7.2f} us  inputs {a[:, 1].mean():6.2f}  image {a[:, 2].mean():6.2f}  walk {a[:, 3].mean():6.2f}   sum {a[:, 0].sum():8.1f} us")
+    if nm == "PV":
+        print(f"  {nm:7s} n={len(v):3d} excl {a[:, 0].mean():7.2f} us  (slowest CTA, from entry: max known {a[:, 6].mean():6.2f}  sum known {a[:, 7].mean():6.2f}  P.V done {a[:, 4].mean():6.2f} us; exp loop 1st trip {a[:, 5].mean():.2f} kcyc, 2nd trip {a[:, 8].mean():.2f} kcyc)   sum {a[:, 0].sum():8.1f} us")
+    else:
+        print(f"  {nm:7s} n={len(v):3d} excl {a[:, 0].mean():7.2f} us  inputs {a[:, 1].mean():6.2f}  image {a[:, 2].mean():6.2f}  walk {a[:, 3].mean():6.2f}  [slowest warp: walk {a[:, 4].mean():6.2f} kcyc, of which waiting for weights {a[:, 5].mean():6.2f}, epilogues {a[:, 8].mean():6.2f} kcyc]   sum {a[:, 0].sum():8.1f} us")
 print(f"step span {(buf[n - 1, 1] - t0) / 1e3:.1f} us")
 m.close()
