@@ -117,6 +117,13 @@ int     ps_cuda_kv_reset(ps_cuda_ctx *ctx);                    /* truncate_token
 int     ps_cuda_kv_truncate(ps_cuda_ctx *ctx, int n_tokens);   /* truncate_tokens(n) */
 int     ps_cuda_kv_rollback(ps_cuda_ctx *ctx, int n_tokens);   /* rollback_tokens(n) */
 int     ps_cuda_kv_advance(ps_cuda_ctx *ctx, int n_tokens);    /* advance_tokens(n) */
+/* slot operations of KVCacheInterface used by the speculative path (src/core/kv_cache.hpp:120-143, 188-231;
+ * src/speculative/token_tree.cpp:195-212, 295-315): cache SLOTS are decoupled from token positions and carry a mask bit
+ * (advance unmasks, rollback masks); `copy` takes a token of the LAST ps_cuda_forward_tree batch. */
+int     ps_cuda_kv_copy_slot(ps_cuda_ctx *ctx, int dst_cache_index, int src_token_index);   /* copy(dst, src) */
+int     ps_cuda_kv_move_slot(ps_cuda_ctx *ctx, int dst_cache_index, int src_cache_index);   /* move(dst, src) */
+int     ps_cuda_kv_mask_slot(ps_cuda_ctx *ctx, int cache_index);                            /* mask(idx), idx < position */
+int     ps_cuda_kv_unmask_slot(ps_cuda_ctx *ctx, int cache_index);                          /* unmask(idx) */
 float  *ps_cuda_kv_k(ps_cuda_ctx *ctx, int layer);             /* device ptr, [n_ctx][kv_dim] */
 float  *ps_cuda_kv_v(ps_cuda_ctx *ctx, int layer);             /* device ptr, [kv_dim][n_ctx] (transposed) */
 
@@ -127,6 +134,13 @@ float  *ps_cuda_kv_v(ps_cuda_ctx *ctx, int layer);             /* device ptr, [k
  * call returns after the copy has landed; the KV position advances by bs. */
 int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w);
 int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, int lm_head, float *logits_host);
+/* The same forward as the speculative path calls it (src/speculative/spec_model.hpp:96-103, token_tree.cpp:131-133): arbitrary
+ * token positions, `tree_mask` = bs x bs bytes, row i = the batch tokens token i attends to (TokenTree::attention_mask; NULL =
+ * causal), attention over the unmasked cache slots below the current position; the batch's K / V rows are appended at cache
+ * slots position .. position + bs - 1 and the position advances by bs (CausalLM::Batch::save_kv + advance, causal_models.cpp:
+ * 353-359) - callers roll back and `copy` the accepted tokens, as TokenTree::verify does.  bs <= min(max_batch, 32). */
+int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, const uint8_t *tree_mask, int lm_head,
+                         float *logits_host);
 /* Model::decode with top_k = 1 (llama_model.cpp:119-132): forward + arg-max on the device; only the token id comes
  * back.  `n_steps` > 1 keeps feeding the produced id back in without a host round trip (ids_host gets n_steps ids). */
 int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, int32_t *ids_host);

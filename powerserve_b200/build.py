@@ -47,5 +47,22 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return LIB
 
 
+SPEC_LIB = os.path.join(HERE, "libps_spec.so")
+SPEC_SRC = os.path.join(HERE, "host", "spec_decode.cpp")
+
+
+def build_spec(force: bool = False) -> str:
+    """libps_spec.so: the host-side speculative decoder (include/ps_spec.h), plain C++ over the C ABI of libps_cuda.so."""
+    deps = [SPEC_SRC, os.path.join(HERE, "..", "include", "ps_spec.h"), os.path.join(HERE, "..", "include", "ps_cuda.h"), LIB]
+    if not force and os.path.exists(SPEC_LIB) and all(os.path.getmtime(SPEC_LIB) >= os.path.getmtime(d) for d in deps if os.path.exists(d)):
+        return SPEC_LIB
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", SPEC_SRC, "-o", SPEC_LIB, "-L" + HERE, "-lps_cuda", "-Wl,-rpath,$ORIGIN"]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + r.stdout + r.stderr)
+    return SPEC_LIB
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    print(build_spec(force="--force" in sys.argv))

@@ -86,10 +86,15 @@ def load_library() -> C.CDLL:
         "ps_cuda_kv_truncate": (ci, [vp, ci]),
         "ps_cuda_kv_rollback": (ci, [vp, ci]),
         "ps_cuda_kv_advance": (ci, [vp, ci]),
+        "ps_cuda_kv_copy_slot": (ci, [vp, ci, ci]),
+        "ps_cuda_kv_move_slot": (ci, [vp, ci, ci]),
+        "ps_cuda_kv_mask_slot": (ci, [vp, ci]),
+        "ps_cuda_kv_unmask_slot": (ci, [vp, ci]),
         "ps_cuda_kv_k": (vp, [vp, ci]),
         "ps_cuda_kv_v": (vp, [vp, ci]),
         "ps_cuda_bind_model": (ci, [vp, C.POINTER(ModelWeights)]),
         "ps_cuda_forward": (ci, [vp, i32p, i32p, ci, ci, C.c_void_p]),
+        "ps_cuda_forward_tree": (ci, [vp, i32p, i32p, ci, C.c_void_p, ci, C.c_void_p]),
         "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
         "ps_cuda_logits_dev": (vp, [vp]),
         "ps_cuda_tp_unique_id": (ci, [vp]),
@@ -239,6 +244,19 @@ class CudaBackend:
     def kv_advance(self, n: int):
         self._ck(self.L.ps_cuda_kv_advance(self.h, n))
 
+    # KVCacheInterface slot operations (speculative decode, kv_cache.hpp:120-143)
+    def kv_copy_slot(self, dst_cache_index: int, src_token_index: int):
+        self._ck(self.L.ps_cuda_kv_copy_slot(self.h, dst_cache_index, src_token_index))
+
+    def kv_move_slot(self, dst_cache_index: int, src_cache_index: int):
+        self._ck(self.L.ps_cuda_kv_move_slot(self.h, dst_cache_index, src_cache_index))
+
+    def kv_mask_slot(self, cache_index: int):
+        self._ck(self.L.ps_cuda_kv_mask_slot(self.h, cache_index))
+
+    def kv_unmask_slot(self, cache_index: int):
+        self._ck(self.L.ps_cuda_kv_unmask_slot(self.h, cache_index))
+
     def kv_k(self, layer: int) -> int:
         return self.L.ps_cuda_kv_k(self.h, layer)
 
@@ -346,6 +364,16 @@ class CudaModel:
                                               bs, int(lm_head), logits.ctypes.data if lm_head else None))
         return logits
 
+    def forward_tree(self, tokens, pos, tree_mask=None, lm_head: bool = True) -> Optional[np.ndarray]:
+        """The speculative path's forward (ps_cuda_forward_tree): arbitrary positions, in-batch tree mask [bs][bs] (None = causal)."""
+        t, p = _i32(tokens), _i32(pos)
+        bs = len(t)
+        m = None if tree_mask is None else np.ascontiguousarray(np.asarray(tree_mask, dtype=np.uint8).reshape(bs, bs))
+        logits = np.empty((bs, self.vocab), np.float32) if lm_head else None
+        self.be._ck(self.be.L.ps_cuda_forward_tree(self.be.h, t.ctypes.data_as(C.POINTER(C.c_int32)), p.ctypes.data_as(C.POINTER(C.c_int32)), bs,
+                                                   m.ctypes.data if m is not None else None, int(lm_head), logits.ctypes.data if lm_head else None))
+        return logits
+
     def decode_greedy(self, first_token: int, n_steps: int) -> np.ndarray:
         ids = np.zeros(n_steps, np.int32)
         self.be._ck(self.be.L.ps_cuda_decode_greedy(self.be.h, int(first_token), n_steps, ids.ctypes.data_as(C.POINTER(C.c_int32))))
@@ -374,3 +402,75 @@ class CudaModel:
 
     def close(self):
         self.be.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------- speculative
+SPEC_LIB_PATH = os.path.join(HERE, "libps_spec.so")
+
+
+class SpecConfig(C.Structure):
+    """ps_spec_config == SpeculativeConfig (src/speculative/speculative_config.hpp:21-36)"""
+    _fields_ = [("draft_batch_size", C.c_int32), ("top_k", C.c_int32), ("temperature", C.c_float), ("p_base", C.c_float), ("max_fan_out", C.c_int32),
+                ("min_prob", C.c_float), ("early_stop", C.c_int32), ("n_stop", C.c_int32), ("stop_tokens", C.c_int32 * 8)]
+
+
+class SpecStats(C.Structure):
+    _fields_ = [(n, C.c_int64) for n in ("n_draft_times", "n_draft_tokens", "n_accepted_tokens", "n_iterations", "n_generated_tokens")] + \
+               [(n, C.c_double) for n in ("prefill_s", "draft_s", "verify_s", "total_s")]
+
+
+_spec_lib: Optional[C.CDLL] = None
+
+
+def load_spec_library() -> C.CDLL:
+    global _spec_lib
+    if _spec_lib is None:
+        load_library()   # libps_spec.so links libps_cuda.so (rpath $ORIGIN)
+        if not os.path.exists(SPEC_LIB_PATH):
+            raise PsCudaError(f"{SPEC_LIB_PATH} is missing - build it with `python -m powerserve_b200.build`")
+        L = C.CDLL(SPEC_LIB_PATH)
+        vp, ci = C.c_void_p, C.c_int
+        L.ps_spec_default_config.argtypes = [C.POINTER(SpecConfig)]
+        L.ps_spec_default_config.restype = None
+        L.ps_spec_create.argtypes = [C.POINTER(vp), vp, vp, C.POINTER(SpecConfig)]
+        L.ps_spec_destroy.argtypes = [vp]
+        L.ps_spec_destroy.restype = None
+        L.ps_spec_set_vocab.argtypes = [vp, ci]
+        L.ps_spec_generate.argtypes = [vp, C.POINTER(C.c_int32), ci, ci, ci, C.POINTER(C.c_int32), C.POINTER(SpecStats)]
+        L.ps_spec_last_error.argtypes = [vp]
+        L.ps_spec_last_error.restype = C.c_char_p
+        _spec_lib = L
+    return _spec_lib
+
+
+class SpecDecoder:
+    """Token-tree speculative decoding over a target and a draft CudaModel (include/ps_spec.h)."""
+
+    def __init__(self, target: CudaModel, draft: CudaModel, **overrides):
+        assert target.vocab == draft.vocab, "target and draft must share the vocabulary"
+        self.L = load_spec_library()
+        self.cfg = SpecConfig()
+        self.L.ps_spec_default_config(C.byref(self.cfg))
+        for k, v in overrides.items():
+            setattr(self.cfg, k, v)
+        self.h = C.c_void_p()
+        rc = self.L.ps_spec_create(C.byref(self.h), target.be.h, draft.be.h, C.byref(self.cfg))
+        if rc:
+            raise PsCudaError(f"ps_spec_create failed ({rc})")
+        self.L.ps_spec_set_vocab(self.h, target.vocab)
+        self.target, self.draft = target, draft
+
+    def generate(self, prompt, n_tokens: int, prefill_batch: int = 128):
+        p = _i32(prompt)
+        out = np.zeros(n_tokens, np.int32)
+        st = SpecStats()
+        rc = self.L.ps_spec_generate(self.h, p.ctypes.data_as(C.POINTER(C.c_int32)), len(p), n_tokens, prefill_batch,
+                                     out.ctypes.data_as(C.POINTER(C.c_int32)), C.byref(st))
+        if rc:
+            raise PsCudaError(f"ps_spec_generate failed ({rc}): {self.L.ps_spec_last_error(self.h).decode()}")
+        return out, {n: getattr(st, n) for n, _ in SpecStats._fields_}
+
+    def close(self):
+        if self.h:
+            self.L.ps_spec_destroy(self.h)
+            self.h = None

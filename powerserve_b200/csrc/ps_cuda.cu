@@ -87,6 +87,14 @@ struct ps_cuda_ctx {
     // kv cache
     std::vector<float *> kc, vct;
     int position = 0;
+    // speculative decode (kv_cache.hpp:97-276): per-slot mask, last batch kept aside for KVCacheInterface::copy
+    std::vector<uint8_t> slot_mask;      // host copy, 1 = masked (not attended)
+    bool slot_mask_dirty = true;
+    uint8_t *slot_mask_dev = nullptr, *tree_dev = nullptr, *h_tree = nullptr;
+    float *tree_bias = nullptr;          // [max_batch][n_ctx] attention bias of the current tree batch
+    float *k_stage = nullptr, *v_stage = nullptr; // [n_layers][max_batch][kvd_l]
+    float **kv_ptrs_dev = nullptr;       // [2 * n_layers]: K caches, then V^T caches
+    int last_batch = 0;                  // tokens held by the staging rows
     // rope table
     float *rope_table = nullptr;
     // workspace
@@ -880,6 +888,20 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         PS_CKC(cudaMemsetAsync(ctx->kc[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
         PS_CKC(cudaMemsetAsync(ctx->vct[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
     }
+    {   // speculative decode: slot mask, staging rows of the last batch, cache pointer table, tree bias
+        const int64_t kvd_l = kvd / tp, tb = std::min<int64_t>(B, 32);
+        ctx->slot_mask.assign((size_t)d.n_ctx, 1); // nothing committed yet: every slot is masked (rollback state)
+        PS_AL(ctx->slot_mask_dev, (size_t)d.n_ctx);
+        PS_AL(ctx->tree_dev, (size_t)(tb * tb));
+        PS_AL(ctx->tree_bias, 4 * (size_t)tb * (size_t)d.n_ctx);
+        PS_AL(ctx->k_stage, 4 * (size_t)d.n_layers * (size_t)tb * (size_t)kvd_l);
+        PS_AL(ctx->v_stage, 4 * (size_t)d.n_layers * (size_t)tb * (size_t)kvd_l);
+        PS_AL(ctx->kv_ptrs_dev, sizeof(float *) * 2 * (size_t)d.n_layers);
+        std::vector<float *> ptrs(2 * (size_t)d.n_layers);
+        for (int L = 0; L < d.n_layers; L++) { ptrs[L] = ctx->kc[L]; ptrs[d.n_layers + L] = ctx->vct[L]; }
+        PS_CKC(cudaMemcpy(ctx->kv_ptrs_dev, ptrs.data(), sizeof(float *) * ptrs.size(), cudaMemcpyHostToDevice));
+        PS_CKC(cudaMallocHost(&ctx->h_tree, (size_t)(tb * tb)));
+    }
     {
         std::vector<float> t;
         build_rope_table(d, t);
@@ -907,6 +929,7 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (ctx->h_pos) cudaFreeHost(ctx->h_pos);
     if (ctx->h_ids) cudaFreeHost(ctx->h_ids);
     if (ctx->h_err) cudaFreeHost(ctx->h_err);
+    if (ctx->h_tree) cudaFreeHost(ctx->h_tree);
     if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
     if (ctx->g_step) cudaGraphExecDestroy(ctx->g_step);
     if (ctx->g_fwd) cudaGraphExecDestroy(ctx->g_fwd);
@@ -1096,21 +1119,74 @@ int ps_cuda_copy_2d(ps_cuda_ctx *ctx, void *dst, int64_t ds0, int64_t ds1, const
 }
 
 // ---------------------------------------------------------------------------------------------- KV cache
+// mask bookkeeping shared by every path that moves the position (kv_cache.hpp:243-271: advance unmasks, rollback masks)
+static void kv_set_mask(ps_cuda_ctx *ctx, int from, int to, uint8_t v) {
+    from = std::max(from, 0);
+    to = std::min(to, ctx->d.n_ctx);
+    for (int i = from; i < to; i++)
+        if (ctx->slot_mask[i] != v) { ctx->slot_mask[i] = v; ctx->slot_mask_dirty = true; }
+}
 int ps_cuda_kv_position(ps_cuda_ctx *ctx) { return ctx->position; }
-int ps_cuda_kv_reset(ps_cuda_ctx *ctx) { ctx->position = 0; return 0; }
-int ps_cuda_kv_truncate(ps_cuda_ctx *ctx, int n) {
-    if (n < 0) return fail(ctx, PS_CUDA_ERR_INVALID, "kv_truncate: negative size");
-    if (n < ctx->position) ctx->position = n; // truncate_tokens, kv_cache.hpp:265-271
+int ps_cuda_kv_reset(ps_cuda_ctx *ctx) {
+    kv_set_mask(ctx, 0, ctx->position, 1);
+    ctx->position = 0;
     return 0;
 }
 int ps_cuda_kv_rollback(ps_cuda_ctx *ctx, int n) {
     if (n < 0 || n > ctx->position) return fail(ctx, PS_CUDA_ERR_INVALID, "kv_rollback: %d > position %d (POWERSERVE_ASSERT_KVCACHE)", n, ctx->position);
     ctx->position -= n;
+    kv_set_mask(ctx, ctx->position, ctx->position + n, 1); // rollback_tokens, kv_cache.hpp:255-263
+    return 0;
+}
+int ps_cuda_kv_truncate(ps_cuda_ctx *ctx, int n) {
+    if (n < 0) return fail(ctx, PS_CUDA_ERR_INVALID, "kv_truncate: negative size");
+    if (n < ctx->position) return ps_cuda_kv_rollback(ctx, ctx->position - n); // truncate_tokens, kv_cache.hpp:265-271
     return 0;
 }
 int ps_cuda_kv_advance(ps_cuda_ctx *ctx, int n) {
     if (n < 0 || ctx->position + n > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
+    kv_set_mask(ctx, ctx->position, ctx->position + n, 0); // advance_tokens, kv_cache.hpp:243-253
     ctx->position += n;
+    return 0;
+}
+// ---- slot operations of KVCacheInterface (speculative decode, kv_cache.hpp:120-143, 188-231)
+static int kv_slot_ck(ps_cuda_ctx *ctx, const char *what, int idx, int limit) {
+    if (idx < 0 || idx >= limit) return fail(ctx, PS_CUDA_ERR_INVALID, "%s: index %d outside [0,%d) (POWERSERVE_ASSERT_KVCACHE)", what, idx, limit);
+    return 0;
+}
+int ps_cuda_kv_copy_slot(ps_cuda_ctx *ctx, int dst_cache_index, int src_token_index) {
+    int rc;
+    if ((rc = kv_slot_ck(ctx, "kv_copy_slot (cache index)", dst_cache_index, ctx->d.n_ctx))) return rc;
+    if ((rc = kv_slot_ck(ctx, "kv_copy_slot (token of the last batch)", src_token_index, ctx->last_batch))) return rc;
+    if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "kv slot operations are single-GPU");
+    const int64_t kvd = (int64_t)ctx->d.n_kv_heads * ctx->d.head_size, lstride = std::min<int64_t>(ctx->d.max_batch, 32) * kvd;
+    ps_k_kv_copy_slot<<<dim3((unsigned)((kvd + 255) / 256), (unsigned)ctx->d.n_layers), 256, 0, ctx->stream>>>(ctx->kv_ptrs_dev, ctx->d.n_layers, ctx->k_stage, ctx->v_stage, lstride,
+                                                                                                             kvd, ctx->d.n_ctx, dst_cache_index, src_token_index);
+    PS_LAUNCH_CK();
+    return 0;
+}
+int ps_cuda_kv_move_slot(ps_cuda_ctx *ctx, int dst_cache_index, int src_cache_index) {
+    int rc;
+    if ((rc = kv_slot_ck(ctx, "kv_move_slot (dst)", dst_cache_index, ctx->d.n_ctx))) return rc;
+    if ((rc = kv_slot_ck(ctx, "kv_move_slot (src)", src_cache_index, ctx->d.n_ctx))) return rc;
+    if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "kv slot operations are single-GPU");
+    if (dst_cache_index == src_cache_index) return 0;
+    const int64_t kvd = (int64_t)ctx->d.n_kv_heads * ctx->d.head_size;
+    ps_k_kv_move_slot<<<dim3((unsigned)((kvd + 255) / 256), (unsigned)ctx->d.n_layers), 256, 0, ctx->stream>>>(ctx->kv_ptrs_dev, ctx->d.n_layers, kvd, ctx->d.n_ctx, dst_cache_index,
+                                                                                                             src_cache_index);
+    PS_LAUNCH_CK();
+    return 0;
+}
+int ps_cuda_kv_mask_slot(ps_cuda_ctx *ctx, int cache_index) {
+    int rc = kv_slot_ck(ctx, "kv_mask_slot", cache_index, ctx->position); // POWERSERVE_ASSERT_KVCACHE(cache_index < position), kv_cache.hpp:224
+    if (rc) return rc;
+    kv_set_mask(ctx, cache_index, cache_index + 1, 1);
+    return 0;
+}
+int ps_cuda_kv_unmask_slot(ps_cuda_ctx *ctx, int cache_index) {
+    int rc = kv_slot_ck(ctx, "kv_unmask_slot", cache_index, ctx->position);
+    if (rc) return rc;
+    kv_set_mask(ctx, cache_index, cache_index + 1, 0);
     return 0;
 }
 float *ps_cuda_kv_k(ps_cuda_ctx *ctx, int layer) { return (layer >= 0 && layer < ctx->d.n_layers) ? ctx->kc[layer] : nullptr; }
@@ -1286,13 +1362,16 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
 
 // LlamaModel::forward / Qwen2Model::forward on the device, one kernel per table op (the fused / graph-replayed decode
 // path lives in ps_decode.cuh and is bit-identical).
-static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
+// `tree_base` >= 0: a tree batch (ps_cuda_forward_tree) - K / V rows go to cache SLOTS tree_base .. tree_base + bs - 1 whatever the
+// token positions are, and the attention bias is ctx->tree_bias (slot mask + in-batch tree mask) instead of the causal `pos` mask.
+static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree_base = -1) {
     const ps_cuda_model_desc &d = ctx->d;
     const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
-    const int64_t n_kv = (int64_t)pos0 + bs; // pos.back() + 1
+    const bool tree = tree_base >= 0;
+    const int64_t n_kv = tree ? (int64_t)tree_base + bs : (int64_t)pos0 + bs; // pos.back() + 1
     const float kq_scale = 1.0f / sqrtf((float)hs);
     const bool tc = ctx->tc_ok && ctx->opt_tc && ctx->opt_fused && bs >= 16; // tensor-core GEMM on the fp16-expanded operands
-    const bool rw = ctx->fused_ok && ctx->opt_fused && bs > 1; // octet-interleaved copies exist: multi-column row-walker
+    const bool rw = ctx->fused_ok && ctx->opt_fused && (bs > 1 || tree); // octet-interleaved copies exist: multi-column row-walker
     int rc;
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
     PS_LAUNCH_CK();
@@ -1326,7 +1405,13 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         PS_LAUNCH_CK();
         ps_k_rope<<<dim3((unsigned)nkv, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
         PS_LAUNCH_CK();
-        ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
+        if (tree) {
+            const size_t lstride = (size_t)std::min<int64_t>(d.max_batch, 32) * (size_t)kvd;
+            ps_k_kv_store_at<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->k_stage + L * lstride, ctx->v_stage + L * lstride, ctx->kr, ctx->v,
+                                                                         kvd, d.n_ctx, tree_base, bs);
+        } else {
+            ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
+        }
         PS_LAUNCH_CK();
         if (bs >= 8) {
             const int r2 = (int)(nh / nkv);
@@ -1337,7 +1422,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
             ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
         }
         PS_LAUNCH_CK();
-        ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
+        ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, tree ? ctx->tree_bias : nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
         if (bs > 1 && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
             static bool pv_attr[64] = {};
@@ -1466,6 +1551,71 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     }
     { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     ctx->position = pos[0] + bs; // m_kv->advance(batch_size), llama_model.cpp:109
+    kv_set_mask(ctx, 0, ctx->position, 0);
+    return 0;
+}
+
+// LlamaModel::forward as the speculative path uses it (src/speculative/spec_model.hpp:96-103, token_tree.cpp:131): arbitrary
+// token positions (ROPE), an in-batch tree mask (row i = the batch tokens token i attends to; NULL = causal, i >= j,
+// attention_mask.cpp:36-41), attention over the UNMASKED cache slots below the current position, and the KV semantics of
+// CausalLM::Batch::save_kv + advance (src/backend/qnn/causal_models.cpp:353-359): the batch's K / V rows go to cache slots
+// position .. position + bs - 1 (kept aside as well for ps_cuda_kv_copy_slot), which are unmasked, and the position advances by bs.
+int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, const uint8_t *tree_mask, int lm_head, float *logits_host) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: no model bound");
+    if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward_tree: tree batches are single-GPU");
+    const int tb = std::min(ctx->d.max_batch, 32);
+    if (bs <= 0 || bs > tb) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: batch %d outside [1,%d]", bs, tb);
+    if (lm_head && !logits_host) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: lm_head requested without a logits buffer");
+    const int base = ctx->position;
+    if (base + bs > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
+    for (int i = 0; i < bs; i++) {
+        if (tokens[i] < 0 || tokens[i] >= ctx->d.vocab_size) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: token %d outside the vocabulary", tokens[i]);
+        if (pos[i] < 0 || pos[i] >= ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: position %d outside [0,%d)", pos[i], ctx->d.n_ctx);
+    }
+    const size_t row = (size_t)(base + bs) * 4;
+    if (row > 160 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward_tree: soft-max row of %d exceeds shared memory", base + bs);
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    memcpy(ctx->h_tokens, tokens, (size_t)bs * 4);
+    memcpy(ctx->h_pos, pos, (size_t)bs * 4);
+    for (int i = 0; i < bs; i++)
+        for (int j = 0; j < bs; j++) ctx->h_tree[i * bs + j] = tree_mask ? (tree_mask[i * bs + j] != 0) : (i >= j);
+    PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)bs * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->tree_dev, ctx->h_tree, (size_t)bs * bs, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += (int64_t)bs * 8 + (int64_t)bs * bs;
+    if (ctx->slot_mask_dirty) { // pageable source, small: the synchronous copy keeps the host vector free to change afterwards
+        PS_CK(cudaMemcpy(ctx->slot_mask_dev, ctx->slot_mask.data(), (size_t)ctx->d.n_ctx, cudaMemcpyHostToDevice));
+        ctx->h2d += ctx->d.n_ctx;
+        ctx->slot_mask_dirty = false;
+    }
+    PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    ps_k_tree_mask<<<dim3((unsigned)std::min<int64_t>((base + bs + 255) / 256, 64), (unsigned)bs), 256, 0, ctx->stream>>>(ctx->tree_bias, ctx->slot_mask_dev, ctx->tree_dev, base, bs,
+                                                                                                                        base + bs);
+    PS_LAUNCH_CK();
+    int rc = forward_ops(ctx, bs, lm_head, 0, base);
+    if (rc) return rc;
+    PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    ctx->logits_last = ctx->logits;
+    if (lm_head) {
+        const size_t bytes = (size_t)bs * ctx->d.vocab_size * 4;
+        if (bytes > ctx->h_logits_cap) {
+            if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+            ctx->h_logits = nullptr;
+            ctx->h_logits_cap = 0;
+            PS_CK(cudaMallocHost(&ctx->h_logits, bytes));
+            ctx->h_logits_cap = bytes;
+        }
+        PS_CK(cudaMemcpyAsync(ctx->h_logits, ctx->logits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_and_check(ctx))) return rc;
+        memcpy(logits_host, ctx->h_logits, bytes);
+        ctx->d2h += (int64_t)bytes;
+    } else if ((rc = sync_and_check(ctx))) return rc;
+    { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
+    ctx->last_batch = bs;
+    kv_set_mask(ctx, base, base + bs, 0);   // advance_tokens(bs)
+    ctx->position = base + bs;
     return 0;
 }
 
@@ -1508,6 +1658,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
         { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
         memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
         ctx->d2h += (int64_t)n_steps * 4;
+        kv_set_mask(ctx, 0, ctx->position + n_steps, 0);
         ctx->position += n_steps;
         return 0;
     }
@@ -1529,6 +1680,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     memcpy(ids_host, ctx->h_ids, (size_t)n_steps * 4);
     ctx->d2h += (int64_t)n_steps * 4;
+    kv_set_mask(ctx, 0, ctx->position + n_steps, 0);
     ctx->position += n_steps;
     return 0;
 }

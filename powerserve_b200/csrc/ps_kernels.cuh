@@ -499,6 +499,50 @@ __global__ void ps_k_kv_store(float *__restrict__ kc, float *__restrict__ vct, c
     }
 }
 
+// ---- speculative decode: the KV cache as KVCacheInterface sees it (src/core/kv_cache.hpp:97-276) - cache
+// SLOTS decoupled from token positions, a per-slot mask, and the last batch's K / V kept aside for `copy`.
+// KV store of a batch at cache slots base .. base + bs - 1 (save_tokens) + a copy into the per-layer staging rows
+__global__ void ps_k_kv_store_at(float *__restrict__ kc, float *__restrict__ vct, float *__restrict__ k_stage, float *__restrict__ v_stage,
+                                 const float *__restrict__ k, const float *__restrict__ v, int64_t kv_dim, int64_t n_ctx, int64_t base, int64_t bs) {
+    const int64_t total = kv_dim * bs;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / kv_dim, e = t % kv_dim;
+        kc[(base + i) * kv_dim + e] = k[t];
+        vct[e * n_ctx + base + i] = v[t];
+        k_stage[t] = k[t];
+        v_stage[t] = v[t];
+    }
+}
+// KVCacheInterface::copy (kv_cache.hpp:120-127, 188-203): token `src` of the last batch -> cache slot `dst`, every layer.
+// kv = [2 * n_layers] device pointers (K caches, then transposed V caches); stage = [n_layers][max_batch][kv_dim] x 2.
+__global__ void ps_k_kv_copy_slot(float *const *__restrict__ kv, int n_layers, const float *__restrict__ k_stage, const float *__restrict__ v_stage,
+                                  int64_t layer_stride, int64_t kv_dim, int64_t n_ctx, int64_t dst, int64_t src) {
+    const int L = blockIdx.y;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < kv_dim; e += (int64_t)gridDim.x * blockDim.x) {
+        kv[L][dst * kv_dim + e] = k_stage[L * layer_stride + src * kv_dim + e];
+        kv[n_layers + L][e * n_ctx + dst] = v_stage[L * layer_stride + src * kv_dim + e];
+    }
+}
+// KVCacheInterface::move (kv_cache.hpp:205-221): cache slot `src` -> cache slot `dst`, every layer
+__global__ void ps_k_kv_move_slot(float *const *__restrict__ kv, int n_layers, int64_t kv_dim, int64_t n_ctx, int64_t dst, int64_t src) {
+    const int L = blockIdx.y;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < kv_dim; e += (int64_t)gridDim.x * blockDim.x) {
+        kv[L][dst * kv_dim + e] = kv[L][src * kv_dim + e];
+        kv[n_layers + L][e * n_ctx + dst] = kv[n_layers + L][e * n_ctx + src];
+    }
+}
+// attention bias of a tree batch (CausalLM::fill_attention_mask, src/backend/qnn/causal_models.cpp:215-230, with the per-slot
+// mask of the cache in front): row i sees cache slot j < base unless the slot is masked, and batch token j - base iff
+// tree[i][j - base].  mask {n_kv, bs}, 0 or -inf, the layout softmax_ext expects.
+__global__ void ps_k_tree_mask(float *__restrict__ mask, const uint8_t *__restrict__ slot_mask, const uint8_t *__restrict__ tree, int64_t base,
+                               int64_t bs, int64_t n_kv) {
+    const int64_t i = blockIdx.y;
+    for (int64_t j = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; j < n_kv; j += (int64_t)gridDim.x * blockDim.x) {
+        const bool vis = j < base ? !slot_mask[j] : tree[i * bs + (j - base)] != 0;
+        mask[i * n_kv + j] = vis ? 0.f : -INFINITY;
+    }
+}
+
 // GET_MASK (src/executor/executor.cpp:210-224)
 __global__ void ps_k_get_mask(float *__restrict__ mask, int64_t n_kv, const int32_t *__restrict__ pos) {
     const int64_t i = blockIdx.y;

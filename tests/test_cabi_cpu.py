@@ -30,6 +30,16 @@ def test_library_exports_every_declared_symbol(lib):
     assert lib.ps_cuda_abi_version() == 1
 
 
+def test_spec_library_exports_every_declared_symbol(lib):
+    build.build_spec()
+    hdr = open(os.path.join(ROOT, "include", "ps_spec.h")).read()
+    declared = set(re.findall(r"\b(ps_spec_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 6
+    sl = capi.load_spec_library()
+    for name in sorted(declared):
+        assert hasattr(sl, name), f"libps_spec.so does not export {name}"
+
+
 def test_no_cpu_fallback_without_device(lib):
     if lib.ps_cuda_device_count() > 0:
         pytest.skip("a CUDA device is present")
