@@ -138,7 +138,9 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
  * token positions, `tree_mask` = bs x bs bytes, row i = the batch tokens token i attends to (TokenTree::attention_mask; NULL =
  * causal), attention over the unmasked cache slots below the current position; the batch's K / V rows are appended at cache
  * slots position .. position + bs - 1 and the position advances by bs (CausalLM::Batch::save_kv + advance, causal_models.cpp:
- * 353-359) - callers roll back and `copy` the accepted tokens, as TokenTree::verify does.  bs <= min(max_batch, 32). */
+ * 353-359) - callers roll back and `copy` the accepted tokens, as TokenTree::verify does.  bs <= min(max_batch, 32).
+ * lm_head = 1: logits_host receives [bs][vocab] fp32; lm_head = 2: the greedy pick is made on the device (first maximum per row,
+ * llama_model.cpp:124-128 with top_k = 1) and logits_host receives bs int32 token ids instead. */
 int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, const uint8_t *tree_mask, int lm_head,
                          float *logits_host);
 /* Model::decode with top_k = 1 (llama_model.cpp:119-132): forward + arg-max on the device; only the token id comes

@@ -109,7 +109,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -154,6 +154,8 @@ struct ps_cuda_ctx {
     float *part_val = nullptr; // per-CTA partial arg-max of the lm_head kernel (greedy pick, stage 1)
     int *part_idx = nullptr;
     cudaGraphExec_t g_step = nullptr, g_fwd = nullptr; // one decode step (with / without the greedy pick)
+    int64_t g_step_kernels = 0, g_fwd_kernels = 0;     // kernels captured in each
+    int attn_clusters = -1;                            // cudaOccupancyMaxActiveClusters of the fused attention kernel (counter "attn_clusters")
     // persistent per-step kernel (ps_step.cuh)
     int opt_persist = 0;            // 1: the whole decode step as ONE persistent kernel (ps_step.cuh); bit-exact and tested, but 2x slower than the per-phase kernels so far
     int opt_l2_ahead = 96;          // stages (4736 B) per CTA the L2 look-ahead warp stays ahead of the shared-memory rings (0 = off)
@@ -440,10 +442,74 @@ int rw_qkv(ps_cuda_ctx *ctx, const LayerDev &ld, int L) {
     return launch_rw(ctx, a, PS_EPI_STORE);
 }
 
+// one fused attention kernel per layer: clusters of 8 CTAs, one per (kv head, 64 output dims)
+template <int R2, int STEPS> int launch_attn_fused_s(ps_cuda_ctx *ctx, int L, bool *done) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int hs = d.head_size, nkv = ctx->nkv_l, cl = 8;
+    const size_t row = (size_t)((d.n_ctx + 31) & ~31) * 4;
+    const int s_cap = (((d.n_ctx + cl - 1) / cl + 7) & ~7) + 8;
+    const size_t smem = (size_t)(R2 + 8) * row + (size_t)R2 * s_cap * 4;
+    if (smem > 212 * 1024 || d.max_batch < 2) return 0; // rows too long for shared memory: the two-kernel path streams them
+    const dim3 grid((unsigned)cl, (unsigned)(hs / 64), (unsigned)nkv);
+    static int ok[64] = {}; // per device: 0 unknown, 1 usable, -1 not
+    if (ok[ctx->device] == 0) {
+        cudaError_t e = cudaFuncSetAttribute(ps_k_attn_fused<R2, STEPS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+        int n_clusters = 0;
+        if (e == cudaSuccess) {
+            cudaLaunchConfig_t qc{};
+            qc.gridDim = grid;
+            qc.blockDim = dim3(PS_AF_THREADS);
+            qc.dynamicSmemBytes = 212 * 1024;
+            cudaLaunchAttribute qa[1];
+            qa[0].id = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = (unsigned)cl; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+            qc.attrs = qa; qc.numAttrs = 1;
+            e = cudaOccupancyMaxActiveClusters(&n_clusters, ps_k_attn_fused<R2, STEPS>, &qc);
+        }
+        if (e != cudaSuccess) cudaGetLastError();
+        ok[ctx->device] = (e == cudaSuccess && n_clusters >= 8) ? 1 : -1; // fewer co-resident clusters than that would serialise the layer
+        ctx->attn_clusters = n_clusters;
+    }
+    if (ok[ctx->device] < 0) return 0;
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = grid;
+    cfg.blockDim = dim3(PS_AF_THREADS);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = ctx->stream;
+    cudaLaunchAttribute at[2];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)cl; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = (ctx->opt_pdl && !ctx->opt_ktime) ? 2 : 1;
+    const float kq_scale = 1.0f / sqrtf((float)hs);
+    // ctx->kq ([n_heads][max_batch][n_ctx]) doubles as the clusters' exponential rows: [hs / 64][kv heads][R2][n_ctx]
+    cudaError_t e = cudaLaunchKernelEx(&cfg, ps_k_attn_fused<R2, STEPS>, ctx->att, (const float *)ctx->kc[L], (const float *)ctx->vct[L], (const float *)ctx->q, ctx->kq,
+                                       (const int32_t *)ctx->pos_dev, nkv, d.n_ctx, kq_scale, s_cap, tl_slot(ctx), tp_out(ctx, PS_TP_SLOT_ATT));
+    ctx->n_launch++;
+    if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "fused attention launch failed: %s", cudaGetErrorString(e));
+    if (ctx->trace_dev) tl_slot(ctx); // keep the timeline's six slots per layer (the second attention slot stays empty)
+    *done = true;
+    return 0;
+}
+template <int R2> int launch_attn_fused(ps_cuda_ctx *ctx, int L, bool *done) {
+    *done = false;
+    if (!ctx->opt_attn_fused || ctx->d.n_ctx % 8) return 0;
+    if (ctx->d.head_size == 64) return launch_attn_fused_s<R2, 2>(ctx, L, done);
+    if (ctx->d.head_size == 128) return launch_attn_fused_s<R2, 4>(ctx, L, done);
+    return 0;
+}
+
 template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
     const ps_cuda_model_desc &d = ctx->d;
     const int hs = d.head_size, nkv = ctx->nkv_l;
     const float kq_scale = 1.0f / sqrtf((float)hs);
+    {
+        bool done = false;
+        int rc0 = launch_attn_fused<R2>(ctx, L, &done);
+        if (rc0 || done) return rc0;
+    }
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
         PS_CK(cudaFuncSetAttribute(ps_k_attn2<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
@@ -718,6 +784,7 @@ int run_step(ps_cuda_ctx *ctx, bool pick, int n_kv_max) {
         PS_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
         int rc = decode_step_fused(ctx, true, pick);
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
+        (pick ? ctx->g_step_kernels : ctx->g_fwd_kernels) = ctx->n_launch - n0;
         ctx->n_launch = n0; // capture enqueued nothing
         if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
         if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
@@ -727,7 +794,7 @@ int run_step(ps_cuda_ctx *ctx, bool pick, int n_kv_max) {
     }
     PS_CK(cudaGraphLaunch(ge, ctx->stream));
     ctx->n_graph++;
-    ctx->n_launch += 1 + 6 * ctx->d.n_layers + 1 + (pick ? 1 : 0); // OUR kernels inside the replayed graph (NCCL's are not counted)
+    ctx->n_launch += pick ? ctx->g_step_kernels : ctx->g_fwd_kernels; // OUR kernels inside the replayed graph (NCCL's are not counted)
     return 0;
 }
 
@@ -1566,7 +1633,7 @@ int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t 
     if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward_tree: tree batches are single-GPU");
     const int tb = std::min(ctx->d.max_batch, 32);
     if (bs <= 0 || bs > tb) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: batch %d outside [1,%d]", bs, tb);
-    if (lm_head && !logits_host) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: lm_head requested without a logits buffer");
+    if (lm_head && !logits_host) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_tree: lm_head requested without an output buffer");
     const int base = ctx->position;
     if (base + bs > ctx->d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", ctx->d.n_ctx);
     for (int i = 0; i < bs; i++) {
@@ -1598,7 +1665,16 @@ int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t 
     if (rc) return rc;
     PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->logits_last = ctx->logits;
-    if (lm_head) {
+    if (lm_head == 2) { // greedy ids only (ProbArray + greedy_sample with top_k = 1 per row, first maximum): bs ints come back instead of bs x vocab floats
+        for (int i = 0; i < bs; i++) {
+            ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits + (size_t)i * ctx->d.vocab_size, ctx->d.vocab_size, ctx->ids_dev + i, ctx->ids_dev + 2048 + i);
+            PS_LAUNCH_CK();
+        }
+        PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)bs * 4, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_and_check(ctx))) return rc;
+        memcpy(logits_host, ctx->h_ids, (size_t)bs * 4);
+        ctx->d2h += (int64_t)bs * 4;
+    } else if (lm_head) {
         const size_t bytes = (size_t)bs * ctx->d.vocab_size * 4;
         if (bytes > ctx->h_logits_cap) {
             if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
@@ -1786,6 +1862,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         ctx->opt_fused = value;
     }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "attn_fused")) ctx->opt_attn_fused = value; // 1: decode attention as ONE cluster kernel per layer (bit-exact, but slower so far: DESIGN.md); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "l2_ahead")) ctx->opt_l2_ahead = value;     // tuning: L2 look-ahead of the step kernel's weight stream, in 4736-byte stages per CTA
     else if (!strcmp(name, "attn_chunk")) ctx->opt_attn_chunk = value; // testing: soft-max positions resident in shared memory (multiple of 256)
     else if (!strcmp(name, "persist")) ctx->opt_persist = value; // 1: the whole decode step as ONE persistent kernel (ps_step.cuh); 0 (default): one kernel per phase
@@ -1818,6 +1895,7 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "graph_replays")) return ctx->n_graph;
     if (!strcmp(name, "step_launches")) return ctx->n_step;          // persistent step-kernel launches
     if (!strcmp(name, "step_ok")) return ctx->step_ok ? 1 : 0;
+    if (!strcmp(name, "attn_clusters")) return ctx->attn_clusters;
     if (!strcmp(name, "step_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the step-kernel launches
     if (!strcmp(name, "step_kernel_launches")) return ctx->kt_launches;
     if (!strncmp(name, "step_dbg", 8)) { // PS_ST_DEBUG builds: word k of the step kernel's debug record

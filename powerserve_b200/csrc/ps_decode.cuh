@@ -515,3 +515,213 @@ __global__ void __launch_bounds__(256) ps_k_argmax_step(const float *__restrict_
     }
     ps_tl_max(tl, 1);
 }
+
+// ====================================================================================================================
+// Decode attention in ONE kernel (replaces ps_k_attn1 + ps_k_attn2 when the rows fit shared memory): thread-block CLUSTERS
+// of eight CTAs (the portable size; clusters of sixteen ran one or two at a time on the B200 and serialised the layer).
+// A cluster serves one kv head and 64 of its output dims (grid = (8, hs / 64, kv heads)): its CTAs split the cache positions
+// for the scores, exchange the row maxima, the exponentials and the partial sums through distributed shared memory, and
+// then each takes eight output dims of the P.V product with its V^T rows staged by TMA.  The scores never visit global
+// memory, the soft-max row is built once per cluster (it was rebuilt by each of the 16 CTAs of a kv group before) and one
+// kernel boundary per layer disappears.  Arithmetic and summation orders are those of ps_k_attn1 / ps_k_attn2 (ggml_vec_dot_f32 lane
+// chains, GGML_F32x8_REDUCE, ggml_v_expf on full 8-groups of the row / libm expf on its tail, double sum, position-ordered
+// FMA chains for P.V) - bit-identical results.  norm_attention.cpp:115-151, ggml.c:2092-2131, 14846-14940.
+// ====================================================================================================================
+#include <cooperative_groups.h>
+#define PS_AF_THREADS 512
+template <int R2, int STEPS>
+__global__ void __launch_bounds__(PS_AF_THREADS) ps_k_attn_fused(float *__restrict__ att, const float *__restrict__ kc, const float *__restrict__ vct,
+                                                                 const float *__restrict__ q, float *__restrict__ ex, const int32_t *__restrict__ pos_dev,
+                                                                 int n_kv_heads, int n_ctx, float scale, int s_cap, long long *tl, const PsTpOut *tpo) {
+    namespace cg = cooperative_groups;
+    constexpr int hs = 32 * STEPS, NW = PS_AF_THREADS / 32;
+    extern __shared__ __align__(128) float s_af[]; // [R2][stride] probabilities | [8][stride] V^T rows | [R2][s_cap] this CTA's scores / exponentials
+    __shared__ float s_q[R2][hs];
+    __shared__ float s_max[R2];
+    __shared__ double s_sum[R2];
+    __shared__ float shf[NW][R2];
+    __shared__ double shd[NW];
+    __shared__ __align__(8) uint64_t bar_v;
+    cg::cluster_group cluster = cg::this_cluster();
+    const int CL = (int)cluster.num_blocks(), c = (int)cluster.block_rank(), g = blockIdx.z;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, kvd = hs * n_kv_heads;
+    constexpr int dpc = 8;                               // output dims of this CTA
+    const int d_base = ((int)blockIdx.y * CL + c) * dpc; // first of them
+    if (tid == 0) {
+        ps_mbar_init(&bar_v, 1);
+        ps_fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    ps_tl_min(tl, 0);
+    ps_grid_dep_wait();
+    ps_grid_dep_launch();
+    ps_tl_min(tl, 2);
+    const uint32_t ll_epoch = (tpo && tpo->peer_ll[0]) ? ps_tp_ll_epoch(tpo) : 0;
+    const long long t_dep = (tl && tid == 0) ? ps_globaltimer() : 0;
+#define PS_AF_PROBE(k)                                                                                                   \
+    do {                                                                                                                 \
+        if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
+    } while (0)
+    const int n_kv = pos_dev[0] + 1;
+    const int stride = (n_kv + 31) & ~31;
+    const int S = (((n_kv + CL - 1) / CL) + 7) & ~7;              // positions per CTA, a multiple of 8: the SIMD-exp groups never straddle CTAs
+    const int j_lo = min(c * S, n_kv), j_hi = min(n_kv, j_lo + S);
+    float *s_p = s_af, *s_v = s_af + R2 * stride, *s_sc = s_v + dpc * stride;
+    // the exponentials travel between the CTAs of the cluster through global memory (L2): rows of this cluster's own scratch
+    float *ex_rows = ex + ((size_t)blockIdx.y * gridDim.z + g) * R2 * (size_t)n_ctx;
+    __syncthreads(); // barrier word initialised
+    if (tid == 0) {  // this CTA's V^T rows: one bulk copy each, in flight during the whole soft-max
+        const uint32_t bytes = (uint32_t)(((n_kv + 3) & ~3) * 4);
+        ps_mbar_expect_tx(&bar_v, bytes * dpc);
+        for (int w = 0; w < dpc; w++) ps_bulk_g2s(s_v + w * stride, vct + ((int64_t)g * hs + d_base + w) * n_ctx, bytes, &bar_v);
+    }
+    // ---- scores of positions [j_lo, j_hi) against the R2 query heads of the group (ps_k_attn1)
+    for (int idx = tid; idx < R2 * hs; idx += PS_AF_THREADS) s_q[idx / hs][idx % hs] = q[(int64_t)g * R2 * hs + idx];
+    __syncthreads();
+    float qv[R2][STEPS];
+#pragma unroll
+    for (int hh = 0; hh < R2; hh++)
+#pragma unroll
+        for (int s = 0; s < STEPS; s++) qv[hh][s] = s_q[hh][32 * s + lane];
+    float lmax = -INFINITY; // lane hh < R2: running maximum of head hh over this warp's positions
+    for (int j0 = j_lo + warp * 8; j0 < j_hi; j0 += NW * 8) {
+        float kv[8][STEPS];
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int s = 0; s < STEPS; s++) kv[t][s] = (j0 + t < j_hi) ? kc[(int64_t)(j0 + t) * kvd + g * hs + 32 * s + lane] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float sum[R2];
+#pragma unroll
+            for (int hh = 0; hh < R2; hh++) {
+                sum[hh] = 0.f;
+#pragma unroll
+                for (int s = 0; s < STEPS; s++) sum[hh] = __fmaf_rn(kv[t][s], qv[hh][s], sum[hh]); // ggml_vec_dot_f32 lane chain
+            }
+            ps_f32x8_reduce_n<R2>(sum);
+            if (lane < R2 && j0 + t < j_hi) {
+                float v = sum[0];
+#pragma unroll
+                for (int hh = 1; hh < R2; hh++)
+                    if (lane == hh) v = sum[hh];
+                v = __fadd_rn(__fmul_rn(v, scale), 0.0f);
+                s_sc[lane * s_cap + (j0 + t - j_lo)] = v;
+                lmax = fmaxf(lmax, v);
+            }
+        }
+    }
+    if (lane < R2) shf[warp][lane] = lmax;
+    __syncthreads();
+    if (tid < R2) {
+        float m = shf[0][tid];
+        for (int w = 1; w < NW; w++) m = fmaxf(m, shf[w][tid]);
+        s_max[tid] = m;
+    }
+    PS_AF_PROBE(4);
+    cluster.sync(); // every CTA's maxima are in its shared memory
+    PS_AF_PROBE(5);
+    // ---- soft-max: row maximum over the cluster, exponentials of the own slice, partial sums in double (ps_k_attn2)
+    constexpr int TPH = PS_AF_THREADS / R2, WPH = TPH / 32; // threads / warps per head
+    const int hh = tid / TPH, ht = tid % TPH;
+    float mx = -INFINITY;
+    for (int r = 0; r < CL; r++) mx = fmaxf(mx, *cluster.map_shared_rank(&s_max[hh], r));
+    {
+        float *pp = s_sc + hh * s_cap;
+        float *gp = ex_rows + (size_t)hh * n_ctx + j_lo;
+        const int n8 = n_kv & ~7, len = j_hi - j_lo;
+        const int g_end = (min(j_hi, n8) - j_lo) >> 3; // full 8-groups of the ROW inside this slice (may be <= 0)
+        double s = 0.0;
+        for (int gi = ht; gi < g_end; gi += TPH) {
+            const float4 *p4 = reinterpret_cast<const float4 *>(pp + gi * 8);
+            const float4 xa = p4[0], xb = p4[1];
+            float vv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int l = 0; l < 8; l++) vv[l] = ps_v_expf(__fadd_rn(vv[l], -mx));
+            float4 *g4 = reinterpret_cast<float4 *>(gp + gi * 8); // rows and slices are 32-byte aligned (n_ctx % 8 == 0, S % 8 == 0)
+            g4[0] = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            g4[1] = make_float4(vv[4], vv[5], vv[6], vv[7]);
+            const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
+            s += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
+        }
+        for (int j = max(n8 - j_lo, 0) + ht; j < len; j += TPH) { // scalar tail of the row: libm expf
+            const float vv = ps_expf_glibc(__fadd_rn(pp[j], -mx));
+            gp[j] = vv;
+            s += (double)vv;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(PS_FULL, s, o);
+        if (lane == 0) shd[warp] = s;
+        __syncthreads();
+        if (ht == 0) {
+            double t = 0.0;
+            for (int w = 0; w < WPH; w++) t += shd[hh * WPH + w];
+            s_sum[hh] = t;
+        }
+    }
+    PS_AF_PROBE(6);
+    cluster.sync(); // release / acquire at cluster scope: every CTA's exponentials (global) and partial sums (shared) are visible
+    PS_AF_PROBE(7);
+    {
+        double sum = 0.0;
+        for (int r = 0; r < CL; r++) sum += *cluster.map_shared_rank(&s_sum[hh], r); // rank order: the same value on every CTA
+        const float inv = (float)(1.0 / sum);
+        float *dstp = s_p + hh * stride;
+        const float *srcp = ex_rows + (size_t)hh * n_ctx;
+        const int n4 = n_kv >> 2;
+#pragma unroll 4
+        for (int j4 = ht; j4 < n4; j4 += TPH) { // the whole row from L2, normalised on the way
+            const float4 e = __ldcg(reinterpret_cast<const float4 *>(srcp) + j4);
+            reinterpret_cast<float4 *>(dstp)[j4] = make_float4(__fmul_rn(e.x, inv), __fmul_rn(e.y, inv), __fmul_rn(e.z, inv), __fmul_rn(e.w, inv));
+        }
+        const int j = (n4 << 2) + ht;
+        if (j < n_kv) dstp[j] = __fmul_rn(__ldcg(srcp + j), inv);
+    }
+    __syncthreads();
+    ps_tl_max(tl, 3);
+    // ---- P.V: warp w < 8 walks V^T row w of this CTA once for all R2 heads (ggml_vec_dot_f32 order)
+    const int np = n_kv & ~31, ntail = n_kv - np;
+    if (warp < dpc) {
+        ps_mbar_wait(&bar_v, 0);
+        const float *vs = s_v + warp * stride;
+        const int d = d_base + warp;
+        float sum[R2];
+#pragma unroll
+        for (int h2 = 0; h2 < R2; h2++) sum[h2] = 0.f;
+        const float vtail = (lane < ntail) ? vs[np + lane] : 0.f;
+#pragma unroll 8
+        for (int s0 = 0; s0 < np; s0 += 32) { // the FMA chains stay in position order
+            const float v = vs[s0 + lane];
+#pragma unroll
+            for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(v, s_p[h2 * stride + s0 + lane], sum[h2]);
+        }
+        ps_f32x8_reduce_n<R2>(sum);
+        for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order (every lane computes the same chain)
+            const float v = __shfl_sync(PS_FULL, vtail, t);
+#pragma unroll
+            for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fadd_rn(sum[h2], __fmul_rn(v, s_p[h2 * stride + np + t]));
+        }
+        if (lane < R2) {
+            float v = sum[0];
+#pragma unroll
+            for (int h2 = 1; h2 < R2; h2++)
+                if (lane == h2) v = sum[h2];
+            att[(int64_t)(g * R2 + lane) * hs + d] = v;
+            if (tpo) { // all-gather by peer stores
+                if (tpo->peer_ll[0]) ps_tp_ll_store(tpo, (int64_t)(g * R2 + lane) * hs + d, v, ll_epoch);
+                else
+                    for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v;
+            }
+        }
+    }
+    if (tpo) {
+        if (tpo->peer_ll[0]) {
+            if (tid == 0) ps_tp_ll_done(tpo, (int)(gridDim.x * gridDim.y * gridDim.z), ll_epoch);
+        } else {
+            __syncthreads();
+            if (tid == 0) ps_tp_signal(tpo, (int)(gridDim.x * gridDim.y * gridDim.z));
+        }
+    }
+    cluster.sync(); // nobody leaves while a peer may still read its maxima / sums
+    ps_tl_max(tl, 1);
+}

@@ -45,7 +45,8 @@ struct ps_spec {
     std::string err;
     std::vector<Node> nodes;
     std::priority_queue<Candidate> main_heap, leaf_heap;
-    std::vector<float> draft_logits, target_logits;
+    std::vector<float> draft_logits;
+    std::vector<int32_t> target_ids;
     std::vector<ProbIndex> probs;
     ps_spec_stats stat{};
 
@@ -179,11 +180,7 @@ struct ps_spec {
                 if ((rc = ps_cuda_kv_move_slot(draft, node.position, node.cache_index))) return fail(rc, draft, "draft move");
                 if ((rc = ps_cuda_kv_advance(draft, 1))) return fail(rc, draft, "draft advance");
             }
-            // ProbArray + greedy_sample with top_k = 1: the first maximum
-            const float *lg = target_logits.data() + (size_t)u * vocab;
-            int next = 0;
-            for (int i = 1; i < vocab; i++)
-                if (lg[i] > lg[next]) next = i;
+            const int next = target_ids[u]; // ProbArray + greedy_sample with top_k = 1: the first maximum of row u
             enqueue(next);
             n_generated += 1;
             auto it = std::find_if(node.children.begin(), node.children.end(), [&](int v) { return nodes[v].token == next; });
@@ -210,7 +207,8 @@ struct ps_spec {
             pos[u] = nodes[u].position;
             for (int x = u; x != Node::no_parent; x = nodes[x].parent) mask[(size_t)u * bs + x] = 1;
         }
-        if ((rc = ps_cuda_forward_tree(target, toks.data(), pos.data(), bs, mask.data(), 1, target_logits.data()))) return fail(rc, target, "target tree forward");
+        // greedy target sampling: the arg-max of every row is taken on the device (12 ids come back instead of 12 x vocab logits)
+        if ((rc = ps_cuda_forward_tree(target, toks.data(), pos.data(), bs, mask.data(), 2, reinterpret_cast<float *>(target_ids.data())))) return fail(rc, target, "target tree forward");
         if ((rc = ps_cuda_kv_rollback(target, bs))) return fail(rc, target, "target rollback");
         rc = do_verify(enqueue);
         stat.verify_s += now_s() - t1;
@@ -263,7 +261,7 @@ int ps_spec_generate(ps_spec *s, const int32_t *prompt, int n_prompt, int n_toke
     s->stat.prefill_s = now_s() - t_begin;
     if (s->vocab <= 0) { s->err = "vocabulary size not set (ps_spec_set_vocab)"; return PS_CUDA_ERR_INVALID; }
     s->draft_logits.resize((size_t)s->vocab);
-    s->target_logits.resize((size_t)s->vocab * s->cfg.draft_batch_size);
+    s->target_ids.resize((size_t)s->cfg.draft_batch_size);
     int last = prompt[n_prompt - 1], n_out = 0;
     while (n_out < n_tokens) { // SpecTokenIterator::decode (spec_model.hpp:76-92): one tree iteration yields >= 1 token
         std::vector<int> q;

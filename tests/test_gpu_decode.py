@@ -11,12 +11,13 @@ from tests import _model as M
 pytestmark = pytest.mark.gpu
 
 
-def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0):
+def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0, attn_fused=0):
     cm.be.set_option("fused", fused)
     cm.be.set_option("graph", graph)
     cm.be.set_option("pdl", pdl)
     cm.be.set_option("persist", persist)     # 1 = the whole step as ONE persistent kernel (ps_step.cuh)
     cm.be.set_option("attn_chunk", attn_chunk)
+    cm.be.set_option("attn_fused", attn_fused)  # 1 = decode attention as one cluster kernel per layer, 0 = scores kernel + soft-max / P.V kernel
     return cm.generate(prompt, n_dec, batch_size=16)
 
 
@@ -35,6 +36,9 @@ def test_fused_equals_table_ops_and_oracle(preset):
     ids_g, lg_g = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1)
     L.assert_bit_equal(lg_g, lg_u, f"{preset}: fused+PDL+graph vs table ops")
     assert ids_u == ids_f == ids_p == ids_g
+    ids_2, lg_2 = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1, attn_fused=1)
+    L.assert_bit_equal(lg_2, lg_u, f"{preset}: one-kernel (cluster) attention vs table ops")
+    assert ids_2 == ids_u
     # device-resident greedy loop (graph replay per step, token fed back on the device)
     cm.reset(); cm.prefill(prompt, 16)
     ids_d = list(cm.decode_greedy(int(prompt[-1]), n_dec))
@@ -66,6 +70,8 @@ def test_fused_long_context_matches_table_ops():
     ids_g, lg_g = run(cm, prompt, 40, fused=1, graph=1)
     L.assert_bit_equal(lg_g, lg_u, "long context")
     assert ids_g == ids_u
+    ids_2, lg_2 = run(cm, prompt, 40, fused=1, graph=1, attn_fused=1)
+    L.assert_bit_equal(lg_2, lg_u, "long context, one-kernel (cluster) attention")
     ids_s, lg_s = run(cm, prompt, 40, fused=1, graph=1, persist=1)
     L.assert_bit_equal(lg_s, lg_u, "long context, persistent step kernel")
     assert ids_s == ids_u
