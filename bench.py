@@ -333,8 +333,12 @@ def main():
         model.tp_import([bytes(h.cpu().numpy().tobytes()) for h in allh])
     prompt = synth.random_prompt(shape.vocab_size, args.prompt + 1, seed=1234)
 
-    # prefill (ModelTokenIterator loop: prompt[:-1] in chunks, lm_head=false), wall clock through the C ABI
+    # prefill (ModelTokenIterator loop: prompt[:-1] in chunks, lm_head=false), wall clock through the C ABI; one untimed chunk
+    # first (lazy allocations, NCCL channel set-up of a tensor-parallel group)
+    model.prefill(prompt[:args.prefill_batch + 1], args.prefill_batch)
     model.reset()
+    barrier_fn = (lambda: (dist.barrier(), torch.cuda.synchronize())) if world > 1 else torch.cuda.synchronize
+    barrier_fn()
     t0 = time.perf_counter()
     model.prefill(prompt, args.prefill_batch)
     prefill_s = time.perf_counter() - t0

@@ -138,6 +138,7 @@ struct ps_cuda_ctx {
     uint8_t *heap = nullptr;
     size_t heap_bytes = 0, off_att = 0, off_x = 0, off_h = 0, off_val = 0, off_idx = 0, off_logits = 0, off_flags = 0;
     size_t off_ll[4] = {}; // in-band-flag mirrors of the four per-layer exchanges (ATT, X1, H, X2): 8 bytes per element
+    int opt_tp_batch = 1;  // option "tp_batch": tensor-parallel batches run as batched row-sharded GEMMs (0: token by token through the fused step)
     int opt_ll = 1;        // option "tp_ll": per-layer exchanges carry their flag in-band (no fences); 0 = fence + epoch flags
     uint8_t *peer_heap[PS_TP_MAX] = {};
     bool p2p = false;          // peers imported: all-gathers run as peer stores inside the producing kernels
@@ -146,7 +147,8 @@ struct ps_cuda_ctx {
     int *tp_err_dev = nullptr;
     PsTpOut *tpo_dev = nullptr; // [2][PS_TP_SLOTS] link tables of the peer-store exchange ([1]: with the in-band-flag pointers)
     PsTpIn *tpi_dev = nullptr;
-    float *tp_rows = nullptr;  // logits of a token-by-token tensor-parallel batch, [max_batch][vocab] (allocated on first use)
+    float *tp_rows = nullptr;  // logits of a tensor-parallel batch, [max_batch][vocab] (allocated on first use)
+    float *tp_tmp = nullptr, *tp_xb = nullptr, *tp_xl = nullptr, *tp_attb = nullptr, *tp_hb = nullptr, *tp_logl = nullptr; // batch forward (forward_ops_tp)
     int64_t n_gather = 0;      // all-gathers enqueued (counter "tp_allgathers")
     uint8_t *ximg = nullptr;   // Q8_K images of up to max_batch activation columns (multi-column row-walker)
     uint8_t *hq = nullptr;     // Q8_K image of the FFN hidden vector, written by the gate/up epilogue for the down mat-vec
@@ -1376,27 +1378,27 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
             if ((rc = rw_repack(ctx, ld.rw_gu, ld.wup, ffn_l, dim, 0, 1, 2))) return rc;
             if ((rc = rw_repack(ctx, ld.rw_down, ld.wdown, dim_l, ffn, 0, 0, 1))) return rc;
         }
-        // fp16-expanded tensor-core operands for the prefill GEMM (2 B / weight; single GPU only, and only if HBM has room)
+        // fp16-expanded tensor-core operands for the prefill GEMM (2 B / weight of this rank's rows; only if HBM has room)
         ctx->tc_ok = false;
-        if (tp == 1 && ctx->opt_tc && qdim % PS_TC_M == 0 && kvd % PS_TC_M == 0) {
+        if (ctx->opt_tc && qdim_l % PS_TC_M == 0 && kvd_l % PS_TC_M == 0) {
             auto a_bytes = [](int64_t rows, int64_t K) { return (size_t)((rows + PS_TC_M - 1) / PS_TC_M) * (size_t)(K / 256) * PS_TC_A_BLOCK; };
-            const size_t per_layer = a_bytes(qdim + 2 * kvd, dim) + a_bytes(dim, qdim) + 2 * a_bytes(ffn, dim) + a_bytes(dim, ffn);
+            const size_t per_layer = a_bytes(qdim_l + 2 * kvd_l, dim) + a_bytes(dim_l, qdim) + 2 * a_bytes(ffn_l, dim) + a_bytes(dim_l, ffn);
             size_t free_b = 0, total_b = 0;
             PS_CK(cudaMemGetInfo(&free_b, &total_b));
             if (per_layer * (size_t)d.n_layers + ((size_t)8 << 30) < free_b) {
                 for (LayerDev &ld : ctx->layers) {
-                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_qkv, a_bytes(qdim + 2 * kvd, dim)))) return rc;
-                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_o, a_bytes(dim, qdim)))) return rc;
-                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_gate, a_bytes(ffn, dim)))) return rc;
-                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_up, a_bytes(ffn, dim)))) return rc;
-                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_down, a_bytes(dim, ffn)))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wq, qdim, dim, 0))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wk, kvd, dim, qdim / PS_TC_M))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wv, kvd, dim, (qdim + kvd) / PS_TC_M))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_o, ld.wo, dim, qdim, 0))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_gate, ld.wgate, ffn, dim, 0))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_up, ld.wup, ffn, dim, 0))) return rc;
-                    if ((rc = tc_expand(ctx, ld.tc_down, ld.wdown, dim, ffn, 0))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_qkv, a_bytes(qdim_l + 2 * kvd_l, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_o, a_bytes(dim_l, qdim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_gate, a_bytes(ffn_l, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_up, a_bytes(ffn_l, dim)))) return rc;
+                    if ((rc = dev_alloc(ctx, (void **)&ld.tc_down, a_bytes(dim_l, ffn)))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wq, qdim_l, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wk, kvd_l, dim, qdim_l / PS_TC_M))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_qkv, ld.wv, kvd_l, dim, (qdim_l + kvd_l) / PS_TC_M))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_o, ld.wo, dim_l, qdim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_gate, ld.wgate, ffn_l, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_up, ld.wup, ffn_l, dim, 0))) return rc;
+                    if ((rc = tc_expand(ctx, ld.tc_down, ld.wdown, dim_l, ffn, 0))) return rc;
                 }
                 const size_t bb = (size_t)((d.max_batch + PS_TC_N - 1) / PS_TC_N) * (size_t)(ctx->maxK / 256) * PS_TC_B_BLOCK;
                 if ((rc = dev_alloc(ctx, (void **)&ctx->tc_b, bb))) return rc;
@@ -1553,6 +1555,142 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
 }
 
 
+// ---- tensor-parallel BATCH forward (prefill chunks, verify batches): the same row sharding as the decode step - every
+// rank owns rows [r * rows / tp, ...) of every matrix and its own kv heads, so every dot product keeps its full K and the
+// result is bit-identical to one GPU - with ONE all-gather per exchange for the whole chunk (4 per layer; NCCL on the
+// context stream) instead of feeding the chunk token by token.  Activations are replicated in full ([bs][dim] etc.);
+// `x_part` ([bs][dim_l]) is this rank's slice of the residual stream, the send buffer of its all-gathers.
+__global__ void ps_k_tp_slice(float *__restrict__ dst, const float *__restrict__ src, int64_t bs, int64_t n, int64_t n_l, int64_t rank) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < bs * n_l; t += (int64_t)gridDim.x * blockDim.x)
+        dst[t] = src[(t / n_l) * n + rank * n_l + t % n_l];
+}
+// all-gather output [tp][bs][n_l] -> [bs][tp * n_l]
+__global__ void ps_k_tp_unshard(float *__restrict__ dst, const float *__restrict__ src, int64_t bs, int64_t n_l, int64_t tp) {
+    const int64_t n = n_l * tp;
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < bs * n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t i = t / n, e = t % n, r = e / n_l;
+        dst[t] = src[(r * bs + i) * n_l + (e - r * n_l)];
+    }
+}
+static int tp_gather_rows(ps_cuda_ctx *ctx, float *dst_full, const float *src_part, int64_t bs, int64_t n_l) {
+    int rc = tp_all_gather(ctx, src_part, ctx->tp_tmp, (size_t)(bs * n_l), false, true);
+    if (rc) return rc;
+    ps_k_tp_unshard<<<grid1d(bs * n_l * ctx->tp), 256, 0, ctx->stream>>>(dst_full, ctx->tp_tmp, bs, n_l, ctx->tp);
+    PS_LAUNCH_CK();
+    return 0;
+}
+static int forward_ops_tp(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int64_t dim = d.dim, hs = d.head_size, qdim = (int64_t)d.n_heads * hs, ffn = d.ffn_dim;
+    const int64_t nh = ctx->nh_l, nkv = ctx->nkv_l, kvd = hs * nkv, qdim_l = nh * hs, ffn_l = ctx->ffn_l, dim_l = ctx->dim_l, vocab_l = ctx->vocab_l;
+    const int tp = ctx->tp, rank = ctx->rank;
+    const int64_t n_kv = (int64_t)pos0 + bs;
+    const float kq_scale = 1.0f / sqrtf((float)hs);
+    const bool tc = ctx->tc_ok && ctx->opt_tc && bs >= 16;
+    int rc;
+    if (!ctx->nccl_comm) return fail(ctx, PS_CUDA_ERR_INVALID, "tensor-parallel batch forward needs ps_cuda_tp_init");
+    if (!ctx->tp_tmp) {
+        const size_t widest = (size_t)std::max<int64_t>(std::max<int64_t>(qdim, dim), std::max<int64_t>(ffn, lm_head ? d.vocab_size : 0));
+        if ((rc = dev_alloc(ctx, (void **)&ctx->tp_tmp, 4 * (size_t)d.max_batch * std::max<size_t>(widest, (size_t)d.vocab_size)))) return rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->tp_xb, 4 * (size_t)d.max_batch * (size_t)dim))) return rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->tp_xl, 4 * (size_t)d.max_batch * (size_t)dim_l))) return rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->tp_attb, 4 * (size_t)d.max_batch * (size_t)qdim))) return rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->tp_hb, 4 * (size_t)d.max_batch * (size_t)ffn))) return rc;
+    }
+    float *x = ctx->tp_xb, *xl = ctx->tp_xl, *attb = ctx->tp_attb, *hb = ctx->tp_hb; // batch-sized twins of the single-token exchange buffers
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[ctx->device] = true; }
+    ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
+    PS_LAUNCH_CK();
+    ps_k_tp_slice<<<grid1d(bs * dim_l), 256, 0, ctx->stream>>>(xl, x, bs, dim, dim_l, rank);
+    PS_LAUNCH_CK();
+    for (int L = 0; L < d.n_layers; L++) {
+        const LayerDev &ld = ctx->layers[L];
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, x, ld.attn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        PsRwSeg sg[3] = {{ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, (int)qdim_l, 0},
+                         {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, (int)qdim_l, (int)(qdim_l + kvd), 0},
+                         {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, (int)(qdim_l + kvd), (int)(qdim_l + 2 * kvd), 0}};
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = tc_gemm(ctx, ld.tc_qkv, (int)(qdim_l + 2 * kvd), (int)dim, bs, sg, 3, nullptr))) return rc;
+        } else {
+            if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+            PsRwmArgs a{};
+            a.w = ld.rw_qkv; a.n_oct = (int)((qdim_l + 2 * kvd) / 8); a.K = (int)dim; a.slot = 0; a.n_slots = 1; a.n_seg = 3; a.bs = bs;
+            for (int t = 0; t < 3; t++) a.seg[t] = sg[t];
+            if ((rc = launch_rwm(ctx, a))) return rc;
+        }
+        ps_k_rope<<<dim3((unsigned)nh, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->qr, ctx->q, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_rope<<<dim3((unsigned)nkv, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
+        PS_LAUNCH_CK();
+        if (bs >= 8) {
+            const int r2 = (int)(nh / nkv);
+            const int qb = std::max(1, std::min(bs, (int)(8192 / (r2 * hs))));
+            ps_k_attn_scores_batch<<<dim3((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb)), 128, (size_t)qb * r2 * hs * 4, ctx->stream>>>(
+                ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs, qb);
+        } else {
+            ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
+        }
+        PS_LAUNCH_CK();
+        ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
+        PS_LAUNCH_CK();
+        if ((size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
+            static bool pv_attr[64] = {};
+            if (!pv_attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr[ctx->device] = true; }
+            ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
+                ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        } else {
+            ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
+        }
+        PS_LAUNCH_CK();
+        if ((rc = tp_gather_rows(ctx, attb, ctx->att, bs, qdim_l))) return rc;                      // exchange 1: attention output
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, attb, (int)qdim, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_o, (int)dim_l, (int)qdim, xl, bs, xl))) return rc;       // x[rows of this rank] += Wo[rows] . att
+        } else {
+            if ((rc = rwm_quantize(ctx, attb, (int)qdim, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_o, (int)dim_l, (int)qdim, 0, 1, xl, bs, nullptr, xl))) return rc;
+        }
+        if ((rc = tp_gather_rows(ctx, x, xl, bs, dim_l))) return rc;                                   // exchange 2: x after Wo
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, x, ld.ffn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_gate, (int)ffn_l, (int)dim, ctx->g, bs, nullptr))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_up, (int)ffn_l, (int)dim, ctx->u, bs, nullptr))) return rc;
+        } else {
+            if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn_l, (int)dim, 0, 2, ctx->g, bs, nullptr, nullptr))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_gu, (int)ffn_l, (int)dim, 1, 2, ctx->u, bs, nullptr, nullptr))) return rc;
+        }
+        ps_k_silu_hadamard<<<grid1d(ffn_l * bs), 256, 0, ctx->stream>>>(ctx->g, ctx->g, ctx->u, ffn_l * bs);
+        PS_LAUNCH_CK();
+        if ((rc = tp_gather_rows(ctx, hb, ctx->g, bs, ffn_l))) return rc;                             // exchange 3: FFN hidden vector
+        if (tc) {
+            if ((rc = tc_prep_b(ctx, hb, (int)ffn, bs))) return rc;
+            if ((rc = tc_single(ctx, ld.tc_down, (int)dim_l, (int)ffn, xl, bs, xl))) return rc;     // x[rows] += Wdown[rows] . h
+        } else {
+            if ((rc = rwm_quantize(ctx, hb, (int)ffn, bs))) return rc;
+            if ((rc = rwm_single(ctx, ld.rw_down, (int)dim_l, (int)ffn, 0, 1, xl, bs, nullptr, xl))) return rc;
+        }
+        if ((rc = tp_gather_rows(ctx, x, xl, bs, dim_l))) return rc;                                   // exchange 4: x after Wdown
+    }
+    if (lm_head) {
+        if (!ctx->tp_rows && (rc = dev_alloc(ctx, (void **)&ctx->tp_rows, (size_t)d.max_batch * d.vocab_size * 4))) return rc;
+        ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, x, ctx->w_out_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
+        if ((rc = rwm_single(ctx, ctx->rw_out, (int)vocab_l, (int)dim, 0, 1, ctx->tp_logl, bs, nullptr, nullptr))) return rc;
+        if ((rc = tp_gather_rows(ctx, ctx->tp_rows, ctx->tp_logl, bs, vocab_l))) return rc;
+    }
+    return 0;
+}
+
+
 static int check_forward_args(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs) {
     if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: no model bound");
     if (bs <= 0 || bs > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: batch %d outside [1,%d]", bs, ctx->d.max_batch);
@@ -1578,8 +1716,13 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     ctx->h2d += (int64_t)bs * 8;
     PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
     ctx->logits_last = ctx->logits;
-    if (ctx->tp > 1 && bs > 1) {
-        // tensor parallel: the sharded path exists for the fused single-token step only; a batch is fed token by token, i.e.
+    if (ctx->tp > 1 && bs > 1 && ctx->nccl_comm && ctx->opt_tp_batch) {
+        // tensor parallel batch (prefill chunk / verify batch): row-sharded GEMMs, one all-gather per exchange for the whole chunk
+        if (lm_head && !ctx->tp_logl) { int rc2 = dev_alloc(ctx, (void **)&ctx->tp_logl, (size_t)ctx->d.max_batch * ctx->vocab_l * 4); if (rc2) return rc2; }
+        rc = forward_ops_tp(ctx, bs, lm_head, pos[0]);
+        if (lm_head) ctx->logits_last = ctx->tp_rows;
+    } else if (ctx->tp > 1 && bs > 1) {
+        // tensor parallel without NCCL (or option tp_batch = 0): the sharded single-token step is fed token by token, i.e.
         // it equals the reference run with batch_size = 1 (NOT a batched pass: the reference's soft-max row length and its
         // SIMD / libm exp split depend on the chunking)
         for (int i = 0; i < bs && !rc; i++) {
@@ -1871,6 +2014,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "cta_trace")) ctx->opt_cta_trace = value;
     else if (!strcmp(name, "rw_kb")) ctx->opt_kb = value; // tuning: cap on the blocks per TMA stage of the row-walker mat-vec
     else if (!strcmp(name, "tp_ll")) ctx->opt_ll = value;
+    else if (!strcmp(name, "tp_batch")) ctx->opt_tp_batch = value;
     else if (!strcmp(name, "tp_p2p")) ctx->p2p = value && ctx->peer_heap[ctx->tp > 1 ? (ctx->rank + 1) % ctx->tp : 0] != nullptr;
     else if (!strcmp(name, "trace")) {
         if (value && !ctx->trace_dev) {

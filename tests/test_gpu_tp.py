@@ -40,14 +40,15 @@ def test_tp_decode_bit_exact(preset, size, mode):
         assert all(p.returncode == 0 for p in procs), "\n".join(outs)
         res = [np.load(os.path.join(td, f"out.rank{r}.npz")) for r in range(size)]
     prompt = synth.random_prompt(synth.PRESETS[preset].vocab_size, n_prompt, seed=11)
-    # the sharded path feeds a prefill chunk token by token, i.e. it equals the reference run with batch_size = 1 (the
-    # reference's own results depend on the chunking: ggml_vec_soft_max_f32 uses its SIMD exp for full 8-groups of the
-    # row and libm expf for the tail, and the row length is the chunk's last position + 1)
+    # a tensor-parallel batch (prefill chunk of 16, verify-shaped batch of 6) runs as batched row-sharded GEMMs with one
+    # all-gather per exchange: it must equal the reference run with the SAME chunking (the reference's results depend on
+    # it: ggml_vec_soft_max_f32 uses its SIMD exp for full 8-groups of a row and libm expf for the tail, and the row length
+    # is the chunk's last position + 1)
     om = M.OracleModel(d)
-    ids_o, lg_o = om.generate(prompt, 4, batch_size=1)
-    ids_long, _ = om.generate(prompt, n_dec, batch_size=1)
+    ids_o, lg_o = om.generate(prompt, 4, batch_size=16)
+    ids_long, _ = om.generate(prompt, n_dec, batch_size=16)
     om.reset()
-    rows_o = np.stack([om.forward([int(t)])[0] for t in prompt[:6]])   # a tensor-parallel batch == the same tokens one by one
+    rows_o = om.forward(prompt[:6])
     om.close()
     for r in res:
         assert list(r["ids"]) == ids_o
