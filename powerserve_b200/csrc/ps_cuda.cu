@@ -109,7 +109,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -376,6 +376,7 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     const int grid = std::min(ctx->n_sm, a.n_oct);
     const int per_cta = (a.n_oct + grid - 1) / grid;
     a.n_act = std::min(PS_RW_WARPS, per_cta);
+    a.unroll2 = (ctx->opt_unroll2 && per_cta <= 8) ? 1 : 0;
     // stage = kb octet-blocks: the largest divisor of nb (<= 16 blocks, option "rw_kb") that leaves every warp a ring of
     // >= 2 stages; a stage boundary (mbarrier wait + re-arm) costs the consuming warp ~150-250 cycles, so fewer is better
     const size_t unit = (size_t)rpt * PS_RW_OCTET_BLOCK, fixed = (size_t)a.K + (size_t)nb * 32, budget = 200 * 1024;
@@ -2005,6 +2006,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         ctx->opt_fused = value;
     }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA
     else if (!strcmp(name, "attn_fused")) ctx->opt_attn_fused = value; // 1: decode attention as ONE cluster kernel per layer (bit-exact, but slower so far: DESIGN.md); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "l2_ahead")) ctx->opt_l2_ahead = value;     // tuning: L2 look-ahead of the step kernel's weight stream, in 4736-byte stages per CTA
     else if (!strcmp(name, "attn_chunk")) ctx->opt_attn_chunk = value; // testing: soft-max positions resident in shared memory (multiple of 256)

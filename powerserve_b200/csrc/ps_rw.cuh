@@ -70,6 +70,7 @@ struct PsRwArgs {
     const unsigned long long *x_ll; // tensor parallel, in-band flags (else null): x as (value, epoch) words; replaces `x` and `tpi`
     const uint32_t *x_epoch;        //   the epoch those words must carry (local counter of the producing slot)
     int *tp_err;                    //   set to 1 if a poll gave up
+    int unroll2;           // walk two blocks per loop trip (launches with few octets per CTA: latency-bound lone warps)
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
     long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (options "trace" + "cta_trace" = launch kind)
@@ -356,13 +357,24 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             ps_mbar_wait(&my_bar[slot], phase);
             if (a.tl) wcyc += clock64() - c0;
             const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
+            if (RPT == 1 && a.unroll2) {
+                // few octets per CTA (q|k|v, o, down): a warp walks its row alone on its scheduler and every block is a chain of
+                // dependent shared-memory loads - two blocks per trip let the loads of one overlap the integer math of the other
+                // (the fp32 chains still advance block by block, in row order)
+#pragma unroll 2
+                for (int b = 0; b < kb; b++) {
+                    const int i = sb * kb + b;
+                    ps_rw_block(st + (size_t)b * PS_RW_OCTET_BLOCK, r, q, moff, s_qa + (size_t)i * 16, s_meta[i * 4 + q], acc[0]);
+                }
+            } else {
 #pragma unroll 1
-            for (int b = 0; b < kb; b++) {
-                const int i = sb * kb + b;
-                const uint4 *qa = s_qa + (size_t)i * 16;
-                const uint2 meta = s_meta[i * 4 + q];
+                for (int b = 0; b < kb; b++) {
+                    const int i = sb * kb + b;
+                    const uint4 *qa = s_qa + (size_t)i * 16;
+                    const uint2 meta = s_meta[i * 4 + q];
 #pragma unroll
-                for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, moff, qa, meta, acc[t]);
+                    for (int t = 0; t < RPT; t++) ps_rw_block(st + (size_t)(b * RPT + t) * PS_RW_OCTET_BLOCK, r, q, moff, qa, meta, acc[t]);
+                }
             }
             __syncwarp();
             if (lane == 0 && s + ns < n_stages) issue(warp, s + ns); // the slot is drained: re-arm it
