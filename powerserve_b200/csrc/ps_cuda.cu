@@ -109,7 +109,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -377,15 +377,40 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     const int per_cta = (a.n_oct + grid - 1) / grid;
     a.n_act = std::min(PS_RW_WARPS, per_cta);
     a.unroll2 = (ctx->opt_unroll2 && per_cta <= 8) ? 1 : 0;
-    // stage = kb octet-blocks: the largest divisor of nb (<= 16 blocks, option "rw_kb") that leaves every warp a ring of
-    // >= 2 stages; a stage boundary (mbarrier wait + re-arm) costs the consuming warp ~150-250 cycles, so fewer is better
-    const size_t unit = (size_t)rpt * PS_RW_OCTET_BLOCK, fixed = (size_t)a.K + (size_t)nb * 32, budget = 200 * 1024;
-    const int kb_cap = std::max(1, (ctx->opt_kb > 0 ? ctx->opt_kb : 16) / rpt);
+    a.defer = (ctx->opt_defer >> kind) & 1;
+    // K-split (ps_rw.cuh): when a CTA owns fewer octets than it has warps, ks warps share an octet - the largest ks in
+    // {8, 4, 2} that still gives every octet of the CTA its own group; lm_head and gate|up have plenty of octets per CTA.
+    int ksplit = 0;
+    if (ctx->opt_ksplit > 1 && rpt == 1 && !a.part_val)
+        for (int ks = 8; ks >= 2 && !ksplit; ks >>= 1)
+            if (ks <= ctx->opt_ksplit && per_cta <= PS_RW_WARPS / ks) ksplit = ks;
+    // stage = kb octet-blocks: the largest divisor of the row's blocks (<= 16 blocks, option "rw_kb") that leaves every warp
+    // a ring of >= 2 stages (one stage is enough when it holds the warp's whole stream); a stage boundary (mbarrier wait +
+    // re-arm) costs the consuming warp ~150-250 cycles, so fewer is better - but never at the price of resident blocks.
+    // K-split: the row's stages are dealt round-robin to ks warps (stage count divisible by ks), every stage is one token hop.
+    const size_t unit = (size_t)rpt * PS_RW_OCTET_BLOCK, budget = 208 * 1024;
+    const int kb_cap0 = std::max(1, (ctx->opt_kb > 0 ? ctx->opt_kb : 16) / rpt);
+    size_t fixed = 0;
     int kb = 0, ns = 0;
-    for (int c = std::min(nb, kb_cap); c >= 1; c--) {
-        if (nb % c) continue;
-        const int n = std::min((int)((budget - fixed) / ((size_t)a.n_act * ((size_t)c * unit + 8))), PS_RW_MAX_NS);
-        if (n >= 2) { kb = c; ns = n; break; }
+    for (; !kb; ksplit = 0) { // second trip: without K-split
+        a.ksplit = ksplit;
+        const int n_grp = ksplit ? std::min(PS_RW_WARPS / ksplit, per_cta) : std::min(PS_RW_WARPS, per_cta);
+        const int kdiv = std::max(1, ksplit);
+        a.n_act = n_grp * kdiv;
+        const int rounds = (per_cta + n_grp - 1) / n_grp; // octets per warp (group)
+        int best_res = 0;
+        const int kb_cap = ksplit ? std::min(kb_cap0, PS_RW_KS_KB) : kb_cap0;
+        for (int c = std::min(nb, kb_cap); c >= 1; c--) {
+            if (nb % c || (nb / c) % kdiv) continue;
+            const size_t fx = (size_t)a.K + (size_t)nb * 32;
+            if (fx >= budget) continue;
+            const int total = rounds * (nb / c / kdiv); // stages of the busiest warp
+            const int n = std::min(std::min((int)((budget - fx) / ((size_t)a.n_act * ((size_t)c * unit + 8))), PS_RW_MAX_NS), total);
+            if (n < 1 || (n < 2 && n < total)) continue;
+            if (!ksplit) { kb = c; ns = n; fixed = fx; break; }
+            if (std::min(n * c, total * c) > best_res) { best_res = std::min(n * c, total * c); kb = c; ns = n; fixed = fx; } // K-split: most resident blocks first, then the larger stage
+        }
+        if (!ksplit) break;
     }
     if (!kb) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matvec: no room for a 2-stage ring (K=%d)", a.K);
     const size_t stage = (size_t)kb * unit;
@@ -394,10 +419,16 @@ int launch_rw_impl(ps_cuda_ctx *ctx, PsRwArgs a, int epi) {
     const size_t smem = fixed + (size_t)a.n_act * ns * (stage + 8);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
-        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_RESIDUAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_SILU>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_STORE, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_rw_matvec<PS_EPI_RESIDUAL, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 210 * 1024));
         attr[ctx->device] = true;
+    }
+    if (a.ksplit) {
+        if (epi == PS_EPI_RESIDUAL) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_RESIDUAL, true>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
+        return launch_k(ctx, ps_k_rw_matvec<PS_EPI_STORE, true>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
     }
     if (epi == PS_EPI_SILU) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_SILU>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
     if (epi == PS_EPI_RESIDUAL) return launch_k(ctx, ps_k_rw_matvec<PS_EPI_RESIDUAL>, dim3(grid), dim3(PS_RW_THREADS + 32), smem, a);
@@ -2006,6 +2037,8 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         ctx->opt_fused = value;
     }
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
+    else if (!strcmp(name, "rw_ksplit")) ctx->opt_ksplit = value;   // opt-in (default 0): most warps that may share a row octet in the mat-vec launches with few octets per CTA; bit-exact but measured 3-4 % slower per step (profiles/r02_ab_matvec_ksplit_8b_ctx2048.txt)
+    else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA
     else if (!strcmp(name, "attn_fused")) ctx->opt_attn_fused = value; // 1: decode attention as ONE cluster kernel per layer (bit-exact, but slower so far: DESIGN.md); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "l2_ahead")) ctx->opt_l2_ahead = value;     // tuning: L2 look-ahead of the step kernel's weight stream, in 4736-byte stages per CTA

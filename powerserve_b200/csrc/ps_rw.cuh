@@ -27,6 +27,7 @@
 #define PS_RW_HDR2 128                         // offset of the second header array (mins 4..7, 4 bytes per row)
 #define PS_RW_QS 160                           // offset of the four 256-byte quant groups
 #define PS_RW_MAX_NS 8
+#define PS_RW_KS_KB 4                            // K-split: most blocks per stage (their factors wait in registers for the token)
 
 enum { PS_RW_OUT_PLAIN = 0, PS_RW_OUT_ROPE = 1, PS_RW_OUT_ROPE_KCACHE = 2, PS_RW_OUT_VCACHE_T = 3 };
 
@@ -71,6 +72,8 @@ struct PsRwArgs {
     const uint32_t *x_epoch;        //   the epoch those words must carry (local counter of the producing slot)
     int *tp_err;                    //   set to 1 if a poll gave up
     int unroll2;           // walk two blocks per loop trip (launches with few octets per CTA: latency-bound lone warps)
+    int ksplit;            // K-split kernels: warps per octet (each walks nb / ksplit consecutive blocks of the row); else 0
+    int defer;             // the helper warp requests the weight stream only after the activation vector has arrived
     int idx_offset;        // added to the row index stored in part_idx (tensor parallel: first vocabulary row of this rank)
     long long *tl;         // optional timeline slot (option "trace")
     long long *cta_tl;     // optional per-CTA stream trace: [grid][8] (options "trace" + "cta_trace" = launch kind)
@@ -124,7 +127,10 @@ PS_D int ps_rw_mins_dot(uint32_t bsums_pair, uint32_t mins_pair) {
     return d;
 }
 
-PS_D void ps_rw_block(const uint8_t *ob, int r, int q, int moff, const uint4 *qa, const uint2 meta, PsRwAcc &acc) {
+// the exact integer sums of one super-block as floats (S of lanes 2q, 2q+1, P of mins lane q) and the two fp32 factors
+// d = yd * d_x, dm = -yd * dmin_x - everything the FMA chains need from the block
+PS_D void ps_rw_block_factors(const uint8_t *ob, int r, int q, int moff, const uint4 *qa, const uint2 meta, float &f0, float &f1, float &fp, float &d,
+                              float &dm) {
     const uint4 h = *reinterpret_cast<const uint4 *>(ob + 16 * r); // d | dmin, scales 0..3, scales 4..7, mins 0..3
     const uint32_t mp = *reinterpret_cast<const uint16_t *>(ob + moff);
     int S0 = 0, S1 = 0, H0 = 0, H1 = 0;
@@ -143,11 +149,19 @@ PS_D void ps_rw_block(const uint8_t *ob, int r, int q, int moff, const uint4 *qa
     S1 += H1 >> 4;
     const int P = ps_rw_mins_dot(meta.y, mp);
     const float yd = __uint_as_float(meta.x);
-    const float d = __fmul_rn(yd, ps_half_bits_to_float(h.x & 0xffffu));
-    const float dm = __fmul_rn(-yd, ps_half_bits_to_float(h.x >> 16));
-    acc.a0 = __fmaf_rn(d, __int2float_rn(S0), acc.a0);
-    acc.a1 = __fmaf_rn(d, __int2float_rn(S1), acc.a1);
-    acc.am = __fmaf_rn(dm, __int2float_rn(P), acc.am);
+    d = __fmul_rn(yd, ps_half_bits_to_float(h.x & 0xffffu));
+    dm = __fmul_rn(-yd, ps_half_bits_to_float(h.x >> 16));
+    f0 = __int2float_rn(S0);
+    f1 = __int2float_rn(S1);
+    fp = __int2float_rn(P);
+}
+
+PS_D void ps_rw_block(const uint8_t *ob, int r, int q, int moff, const uint4 *qa, const uint2 meta, PsRwAcc &acc) {
+    float f0, f1, fp, d, dm;
+    ps_rw_block_factors(ob, r, q, moff, qa, meta, f0, f1, fp, d, dm);
+    acc.a0 = __fmaf_rn(d, f0, acc.a0);
+    acc.a1 = __fmaf_rn(d, f1, acc.a1);
+    acc.am = __fmaf_rn(dm, fp, acc.am);
 }
 
 // hsum_float_8(acc) + the movehl/movehdup sum of acc_m (ggml-quants.c:62-68, 7862-7871) across the quad; every lane
@@ -200,12 +214,21 @@ PS_D void ps_rw_load8(const float *p, int lane, float e[8]) {
 // Threads: PS_RW_WARPS compute warps + one helper warp that initialises the mbarriers and fills every warp's ring
 // (lane w serves warp w) and then exits, so no compute warp ever stalls on the TMA queue during the prologue.
 // Dynamic shared memory: [qa: K bytes][meta: nb x 4 x 8][rings: n_act x ns x stage_bytes][bars: n_act x ns x 8]
-template <int EPI>
+//
+// KSPLIT (q|k|v, o, down: matrices with only 3-6 row octets per SM, where a lone warp per octet walks 16-56 blocks
+// serially at ~230 cycles each): `ksplit` warps share an octet.  The row's stages (kb blocks each) are dealt round-robin to
+// the warps of the group; a warp does the integer work of its stage (exact sums + the fp32 factors, kept in registers),
+// then waits for the octet's TOKEN - the three running FMA accumulators of every row plus a stage counter, one 16-byte
+// shared-memory word per lane - applies its kb blocks and passes the token on.  The chains therefore still advance block by
+// block in row order (the arithmetic is that of the one-warp walk); only the integer work of different stages overlaps.
+template <int EPI, bool KSPLIT = false>
 __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const PsRwArgs a) {
     constexpr int RPT = (EPI == PS_EPI_SILU) ? 2 : 1;
+    static_assert(!(KSPLIT && RPT != 1), "K-split walks one matrix");
     extern __shared__ __align__(128) uint8_t ps_rw_smem[];
     __shared__ double sh_red[PS_RW_WARPS];
     __shared__ __align__(8) uint64_t xbar;
+    __shared__ uint4 ks_tok[KSPLIT ? PS_RW_WARPS * 32 : 1]; // K-split: the tokens, [group][lane] = {a0, a1, am, stages applied}
     const int K = a.K, nb = K / 256, kb = a.kb, ns = a.ns;
     const uint32_t stage_bytes = (uint32_t)kb * RPT * PS_RW_OCTET_BLOCK;
     uint4 *s_qa = reinterpret_cast<uint4 *>(ps_rw_smem);
@@ -216,12 +239,14 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
     // this CTA's octets [o0, o1); warp w walks o0 + w, o0 + w + n_act, ...
     const int o0 = (int)(((long long)blockIdx.x * a.n_oct) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.n_oct) / gridDim.x);
-    const int spo = nb / kb;                 // stages per octet
+    // K-split: a group of `ks` warps per octet, `seg` blocks each; otherwise one warp per octet walking all nb blocks
+    const int ks = KSPLIT ? a.ksplit : 1, n_grp = a.n_act / ks;
+    const int spo = nb / kb / ks;            // stages per (octet, warp); K-split: warp k of a group owns stages k, k + ks, ...
     const size_t oct_bytes = (size_t)nb * RPT * PS_RW_OCTET_BLOCK;
-    auto stages_of = [&](int w) { return (w < a.n_act && o0 + w < o1) ? ((o1 - o0 - w - 1) / a.n_act + 1) * spo : 0; };
+    auto stages_of = [&](int w) { return (w < a.n_act && o0 + w / ks < o1) ? ((o1 - o0 - w / ks - 1) / n_grp + 1) * spo : 0; };
     auto issue = [&](int w, int s) { // request stage #s of warp w's stream into slot s % ns of its ring
-        const int oct = o0 + w + (s / spo) * a.n_act;
-        const uint8_t *src = a.w + (size_t)oct * oct_bytes + (size_t)(s % spo) * stage_bytes;
+        const int oct = o0 + w / ks + (s / spo) * n_grp;
+        const uint8_t *src = a.w + (size_t)oct * oct_bytes + (size_t)((s % spo) * ks + w % ks) * stage_bytes;
         uint64_t *bar = s_bar + w * ns + (s % ns);
         ps_mbar_expect_tx(bar, stage_bytes);
         ps_bulk_g2s(s_ring + ((size_t)w * ns + (s % ns)) * stage_bytes, src, stage_bytes, bar);
@@ -235,11 +260,15 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             for (int s = 0; s < ns; s++) ps_mbar_init(s_bar + lane * ns + s, 1);
         }
         if (lane == 0) ps_mbar_init(&xbar, 1);
+        if (KSPLIT)
+            for (int t = lane; t < PS_RW_WARPS * 32; t += 32) ks_tok[t] = make_uint4(0, 0, 0, 0);
         ps_fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         asm volatile("bar.arrive 1, %0;" ::"n"(PS_RW_THREADS + 32) : "memory"); // barriers are live
-        ps_bar_sync(3, PS_RW_THREADS + 32); // the compute warps' norm-weight loads are on their way (DRAM queues are FIFO)
+        // barrier 3: the compute warps' norm-weight loads are on their way (DRAM queues are FIFO); with `defer` they arrive
+        // only once the activation vector is in their registers, so its few KB do not queue behind ~200 KB of weights per SM
+        ps_bar_sync(3, PS_RW_THREADS + 32);
         for (int s = 0; s < ns && s < n; s++) issue(lane, s);
         return;
     }
@@ -249,7 +278,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     float wv0[8];
     const bool early_w = a.norm_w != nullptr && warp < nb;
     if (early_w) ps_rw_load8(a.norm_w + warp * 256, lane, wv0);
-    asm volatile("bar.arrive 3, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
+    if (!a.defer) asm volatile("bar.arrive 3, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(a.tl, 2);
@@ -273,6 +302,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             ps_bulk_g2s(ps_rw_smem, a.xq_in, bytes, &xbar);
         }
         ps_mbar_wait(&xbar, 0);
+        if (a.defer) asm volatile("bar.arrive 3, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
         PS_RW_PROBE(4);
     } else { // (RMSNorm) + quantize_row_q8_K, one warp per 256-block
         float e0[8];
@@ -283,6 +313,15 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             else ps_rw_load8(a.x + i * 256, lane, e);
         };
         if (have0) load_x(warp, e0);
+        if (a.defer) { // the first block of x is here (the sum below consumes it) before the weight stream is requested
+            float sink = 0.f;
+            if (have0) {
+#pragma unroll
+                for (int t = 0; t < 8; t++) sink += e0[t];
+            }
+            asm volatile("" ::"f"(sink) : "memory");
+            asm volatile("bar.arrive 3, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
+        }
         float nscale = 1.f;
         if (a.norm_w) {
             double ss = 0.0;
@@ -345,12 +384,62 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
     const int moff = ps_rw_mins_off(r, q);
     long long wcyc = 0; // trace: cycles this warp spent waiting for weight stages
     const long long c_begin = a.tl ? clock64() : 0, t_begin = a.tl ? ps_globaltimer() : 0;
+    const int grp = warp / ks, kk = warp - grp * ks; // K-split: octet group of the warp, its segment of the row
 #pragma unroll 1
     for (int m = 0; m < n_mine; m++) {
-        const int oct = o0 + warp + m * a.n_act;
+        const int oct = o0 + grp + m * n_grp;
         PsRwAcc acc[RPT];
 #pragma unroll
         for (int t = 0; t < RPT; t++) acc[t].a0 = acc[t].a1 = acc[t].am = 0.f;
+        if constexpr (KSPLIT) {
+            const int G = spo * ks; // stages of a row
+            uint4 *tok = ks_tok + grp * 32 + lane; // this lane's word of the group's token: {a0, a1, am, stages applied so far}
+#pragma unroll 1
+            for (int j = 0; j < spo; j++, s++) {
+                const int g = j * ks + kk; // this warp's stage of the row: blocks [g * kb, (g + 1) * kb)
+                const long long c0 = a.tl ? clock64() : 0;
+                ps_mbar_wait(&my_bar[slot], phase);
+                if (a.tl) wcyc += clock64() - c0;
+                const uint8_t *st = my_ring + (size_t)slot * stage_bytes;
+                // the stage's integer work, kept in registers (kb <= PS_RW_KS_KB) until the token arrives
+                float f0[PS_RW_KS_KB], f1[PS_RW_KS_KB], fp[PS_RW_KS_KB], fd[PS_RW_KS_KB], fm[PS_RW_KS_KB];
+#pragma unroll
+                for (int b = 0; b < PS_RW_KS_KB; b++) {
+                    if (b < kb) {
+                        const int i = g * kb + b;
+                        ps_rw_block_factors(st + (size_t)b * PS_RW_OCTET_BLOCK, r, q, moff, s_qa + (size_t)i * 16, s_meta[i * 4 + q], f0[b], f1[b], fp[b], fd[b],
+                                            fm[b]);
+                    }
+                }
+                __syncwarp(); // the slot is drained: re-arm it
+                if (lane == 0 && s + ns < n_stages) issue(warp, s + ns);
+                if (++slot == ns) { slot = 0; phase ^= 1; }
+                // the token: stages 0 .. g - 1 of this octet (and all stages of the group's earlier octets) are applied.  Every
+                // lane polls its own 16-byte word, whose last field is the count - value and flag travel in ONE shared-memory
+                // store, so the hop needs no fence.  (A new octet's first stage waits too: its token write must not overtake
+                // the previous octet's last reader.)
+                const uint32_t want = (uint32_t)(m * G + g);
+                if (want > 0) {
+                    uint4 t;
+                    do {
+                        asm volatile("ld.volatile.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(t.x), "=r"(t.y), "=r"(t.z), "=r"(t.w) : "r"(ps_smem_u32(tok)) : "memory");
+                    } while (t.w != want);
+                    if (g > 0) { acc[0].a0 = __uint_as_float(t.x); acc[0].a1 = __uint_as_float(t.y); acc[0].am = __uint_as_float(t.z); }
+                }
+#pragma unroll
+                for (int b = 0; b < PS_RW_KS_KB; b++) {
+                    if (b < kb) {
+                        acc[0].a0 = __fmaf_rn(fd[b], f0[b], acc[0].a0);
+                        acc[0].a1 = __fmaf_rn(fd[b], f1[b], acc[0].a1);
+                        acc[0].am = __fmaf_rn(fm[b], fp[b], acc[0].am);
+                    }
+                }
+                asm volatile("st.volatile.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(ps_smem_u32(tok)), "r"(__float_as_uint(acc[0].a0)), "r"(__float_as_uint(acc[0].a1)),
+                             "r"(__float_as_uint(acc[0].am)), "r"(want + 1)
+                             : "memory");
+            }
+            if (kk != ks - 1) continue; // the warp that applied the last stage owns the epilogue
+        } else {
 #pragma unroll 1
         for (int sb = 0; sb < spo; sb++, s++) {
             const long long c0 = a.tl ? clock64() : 0;
@@ -379,6 +468,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
             __syncwarp();
             if (lane == 0 && s + ns < n_stages) issue(warp, s + ns); // the slot is drained: re-arm it
             if (++slot == ns) { slot = 0; phase ^= 1; }
+        }
         }
         // ---- epilogue
         const int row = oct * 8 + r;

@@ -89,3 +89,22 @@ def test_step_kernel_chunked_attention():
     L.assert_bit_equal(lg_s, lg_u, "chunked attention")
     assert ids_s == ids_u and cm.be.counter("step_error") == 0
     cm.close()
+
+
+@pytest.mark.parametrize("preset", ["slice-8b", "slice-1b", "tiny-llama"])
+def test_matvec_ksplit_and_deferred_stream_are_bit_exact(preset):
+    """K-split walks (several warps share a row octet; the FMA chains travel from warp to warp as a token, stage by stage in
+    row order) and the deferred weight stream are scheduling choices: every setting must leave the table-op path's bits."""
+    d = M.model_dir(preset)
+    shape = synth.PRESETS[preset]
+    prompt = synth.random_prompt(shape.vocab_size, 41, seed=5)
+    cm = capi.CudaModel(d, max_batch=16)
+    ids_u, lg_u = run(cm, prompt, 8, fused=0, graph=0)
+    for ksplit, defer, kb in [(0, 0, 0), (2, 0, 0), (4, 62, 0), (8, 0, 0), (8, 62, 1), (4, 0, 2)]:
+        cm.be.set_option("rw_ksplit", ksplit)
+        cm.be.set_option("rw_defer", defer)
+        cm.be.set_option("rw_kb", kb)        # cap on the blocks per stage = per token hop
+        ids_f, lg_f = run(cm, prompt, 8, fused=1, graph=1)
+        L.assert_bit_equal(lg_f, lg_u, f"{preset}: rw_ksplit={ksplit} rw_defer={defer} rw_kb={kb}")
+        assert ids_f == ids_u
+    cm.close()
