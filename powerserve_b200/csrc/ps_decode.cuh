@@ -242,14 +242,16 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
                                                   const int32_t *__restrict__ pos_dev, int hs, int n_kv_heads, int n_ctx, float scale, long long *tl) {
     __shared__ float s_q[R2][256];
     ps_tl_min(tl, 0);
-    ps_grid_dep_wait();
-    ps_grid_dep_launch();
-    ps_tl_min(tl, 2);
+    // Everything this kernel reads except the query vector and cache row `pos` is older than the kernel before the
+    // previous one (pos_dev: the last kernel of the previous step; cache rows < pos: earlier steps / the prefill), and a
+    // grid can only start once its predecessor is past ITS dependency wait - so those loads are issued BEFORE the wait
+    // and their DRAM latency overlaps the tail of the q|k|v kernel.  Row `pos` (written by that kernel) follows the wait.
     const int pos = pos_dev[0];
     const int64_t n_kv = (int64_t)pos + 1;
     const int n_items = (int)((n_kv + 31) / 32) * n_kv_heads;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, steps = hs / 32;
     const int kvd = hs * n_kv_heads;
+    bool waited = false;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int chunk = item / n_kv_heads, g = item % n_kv_heads;
         const int64_t j0 = (int64_t)chunk * 32 + warp * 8;
@@ -259,8 +261,21 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 #pragma unroll
             for (int s = 0; s < 8; s++) {
                 kv[t][s] = 0.f;
-                if (s < steps && j0 + t < n_kv) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
+                if (s < steps && j0 + t < pos) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
             }
+        if (!waited) {
+            ps_grid_dep_wait();
+            ps_grid_dep_launch();
+            ps_tl_min(tl, 2);
+            waited = true;
+        }
+        if (j0 <= pos && pos < j0 + 8) { // warp-uniform: the row the q|k|v kernel has just written
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < steps && j0 + t == pos) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
+        }
         __syncthreads(); // the previous item's queries are no longer needed
         for (int idx = tid; idx < R2 * hs; idx += 128) s_q[idx / hs][idx % hs] = q[(int64_t)g * R2 * hs + idx];
         __syncthreads();
@@ -289,6 +304,11 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
             }
         }
     }
+    if (!waited) { // no item for this CTA: it still takes part in the dependency chain
+        ps_grid_dep_wait();
+        ps_grid_dep_launch();
+        ps_tl_min(tl, 2);
+    }
     ps_tl_max(tl, 1);
 }
 
@@ -316,6 +336,22 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
     }
     ps_tl_min(tl, 0);
+    // The position (last kernel of the previous step) and the V^T rows (column `pos` comes from the q|k|v kernel, which was
+    // complete before the scores kernel let this grid start) are older than this kernel's predecessor: the V^T copies are
+    // requested BEFORE the dependency wait; only the score rows follow it.
+    const int64_t n_kv = (int64_t)pos_dev[0] + 1;
+    constexpr int TPH = PS_A2_THREADS / R2, WPH = TPH / 32;          // threads / warps per head
+    const int hh = tid / TPH, ht = tid % TPH;
+    const int64_t stride = (n_kv + 31) & ~(int64_t)31;
+    const int64_t n8 = n_kv & ~(int64_t)7;
+    float *s_v = s_p + R2 * stride;
+    const int n_rows = min(8, hs - (int)blockIdx.x * 8);
+    // rows are 16-byte aligned (n_ctx % 4 == 0); a copy may run up to 3 floats past n_kv, still inside its row
+    const uint32_t bytes = (uint32_t)(((n_kv + 3) & ~(int64_t)3) * 4);
+    if (tid == 0 && v_smem) {
+        ps_mbar_expect_tx(&bar_v, bytes * n_rows);
+        for (int w = 0; w < n_rows; w++) ps_bulk_g2s(s_v + w * stride, vct + ((int64_t)g * hs + blockIdx.x * 8 + w) * n_ctx, bytes, &bar_v);
+    }
     ps_grid_dep_wait();
     ps_grid_dep_launch();
     ps_tl_min(tl, 2);
@@ -325,22 +361,10 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
     do {                                                                                                                 \
         if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
     } while (0)
-    const int64_t n_kv = (int64_t)pos_dev[0] + 1;
-    constexpr int TPH = PS_A2_THREADS / R2, WPH = TPH / 32;          // threads / warps per head
-    const int hh = tid / TPH, ht = tid % TPH;
-    const int64_t stride = (n_kv + 31) & ~(int64_t)31;
-    const int64_t n8 = n_kv & ~(int64_t)7;
-    float *s_v = s_p + R2 * stride;
-    const int n_rows = min(8, hs - (int)blockIdx.x * 8);
-    if (tid == 0) { // rows are 16-byte aligned (n_ctx % 4 == 0); a copy may run up to 3 floats past n_kv, still inside its row
-        const uint32_t bytes = (uint32_t)(((n_kv + 3) & ~(int64_t)3) * 4);
+    if (tid == 0) {
         ps_mbar_expect_tx(&bar_s, bytes * R2);
 #pragma unroll
         for (int h2 = 0; h2 < R2; h2++) ps_bulk_g2s(s_p + h2 * stride, sc + (int64_t)(g * R2 + h2) * n_ctx, bytes, &bar_s);
-        if (v_smem) {
-            ps_mbar_expect_tx(&bar_v, bytes * n_rows);
-            for (int w = 0; w < n_rows; w++) ps_bulk_g2s(s_v + w * stride, vct + ((int64_t)g * hs + blockIdx.x * 8 + w) * n_ctx, bytes, &bar_v);
-        }
     }
     __syncthreads(); // the barrier words are initialised for everybody
     ps_mbar_wait(&bar_s, 0);
