@@ -109,6 +109,19 @@ int ps_cuda_attn_pv(ps_cuda_ctx *ctx, float *out, const float *v_cache_t, const 
 int ps_cuda_copy_2d(ps_cuda_ctx *ctx, void *dst, int64_t dst_stride0, int64_t dst_stride1, const void *src,
                     int64_t src_stride0, int64_t src_stride1, int64_t ne0, int64_t ne1);
 
+/* the same for views of up to four dims whose shapes may differ (GGMLBackend::cont of a permuted view, copy into a
+ * cache view; ggml_wrapper.cpp:135-161 -> powerserve_compute_forward_dup, ggml.c:9519-9558): element t of the source in
+ * its row-major order lands on element t of the destination; shapes in elements, strides in bytes */
+int ps_cuda_copy_4d(ps_cuda_ctx *ctx, void *dst, const int64_t dst_ne[4], const int64_t dst_nb[4], const void *src,
+                    const int64_t src_ne[4], const int64_t src_nb[4]);
+/* GGMLBackend::matmul with an FP32 src0 (ggml_wrapper.cpp:20-40 -> vec_dot_f32; the attention products over strided
+ * cache views, norm_attention.cpp:117-147): dst {ne01, ne11, ne12} contiguous; src0 {ne00, ne01, ne02}, src1 {ne00, ne11,
+ * ne12}, ne12 % ne02 == 0 (GQA broadcast, ggml.c:13365); innermost dims contiguous, nb* in bytes */
+int ps_cuda_matmul_f32(ps_cuda_ctx *ctx, float *dst, const void *src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01,
+                       int64_t nb02, const void *src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12);
+/* GGMLBackend::softmax (ggml_wrapper.cpp:57-69 -> powerserve_compute_forward_soft_max, ggml.c:15060-15089): scale 1, no mask */
+int ps_cuda_softmax(ps_cuda_ctx *ctx, float *dst, const float *x, int64_t ne0, int64_t n_rows);
+
 /* ---------------------------------------------------------------------------------------------- KV cache
  * Device implementation of the position bookkeeping of KVCacheInterface (src/core/kv_cache.hpp:97-163) that
  * Platform::get/reset_kv_position (src/backend/platform.cpp:34-50) and LlamaModel::forward (:84-86,109) use. */

@@ -81,6 +81,9 @@ def load_library() -> C.CDLL:
         "ps_cuda_attn_scores": (ci, [vp, fp, fp, fp, i64, i64, i64, i64, i64]),
         "ps_cuda_attn_pv": (ci, [vp, fp, fp, fp, i64, i64, i64, i64, i64, i64]),
         "ps_cuda_copy_2d": (ci, [vp, vp, i64, i64, vp, i64, i64, i64, i64]),
+        "ps_cuda_copy_4d": (ci, [vp, vp, C.POINTER(i64), C.POINTER(i64), vp, C.POINTER(i64), C.POINTER(i64)]),
+        "ps_cuda_matmul_f32": (ci, [vp, fp, vp, i64, i64, i64, i64, i64, vp, i64, i64, i64, i64]),
+        "ps_cuda_softmax": (ci, [vp, fp, fp, i64, i64]),
         "ps_cuda_kv_position": (ci, [vp]),
         "ps_cuda_kv_reset": (ci, [vp]),
         "ps_cuda_kv_truncate": (ci, [vp, ci]),
@@ -234,6 +237,18 @@ class CudaBackend:
     def copy_2d(self, dst, ds0, ds1, src, ss0, ss1, ne0, ne1):
         """GGMLBackend::copy / cont on 2-D fp32 views (byte strides; powerserve_compute_forward_dup)."""
         self._ck(self.L.ps_cuda_copy_2d(self.h, dst.ptr, ds0, ds1, src.ptr, ss0, ss1, ne0, ne1))
+
+    def copy_4d(self, dst, dst_ne, dst_nb, src, src_ne, src_nb, dst_off=0, src_off=0):
+        """GGMLBackend::copy / cont on views of up to four dims whose shapes may differ (shapes in elements, strides in bytes)."""
+        a = lambda v: (C.c_int64 * 4)(*[int(x) for x in v])
+        self._ck(self.L.ps_cuda_copy_4d(self.h, dst.ptr + dst_off, a(dst_ne), a(dst_nb), src.ptr + src_off, a(src_ne), a(src_nb)))
+
+    def matmul_f32(self, dst, src0, ne00, ne01, ne02, nb01, nb02, src1, ne11, ne12, nb11, nb12):
+        """GGMLBackend::matmul with an FP32 src0 over strided views (the attention products of the unfused graph)."""
+        self._ck(self.L.ps_cuda_matmul_f32(self.h, dst.ptr, src0.ptr, ne00, ne01, ne02, nb01, nb02, src1.ptr, ne11, ne12, nb11, nb12))
+
+    def softmax(self, out, x, ne0, n_rows):
+        self._ck(self.L.ps_cuda_softmax(self.h, out.ptr, x.ptr, ne0, n_rows))
 
     def read_device(self, dev_ptr: int, n_floats: int, dtype=np.float32) -> np.ndarray:
         out = np.empty(n_floats, dtype=dtype)

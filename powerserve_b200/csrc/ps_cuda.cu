@@ -14,6 +14,7 @@
 #include <mutex>
 #include <string>
 #include <unordered_map>
+#include <unordered_set>
 #include <vector>
 
 #define PS_TL_SLOTS 512
@@ -78,6 +79,7 @@ struct ps_cuda_ctx {
     std::mutex mu; // one in-flight generation per context (SURVEY 8b "Threading")
     std::unordered_map<const void *, DevWeight> weights;
     std::vector<void *> owned; // every cudaMalloc we must free
+    std::unordered_set<void *> pooled; // ps_cuda_malloc blocks: stream-ordered pool (CUDABuffer intermediates come and go every forward pass)
     // model binding
     bool bound = false;
     const uint8_t *w_embd = nullptr, *w_out = nullptr;
@@ -1025,6 +1027,8 @@ void ps_cuda_destroy(ps_cuda_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (void *p : ctx->pooled) cudaFreeAsync(p, ctx->stream);
+    cudaStreamSynchronize(ctx->stream);
     for (void *p : ctx->owned) cudaFree(p);
     if (ctx->h_tokens) cudaFreeHost(ctx->h_tokens);
     if (ctx->h_pos) cudaFreeHost(ctx->h_pos);
@@ -1052,12 +1056,31 @@ int ps_cuda_sync(ps_cuda_ctx *ctx) {
 void *ps_cuda_stream(ps_cuda_ctx *ctx) { return (void *)ctx->stream; }
 
 // ---------------------------------------------------------------------------------------------- memory
+// CUDABuffer backing for graph intermediates: the executor allocates and frees ~30 tensors per layer on every forward pass
+// (executor.cpp:23-45, cpu_buffer.hpp:41-51), so these come from the device's stream-ordered memory pool - freed blocks are
+// cached by the pool (release threshold: never) and handed out again in stream order, without a device synchronisation.
 int ps_cuda_malloc(ps_cuda_ctx *ctx, size_t bytes, void **dev) {
     PS_CK(cudaSetDevice(ctx->device));
-    return dev_alloc(ctx, dev, bytes);
+    static bool pool_set[64] = {};
+    if (!pool_set[ctx->device]) {
+        cudaMemPool_t pool;
+        PS_CK(cudaDeviceGetDefaultMemPool(&pool, ctx->device));
+        unsigned long long keep = ~0ull;
+        PS_CK(cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep));
+        pool_set[ctx->device] = true;
+    }
+    *dev = nullptr;
+    cudaError_t e = cudaMallocAsync(dev, std::max<size_t>(bytes, 256), ctx->stream);
+    if (e != cudaSuccess) return fail(ctx, PS_CUDA_ERR_OOM, "ps_cuda_malloc(%zu): %s", bytes, cudaGetErrorString(e));
+    ctx->pooled.insert(*dev);
+    return 0;
 }
 
 int ps_cuda_free(ps_cuda_ctx *ctx, void *dev) {
+    if (ctx->pooled.erase(dev)) {
+        PS_CK(cudaFreeAsync(dev, ctx->stream));
+        return 0;
+    }
     for (size_t i = 0; i < ctx->owned.size(); i++)
         if (ctx->owned[i] == dev) {
             PS_CK(cudaStreamSynchronize(ctx->stream));
@@ -1215,6 +1238,41 @@ int ps_cuda_attn_pv(ps_cuda_ctx *ctx, float *out, const float *v_cache_t, const 
 
 int ps_cuda_copy_2d(ps_cuda_ctx *ctx, void *dst, int64_t ds0, int64_t ds1, const void *src, int64_t ss0, int64_t ss1, int64_t ne0, int64_t ne1) {
     ps_k_copy_2d<<<grid1d(ne0 * ne1), 256, 0, ctx->stream>>>((uint8_t *)dst, ds0, ds1, (const uint8_t *)src, ss0, ss1, ne0, ne1);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_copy_4d(ps_cuda_ctx *ctx, void *dst, const int64_t dst_ne[4], const int64_t dst_nb[4], const void *src, const int64_t src_ne[4],
+                    const int64_t src_nb[4]) {
+    PsNd d, s;
+    int64_t nd = 1, ns = 1;
+    for (int k = 0; k < 4; k++) {
+        d.ne[k] = dst_ne[k]; d.nb[k] = dst_nb[k]; s.ne[k] = src_ne[k]; s.nb[k] = src_nb[k];
+        if (dst_ne[k] <= 0 || src_ne[k] <= 0) return fail(ctx, PS_CUDA_ERR_INVALID, "copy_4d: empty dimension");
+        nd *= dst_ne[k]; ns *= src_ne[k];
+    }
+    if (nd != ns) return fail(ctx, PS_CUDA_ERR_INVALID, "copy_4d: %lld elements into %lld", (long long)ns, (long long)nd);
+    ps_k_copy_4d<<<grid1d(ns), 256, 0, ctx->stream>>>((uint8_t *)dst, d, (const uint8_t *)src, s, ns);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_matmul_f32(ps_cuda_ctx *ctx, float *dst, const void *src0, int64_t ne00, int64_t ne01, int64_t ne02, int64_t nb01, int64_t nb02,
+                       const void *src1, int64_t ne11, int64_t ne12, int64_t nb11, int64_t nb12) {
+    if (ne00 <= 0 || ne01 <= 0 || ne02 <= 0 || ne11 <= 0 || ne12 <= 0 || ne12 % ne02)
+        return fail(ctx, PS_CUDA_ERR_INVALID, "matmul_f32: src1 heads (%lld) must be a multiple of src0 heads (%lld)", (long long)ne12, (long long)ne02);
+    const int64_t n_out = ne01 * ne11 * ne12;
+    ps_k_matmul_f32<<<(unsigned)std::min<int64_t>((n_out + 3) / 4, 1 << 20), 128, 0, ctx->stream>>>(dst, (const uint8_t *)src0, ne00, ne01, ne02, nb01, nb02,
+                                                                                                    (const uint8_t *)src1, ne11, ne12, nb11, nb12);
+    PS_LAUNCH_CK();
+    return 0;
+}
+
+int ps_cuda_softmax(ps_cuda_ctx *ctx, float *dst, const float *x, int64_t ne0, int64_t n_rows) {
+    if (ne0 * 4 > 160 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "softmax: row of %lld exceeds shared memory", (long long)ne0);
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[ctx->device] = true; }
+    ps_k_softmax_ext<<<(unsigned)n_rows, 256, (size_t)ne0 * 4, ctx->stream>>>(dst, x, nullptr, nullptr, ne0, 1, 1.0f);
     PS_LAUNCH_CK();
     return 0;
 }

@@ -603,7 +603,8 @@ __global__ void __launch_bounds__(128) ps_k_attn_scores(float *__restrict__ kq, 
 }
 
 // ggml_compute_forward_soft_max_f32 (ggml.c:14846-14940) + ggml_vec_soft_max_f32 AVX2 branch (:2814-2868).
-// One CTA per row of {ne0, ne1, ne2}.  mask == nullptr -> the position mask of GET_MASK is applied from `pos`.
+// One CTA per row of {ne0, ne1, ne2}.  mask == nullptr -> the position mask of GET_MASK is applied from `pos`; both
+// nullptr -> no mask at all (GGMLBackend::softmax: ggml_compute_forward_soft_max_f32 with src1 == NULL).
 __global__ void __launch_bounds__(256) ps_k_softmax_ext(float *__restrict__ dst, const float *__restrict__ x, const float *__restrict__ mask,
                                                         const int32_t *__restrict__ pos, int64_t ne0, int64_t ne1, float scale) {
     extern __shared__ float wp[];
@@ -614,8 +615,9 @@ __global__ void __launch_bounds__(256) ps_k_softmax_ext(float *__restrict__ dst,
     float *dp = dst + row * ne0;
     float mx = -INFINITY;
     for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) {
-        const float m = mask ? mask[i1 * ne0 + j] : ((j <= (int64_t)pos[i1]) ? 0.f : -INFINITY);
-        const float v = __fadd_rn(__fmul_rn(sp[j], scale), m); // ggml_vec_scale_f32 then `wp[i] += slope*mp[i]`, slope == 1
+        float v = __fmul_rn(sp[j], scale);
+        if (mask) v = __fadd_rn(v, mask[i1 * ne0 + j]);
+        else if (pos) v = __fadd_rn(v, (j <= (int64_t)pos[i1]) ? 0.f : -INFINITY); // ggml_vec_scale_f32 then `wp[i] += slope*mp[i]`, slope == 1
         wp[j] = v;
         mx = fmaxf(mx, v);
     }
@@ -808,6 +810,46 @@ __global__ void ps_k_copy_2d(uint8_t *__restrict__ dst, int64_t ds0, int64_t ds1
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < ne0 * ne1; t += (int64_t)gridDim.x * blockDim.x) {
         const int64_t i0 = t % ne0, i1 = t / ne0;
         *reinterpret_cast<float *>(dst + i0 * ds0 + i1 * ds1) = *reinterpret_cast<const float *>(src + i0 * ss0 + i1 * ss1);
+    }
+}
+
+// powerserve_compute_forward_dup (ggml.c:9519-9558) for fp32 views of up to four dims with byte strides and possibly
+// different shapes (GGMLBackend::copy / cont): element t of the source in ITS row-major order goes to element t of the
+// destination in the destination's order - what dup does when the shapes differ but the element counts agree.
+struct PsNd { int64_t ne[4], nb[4]; };
+__global__ void ps_k_copy_4d(uint8_t *__restrict__ dst, const PsNd d, const uint8_t *__restrict__ src, const PsNd s, int64_t n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x) {
+        int64_t r = t, so = 0, doff = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { so += (r % s.ne[k]) * s.nb[k]; r /= s.ne[k]; }
+        r = t;
+#pragma unroll
+        for (int k = 0; k < 4; k++) { doff += (r % d.ne[k]) * d.nb[k]; r /= d.ne[k]; }
+        *reinterpret_cast<float *>(dst + doff) = *reinterpret_cast<const float *>(src + so);
+    }
+}
+
+// GGMLBackend::matmul with an FP32 src0 (the two attention products over strided cache views, norm_attention.cpp:117-147 ->
+// powerserve_compute_forward_mul_mat with vec_dot_f32, ggml.c:13344-13432, 2092-2131): dst{ne01, ne11, ne12} (contiguous) =
+// dot over ne00 of src0 row (i01, i12 / r2) and src1 column (i11, i12); innermost dims contiguous, byte strides otherwise.
+// One warp per output element: lane t = 8 j + l is lane l of accumulator j (GGML_F32_STEP 32, GGML_F32_EPR 8), then
+// GGML_F32x8_REDUCE and the leftovers in order (mul, then add).  The op-by-op executor path: a bring-up / debug path.
+__global__ void __launch_bounds__(128) ps_k_matmul_f32(float *__restrict__ dst, const uint8_t *__restrict__ a, int64_t ne00, int64_t ne01, int64_t ne02,
+                                                       int64_t nb01, int64_t nb02, const uint8_t *__restrict__ b, int64_t ne11, int64_t ne12,
+                                                       int64_t nb11, int64_t nb12) {
+    const int lane = threadIdx.x & 31;
+    const int64_t n_out = ne01 * ne11 * ne12, r2 = ne12 / ne02, np = ne00 & ~(int64_t)31;
+    for (int64_t o = (int64_t)blockIdx.x * 4 + (threadIdx.x >> 5); o < n_out; o += (int64_t)gridDim.x * 4) {
+        const int64_t i01 = o % ne01, i11 = (o / ne01) % ne11, i12 = o / (ne01 * ne11);
+        const float *x = reinterpret_cast<const float *>(a + i01 * nb01 + (i12 / r2) * nb02);
+        const float *y = reinterpret_cast<const float *>(b + i11 * nb11 + i12 * nb12);
+        float sum = 0.f;
+        for (int64_t s = 0; s < np; s += 32) sum = __fmaf_rn(x[s + lane], y[s + lane], sum);
+        sum = ps_f32x8_reduce(sum);
+        if (lane == 0) {
+            for (int64_t j = np; j < ne00; j++) sum = __fadd_rn(sum, __fmul_rn(x[j], y[j]));
+            dst[o] = sum;
+        }
     }
 }
 

@@ -65,7 +65,7 @@ auto Graph::qnn_forward(""")
 
 
 def patch_executor(s):
-    return sub(s, "#if defined(POWERSERVE_WITH_QNN)\n        case OpType::QNN_FORWARD: {", """#if defined(POWERSERVE_WITH_CUDA)
+    s = sub(s, "#if defined(POWERSERVE_WITH_QNN)\n        case OpType::QNN_FORWARD: {", """#if defined(POWERSERVE_WITH_CUDA)
         case OpType::CUDA_FORWARD: {
             auto &params = op->get_params<CUDAForwardParams>();
             m_platform.cuda_backends[model_id]->forward(op->output(), params.tokens, params.pos, params.lm_head);
@@ -74,6 +74,25 @@ def patch_executor(s):
 
 #if defined(POWERSERVE_WITH_QNN)
         case OpType::QNN_FORWARD: {""")
+    # op-by-op mode: the unfused graph runs on the device, one CUDABackend method per op (buffer type decides the backend)
+    s = sub(s, "void Executor::allocate_buffers() {\n", """void Executor::allocate_buffers() {
+#if defined(POWERSERVE_WITH_CUDA)
+    if (auto it = m_platform.cuda_backends.find(m_graph.m_model_id);
+        it != m_platform.cuda_backends.end() && it->second->per_op()) {
+        it->second->allocate_buffers(m_graph); // CUDABuffers instead of CPUBuffers
+        return;
+    }
+#endif
+""")
+    return sub(s, "    auto &model_id = m_graph.m_model_id;\n    plan();\n", """    auto &model_id = m_graph.m_model_id;
+#if defined(POWERSERVE_WITH_CUDA)
+    if (auto it = m_platform.cuda_backends.find(model_id); it != m_platform.cuda_backends.end() && it->second->per_op()) {
+        it->second->run(m_graph); // the same switch over OpType, dispatched to the CUDABackend operator table
+        return;
+    }
+#endif
+    plan();
+""")
 
 
 def patch_platform_hpp(s):
@@ -109,24 +128,43 @@ void Platform::init_qnn_backend""")
 
 
 def patch_model_forward(s):
-    # LlamaModel::forward / Qwen2Model::forward: the whole forward pass becomes ONE graph op, like g.qnn_forward
+    # LlamaModel::forward / Qwen2Model::forward: the whole forward pass becomes ONE graph op, like g.qnn_forward - or, in
+    # op-by-op mode, the usual graph is built over the DEVICE caches and executed by the CUDABackend operator table
     s = sub(s, "    auto &llm_config = m_config->llm;\n\n#if defined(POWERSERVE_WITH_QNN)\n", """    auto &llm_config = m_config->llm;
 
 #if defined(POWERSERVE_WITH_CUDA)
-    const bool use_cuda = m_platform->cuda_backends.count(m_config->model_id) > 0;
+    const bool have_cuda    = m_platform->cuda_backends.count(m_config->model_id) > 0;
+    const bool use_cuda_ops = have_cuda && m_platform->cuda_backends.at(m_config->model_id)->per_op();
+    const bool use_cuda     = have_cuda && !use_cuda_ops;
     if (use_cuda) {
         logits = g.cuda_forward(tokens, pos, llm_config.vocab_size, lm_head);
     } else
 #endif
 #if defined(POWERSERVE_WITH_QNN)
 """)
-    return sub(s, "#if defined(POWERSERVE_WITH_QNN)\n    if (!m_platform->qnn_backend)\n#endif\n    {", """#if defined(POWERSERVE_WITH_CUDA)
-    if (!use_cuda)
+    s = sub(s, "                auto [k_cache, v_cache] = m_platform->ggml_backends[m_config->model_id]->m_kv->get_cache(L);\n", """#if defined(POWERSERVE_WITH_CUDA)
+                auto [k_cache, v_cache] = use_cuda_ops ? m_platform->cuda_backends[m_config->model_id]->get_cache(L)
+                                                       : m_platform->ggml_backends[m_config->model_id]->m_kv->get_cache(L);
+#else
+                auto [k_cache, v_cache] = m_platform->ggml_backends[m_config->model_id]->m_kv->get_cache(L);
+#endif
+""")
+    s = sub(s, "#if defined(POWERSERVE_WITH_QNN)\n    if (!m_platform->qnn_backend)\n#endif\n    {", """#if defined(POWERSERVE_WITH_CUDA)
+    if (use_cuda_ops) {
+        m_platform->cuda_backends[m_config->model_id]->advance(batch_size);
+    } else if (!use_cuda)
 #endif
 #if defined(POWERSERVE_WITH_QNN)
     if (!m_platform->qnn_backend)
 #endif
     {""")
+    return sub(s, "    return LogitsVector(logits->m_data, m_config->llm.vocab_size, batch_size);\n", """#if defined(POWERSERVE_WITH_CUDA)
+    if (use_cuda_ops) { // the logits tensor lives on the device; LogitsVector reads a CPUBuffer (model.hpp:27-40)
+        return LogitsVector(m_platform->cuda_backends[m_config->model_id]->download(logits), m_config->llm.vocab_size, batch_size);
+    }
+#endif
+    return LogitsVector(logits->m_data, m_config->llm.vocab_size, batch_size);
+""")
 
 
 # ---- Q4_K / Q6_K enablement (SURVEY F1): the reference's DataType layer rejects the K-quants its vendored ggml supports;

@@ -2,6 +2,10 @@
 #include "cuda_backend.hpp"
 
 #include "backend/ggml/ggml.hpp" // convert_datatype_to_ggml
+#include "graph/graph.hpp"
+
+#include <cstdio>
+#include <cstdlib>
 
 namespace powerserve::cuda {
 
@@ -29,6 +33,16 @@ CUDABackend::CUDABackend(const ModelConfig::LLMConfig &c, const HyperParams &hpa
     d.max_batch = (int)hparams.batch_size;
     d.tp_rank = 0; d.tp_size = 1;
     if (ps_cuda_create(&m_ctx, device, &d) != 0) POWERSERVE_ABORT("cuda backend: {}", ps_cuda_last_error(nullptr));
+    if (const char *e = getenv("POWERSERVE_CUDA_PER_OP")) m_per_op = atoi(e) != 0;
+    // the device caches in the shape / strides GGMLKV gives its tensors (ggml_kv_cache.cpp:35-58)
+    const size_t kv_dim = c.n_kv_heads * c.head_size, n_ctx = c.seq_len;
+    const Stride stride = {sizeof(float), sizeof(float) * n_ctx, sizeof(float) * kv_dim * n_ctx, sizeof(float) * kv_dim * n_ctx};
+    for (size_t L = 0; L < c.n_layers; L++) {
+        m_key_tensors.emplace_back(Tensor(DataType::FP32, {n_ctx, kv_dim, 1, 1}));
+        m_value_tensors.emplace_back(Tensor(DataType::FP32, {n_ctx, kv_dim, 1, 1}));
+        m_key_tensors[L].m_data   = std::make_shared<CUDABuffer>(m_ctx, stride, ps_cuda_kv_k(m_ctx, (int)L), false);
+        m_value_tensors[L].m_data = std::make_shared<CUDABuffer>(m_ctx, stride, ps_cuda_kv_v(m_ctx, (int)L), false);
+    }
 }
 
 CUDABackend::~CUDABackend() { ps_cuda_destroy(m_ctx); }
@@ -83,6 +97,18 @@ void CUDABackend::get_embedding(const Tensor *dst, const Tensor *weight, const s
 
 void CUDABackend::matmul(const Tensor *dst, const Tensor *src0, const Tensor *src1) const {
     POWERSERVE_ASSERT(tensor_can_mul_mat(src0, src1));
+    if (dynamic_cast<CUDABuffer *>(src0->m_data.get())) {
+        // FP32 x FP32 over device views (the attention products: k_view . q and v_view . kq, norm_attention.cpp:117-147)
+        POWERSERVE_ASSERT(src0->m_dtype == DataType::FP32 && src1->m_dtype == DataType::FP32);
+        POWERSERVE_ASSERT(src0->m_shape[3] == 1 && src1->m_shape[3] == 1);
+        const auto &a = src0->get<CUDABuffer>();
+        const auto &b = src1->get<CUDABuffer>();
+        POWERSERVE_ASSERT(a.m_stride[0] == sizeof(float) && b.m_stride[0] == sizeof(float));
+        PS_CHECK(ps_cuda_matmul_f32(m_ctx, (float *)dev(dst), a.m_data, (int64_t)src0->m_shape[0], (int64_t)src0->m_shape[1], (int64_t)src0->m_shape[2],
+                                    (int64_t)a.m_stride[1], (int64_t)a.m_stride[2], b.m_data, (int64_t)src1->m_shape[1], (int64_t)src1->m_shape[2],
+                                    (int64_t)b.m_stride[1], (int64_t)b.m_stride[2]));
+        return;
+    }
     PS_CHECK(ps_cuda_matmul(m_ctx, (float *)dev(dst), device_weight(src0), ggml_type_of(*src0), (int64_t)src0->m_shape[0],
                             (int64_t)src0->m_shape[1], (const float *)dev(src1), (int64_t)src1->nrows()));
 }
@@ -108,15 +134,139 @@ void CUDABackend::silu_hadamard(const Tensor *out, const Tensor *hb, const Tenso
     PS_CHECK(ps_cuda_silu_hadamard(m_ctx, (float *)dev(out), (const float *)dev(hb), (const float *)dev(hb2), (int64_t)hb->n_elements()));
 }
 
+void CUDABackend::softmax(const Tensor *out, const Tensor *x) const {
+    PS_CHECK(ps_cuda_softmax(m_ctx, (float *)dev(out), (const float *)dev(x), (int64_t)x->m_shape[0], (int64_t)x->nrows()));
+}
+
+// permute / transpose / VIEW rewrite strides and the data pointer of a view buffer (ggml_wrapper.cpp:125-133,
+// ggml.cpp:170-177, executor.cpp:194-199); nothing runs on the device
+void CUDABackend::permute(const Tensor *out, const Tensor *x, Shape axes) const {
+    const Stride &xs = x->get<CUDABuffer>().m_stride;
+    Stride stride{};
+    for (size_t i = 0; i < 4; i++) stride[axes[i]] = xs[i];
+    out->get<CUDABuffer>().m_stride = stride;
+}
+
+void CUDABackend::transpose(const Tensor *out, const Tensor *x) const {
+    Stride stride{x->get<CUDABuffer>().m_stride};
+    std::swap(stride[0], stride[1]);
+    out->get<CUDABuffer>().m_data   = x->get<CUDABuffer>().m_data;
+    out->get<CUDABuffer>().m_stride = stride;
+}
+
+void CUDABackend::view(const Tensor *out, const Stride &stride, size_t offset) const {
+    auto &b    = out->get<CUDABuffer>();
+    b.m_stride = stride;
+    b.m_data   = (char *)b.m_data + offset;
+}
+
+// copy / cont: powerserve_compute_forward_dup over two strided views whose shapes may differ (ggml_wrapper.cpp:135-161)
 void CUDABackend::copy(const Tensor *dst, const Tensor *src) const {
-    auto &d = const_cast<Tensor *>(dst)->get<CUDABuffer>();
-    auto &s = const_cast<Tensor *>(src)->get<CUDABuffer>();
-    PS_CHECK(ps_cuda_copy_2d(m_ctx, d.m_data, (int64_t)d.m_stride[0], (int64_t)d.m_stride[1], s.m_data, (int64_t)s.m_stride[0],
-                             (int64_t)s.m_stride[1], (int64_t)src->m_shape[0], (int64_t)src->nrows()));
+    POWERSERVE_ASSERT(dst->m_dtype == DataType::FP32 && src->m_dtype == DataType::FP32);
+    const auto &d = dst->get<CUDABuffer>();
+    const auto &s = src->get<CUDABuffer>();
+    int64_t dne[4], dnb[4], sne[4], snb[4];
+    for (size_t i = 0; i < 4; i++) {
+        dne[i] = (int64_t)dst->m_shape[i]; dnb[i] = (int64_t)d.m_stride[i];
+        sne[i] = (int64_t)src->m_shape[i]; snb[i] = (int64_t)s.m_stride[i];
+    }
+    PS_CHECK(ps_cuda_copy_4d(m_ctx, d.m_data, dne, dnb, s.m_data, sne, snb));
+}
+
+void CUDABackend::cont(const Tensor *out, const Tensor *x) const { copy(out, x); }
+
+void CUDABackend::print(const Tensor *x, size_t size) const {
+    POWERSERVE_UNUSED(size);
+    POWERSERVE_ASSERT(x->m_dtype == DataType::FP32);
+    // GGMLBackend::print (ggml.cpp:131-151): shape, strides, every element, then exit
+    Tensor host(DataType::FP32, x->m_shape);
+    host.m_data = CPUBuffer::create_buffer<float>(x->m_shape);
+    {
+        Tensor dense(DataType::FP32, x->m_shape);
+        dense.m_data = CUDABuffer::create_buffer<float>(m_ctx, x->m_shape);
+        copy(&dense, x);
+        PS_CHECK(ps_cuda_memcpy_d2h(m_ctx, host.get<CPUBuffer>().m_data, dense.get<CUDABuffer>().m_data, x->n_elements() * sizeof(float)));
+    }
+    const auto shape  = x->m_shape;
+    const auto stride = x->get<CUDABuffer>().m_stride;
+    printf("\n{%ld, %ld, %ld, %ld}\n", shape[3], shape[2], shape[1], shape[0]);
+    printf("\n{%ld, %ld, %ld, %ld}\n", stride[3], stride[2], stride[1], stride[0]);
+    const float *p = static_cast<const float *>(host.get<CPUBuffer>().m_data);
+    for (size_t i = 0; i < x->n_elements(); i++) printf("%.6f\n", (double)p[i]);
+    exit(0);
 }
 
 void CUDABackend::get_mask(const Tensor *out, const std::vector<int> &pos) const {
     PS_CHECK(ps_cuda_get_mask(m_ctx, (float *)dev(out), (int64_t)out->m_shape[0], (int64_t)pos.size(), pos.data()));
+}
+
+// ---- op-by-op execution of the unfused graph (the CUDA counterparts of Executor::allocate_buffers / Executor::run)
+void CUDABackend::allocate_buffers(Graph &g) const {
+    for (auto tensor : g.tensors) {
+        if (tensor->m_data) continue; // weights (CPUBuffer views of GGUF memory) and the device caches
+        POWERSERVE_ASSERT(tensor->m_dtype == DataType::FP32, "could not allocate a device buffer for data type: {}", static_cast<int>(tensor->m_dtype));
+        if (tensor->type == NodeType::TENSOR_VIEW) {
+            auto *parent = dynamic_cast<CUDABuffer *>(tensor->tensor_view()->parent->m_data.get());
+            POWERSERVE_ASSERT(parent != nullptr, "view of a tensor that is not on the device");
+            tensor->m_data = CUDABuffer::create_buffer_view<float>(*parent, tensor->m_shape);
+        } else {
+            tensor->m_data = CUDABuffer::create_buffer<float>(m_ctx, tensor->m_shape);
+        }
+    }
+}
+
+void CUDABackend::run(Graph &g) const {
+    for (auto op : g.ops) {
+        switch (op->op) {
+        case OpType::GET_EMBEDDING: {
+            auto [tokens] = op->get_params<GetEmbeddingParams>();
+            get_embedding(op->output(), op->prev[0]->tensor(), tokens);
+        } break;
+        case OpType::ADD: add(op->output(), op->prev[0]->tensor(), op->prev[1]->tensor()); break;
+        case OpType::MAT_MUL: matmul(op->output(), op->prev[0]->tensor(), op->prev[1]->tensor()); break;
+        case OpType::RMS_NORM: {
+            auto [eps] = op->get_params<RMSNormParams>();
+            rmsnorm(op->output(), op->prev[0]->tensor(), op->prev[1]->tensor(), eps);
+        } break;
+        case OpType::SILU_HADAMARD: silu_hadamard(op->output(), op->prev[0]->tensor(), op->prev[1]->tensor()); break;
+        case OpType::ROPE: {
+            auto [pos, rope_cfg] = op->get_params<RopeParams>();
+            rope(op->next[0]->tensor(), op->prev[0]->tensor(), pos, rope_cfg);
+        } break;
+        case OpType::SOFTMAX: softmax(op->output(), op->prev[0]->tensor()); break;
+        case OpType::COPY: copy(op->prev[0]->tensor(), op->prev[1]->tensor()); break;
+        case OpType::PRINT: print(op->prev[0]->tensor(), op->get_params<PrintParams>().size); break;
+        case OpType::PERMUTE: {
+            auto [axes] = op->get_params<PermuteParams>();
+            permute(op->output(), op->prev[0]->tensor(), axes);
+        } break;
+        case OpType::CONT: cont(op->output(), op->prev[0]->tensor()); break;
+        case OpType::VIEW: {
+            auto [stride, offset] = op->get_params<ViewParams>();
+            view(op->output(), stride, offset);
+        } break;
+        case OpType::SOFTMAX_EXT: {
+            auto [scale, max_bias] = op->get_params<SoftmaxExtParams>();
+            softmax_ext(op->output(), op->prev[0]->tensor(), op->prev[1]->tensor(), scale, max_bias);
+        } break;
+        case OpType::GET_MASK: {
+            auto [mask, pos] = op->get_params<GetMaskParams>();
+            get_mask(op->output(), pos);
+        } break;
+        case OpType::TRANSPOSE: transpose(op->output(), op->prev[0]->tensor()); break;
+        default: POWERSERVE_ABORT("cuda backend: OpType {} has no device twin", static_cast<int>(op->op));
+        }
+    }
+}
+
+auto CUDABackend::get_cache(size_t L) -> std::pair<Tensor &, Tensor &> { return {m_key_tensors[L], m_value_tensors[L]}; }
+
+void CUDABackend::advance(size_t n) { PS_CHECK(ps_cuda_kv_advance(m_ctx, (int)n)); }
+
+auto CUDABackend::download(const Tensor *t) const -> BufferPtr {
+    auto host = CPUBuffer::create_buffer<float>(t->m_shape);
+    PS_CHECK(ps_cuda_memcpy_d2h(m_ctx, dynamic_cast<CPUBuffer &>(*host).m_data, dev(t), t->n_elements() * sizeof(float)));
+    return host;
 }
 
 size_t CUDABackend::kv_position() const { return (size_t)ps_cuda_kv_position(m_ctx); }

@@ -18,6 +18,10 @@
 #include <memory>
 #include <vector>
 
+namespace powerserve {
+struct Graph;
+}
+
 namespace powerserve::cuda {
 
 // Device memory behind a Tensor (the CUDA counterpart of CPUBuffer, src/backend/cpu_buffer.hpp:23-65).
@@ -29,6 +33,16 @@ struct CUDABuffer : BaseBuffer {
 
     CUDABuffer(ps_cuda_ctx *ctx, Stride stride, void *data, bool owned) : m_ctx(ctx), m_stride(stride), m_data(data), m_owned(owned) {}
     ~CUDABuffer() override;
+
+    // a view of a parent buffer's memory with the contiguous strides of `shape` (CPUBuffer::create_buffer_view, cpu_buffer.hpp:53-64)
+    template <typename T>
+    static auto create_buffer_view(CUDABuffer &parent, Shape shape) -> BufferPtr {
+        Stride stride;
+        stride[0] = sizeof(T);
+        for (size_t i = 1; i < shape.size(); i++) stride[i] = stride[i - 1] * shape[i - 1];
+        POWERSERVE_ASSERT(parent.m_data != nullptr, "parent buffer is nullptr");
+        return std::make_shared<CUDABuffer>(parent.m_ctx, stride, parent.m_data, false);
+    }
 
     template <typename T>
     static auto create_buffer(ps_cuda_ctx *ctx, Shape shape) -> BufferPtr {
@@ -61,10 +75,27 @@ public:
     void matmul(const Tensor *dst, const Tensor *src0, const Tensor *src1) const;
     void rmsnorm(const Tensor *o, const Tensor *x, const Tensor *weight, float eps) const;
     void rope(Tensor *out, const Tensor *src, const std::vector<int> &pos, const ModelConfig::LLMConfig::RopeConfig &rope_cfg) const;
+    void softmax(const Tensor *out, const Tensor *x) const;
     void softmax_ext(const Tensor *out, const Tensor *x, const Tensor *mask, float scale, float max_bias) const;
-    void silu_hadamard(const Tensor *out, const Tensor *hb, const Tensor *hb2) const;
+    void permute(const Tensor *out, const Tensor *x, Shape axes) const;
+    void transpose(const Tensor *out, const Tensor *x) const;
+    void cont(const Tensor *out, const Tensor *x) const;
     void copy(const Tensor *dst, const Tensor *src) const;
-    void get_mask(const Tensor *out, const std::vector<int> &pos) const;
+    void silu_hadamard(const Tensor *out, const Tensor *hb, const Tensor *hb2) const;
+    void print(const Tensor *x, size_t size) const;
+    void get_mask(const Tensor *out, const std::vector<int> &pos) const;                 // executor-inline GET_MASK, executor.cpp:210-224
+    void view(const Tensor *out, const Stride &stride, size_t offset) const;             // executor-inline VIEW, executor.cpp:194-199
+
+    // ---- op-by-op execution of the UNFUSED PowerServe graph on the device (Executor::allocate_buffers / Executor::run,
+    // executor.cpp:23-45, 77-235): every intermediate is a CUDABuffer, every op one call of the table above.  A bring-up /
+    // debug path (about 30 launches per layer); selected with set_per_op(true) or POWERSERVE_CUDA_PER_OP=1.
+    bool per_op() const { return m_per_op; }
+    void set_per_op(bool v) { m_per_op = v; }
+    void allocate_buffers(Graph &g) const;
+    void run(Graph &g) const;
+    auto get_cache(size_t L) -> std::pair<Tensor &, Tensor &>;   // GGMLKV::get_cache (ggml_kv_cache.hpp:157-159) over the device caches
+    void advance(size_t n);                                      // GGMLKV::advance
+    auto download(const Tensor *t) const -> BufferPtr;           // device tensor -> CPUBuffer (LogitsVector reads a CPUBuffer)
 
     // ---- KV position (Platform::get_kv_position / reset_kv_position, src/backend/platform.cpp:34-50)
     size_t kv_position() const;
@@ -86,6 +117,8 @@ private:
     ps_cuda_ctx *m_ctx = nullptr;
     ModelConfig::LLMConfig m_config;
     std::vector<ps_cuda_layer_weights> m_layers;
+    bool m_per_op = false;
+    std::vector<Tensor> m_key_tensors, m_value_tensors; // per layer, CUDABuffers over ps_cuda_kv_k / ps_cuda_kv_v
 };
 
 } // namespace powerserve::cuda

@@ -38,6 +38,85 @@ def test_copy_2d_strided(be, ne0, ne1):
         b.free()
 
 
+def test_copy_4d_views_of_the_unfused_graph(be):
+    """The three dup shapes of NormAttention::build (norm_attention.cpp:82-151): rope_k {hs, n_kv_heads, bs} into the 1-D cache
+    view at an offset, the transposed v into the {bs, kv_dim} view of the transposed cache, and `cont` of the permuted
+    {hs, n_heads, bs} view of the P.V product into {dim, bs}."""
+    rng = np.random.default_rng(11)
+    hs, nkv, nh, bs, n_ctx, pos = 64, 2, 8, 5, 96, 17
+    kvd, dim = hs * nkv, hs * nh
+    k = rng.standard_normal(kvd * bs).astype(np.float32)
+    cache0 = rng.standard_normal(n_ctx * kvd).astype(np.float32)
+    kd, cd = be.upload(k), be.upload(cache0)
+    be.copy_4d(cd, [bs * kvd, 1, 1, 1], [4, 4 * bs * kvd, 4 * bs * kvd, 4 * bs * kvd], kd, [hs, nkv, bs, 1], [4, 4 * hs, 4 * kvd, 4 * kvd * bs], dst_off=4 * kvd * pos)
+    want = cache0.copy()
+    want[kvd * pos: kvd * (pos + bs)] = k
+    L.assert_bit_equal(cd.numpy(), want, "k rows into the cache view")
+    # v {kv_dim, bs} seen transposed as {bs, kv_dim} (strides swapped) -> cache^T view {bs, kv_dim} with row pitch n_ctx
+    v = rng.standard_normal(kvd * bs).astype(np.float32)
+    vt0 = rng.standard_normal(kvd * n_ctx).astype(np.float32)
+    vd, vtd = be.upload(v), be.upload(vt0)
+    be.copy_4d(vtd, [bs, kvd, 1, 1], [4, 4 * n_ctx, 4 * n_ctx * kvd, 4 * n_ctx * kvd], vd, [bs, kvd, 1, 1], [4 * kvd, 4, 4 * kvd * bs, 4 * kvd * bs], dst_off=4 * pos)
+    want = vt0.reshape(kvd, n_ctx).copy()
+    want[:, pos:pos + bs] = v.reshape(bs, kvd).T
+    L.assert_bit_equal(vtd.numpy(), want.reshape(-1), "transposed v into the cache view")
+    # kqv {hs, bs, n_heads} permuted {0, 2, 1, 3} -> view {hs, n_heads, bs} -> cont {dim, bs}
+    kqv = rng.standard_normal(hs * bs * nh).astype(np.float32)
+    qd, od = be.upload(kqv), be.empty(dim * bs)
+    be.copy_4d(od, [dim, bs, 1, 1], [4, 4 * dim, 4 * dim * bs, 4 * dim * bs], qd, [hs, nh, bs, 1], [4, 4 * hs * bs, 4 * hs, 4 * hs * bs * nh])
+    L.assert_bit_equal(od.numpy(), kqv.reshape(nh, bs, hs).transpose(1, 0, 2).reshape(-1), "cont of the permuted P.V product")
+    for b in (kd, cd, vd, vtd, qd, od):
+        b.free()
+
+
+@pytest.mark.parametrize("hs,nkv,r2,bs,n_kv", [(64, 2, 4, 1, 1), (64, 2, 4, 3, 37), (128, 2, 2, 2, 70), (32, 1, 1, 1, 257), (96, 2, 3, 4, 33)])
+def test_matmul_f32_strided_attention_products(be, hs, nkv, r2, bs, n_kv):
+    """matmul with FP32 src0 over the strided views of the unfused graph: scores = k_view {hs, n_kv, n_kv_heads} . q {hs, bs, n_heads}
+    (a permuted view of the rope output) and P.V = v_view {n_kv, hs, n_kv_heads} . kq {n_kv, bs, n_heads}; every output element
+    must be ggml_vec_dot_f32 of its row and column (oracle: ps_or_vec_dot_f32, ggml.c:2092-2131)."""
+    o = L.oracle()
+    rng = np.random.default_rng(hs * 7 + n_kv)
+    nh, kvd, n_ctx = nkv * r2, hs * nkv, 260
+    kc = rng.standard_normal(n_ctx * kvd).astype(np.float32)            # [pos][kv_dim]
+    q = rng.standard_normal(bs * nh * hs).astype(np.float32)            # rope output {hs, n_heads, bs}
+    kcd, qd, sd = be.upload(kc), be.upload(q), be.empty(n_kv * bs * nh)
+    be.matmul_f32(sd, kcd, hs, n_kv, nkv, 4 * kvd, 4 * hs, qd, bs, nh, 4 * hs * nh, 4 * hs)   # q viewed {hs, bs, n_heads}: strides (4, hs*nh*4, hs*4)
+    got = sd.numpy().reshape(nh, bs, n_kv)
+    K3, Q3 = kc.reshape(n_ctx, nkv, hs), q.reshape(bs, nh, hs)
+    for h in range(nh):
+        for i in range(bs):
+            for j in range(n_kv):
+                a, b = np.ascontiguousarray(K3[j, h // r2]), np.ascontiguousarray(Q3[i, h])
+                assert L.bits(np.float32(o.ps_or_vec_dot_f32(hs, L.fptr(a), L.fptr(b)))) == L.bits(got[h, i, j]), (h, i, j)
+    vt = rng.standard_normal(kvd * n_ctx).astype(np.float32)            # [kv_dim][n_ctx]
+    p = rng.standard_normal(nh * bs * n_kv).astype(np.float32)          # {n_kv, bs, n_heads}
+    vtd, pd, od = be.upload(vt), be.upload(p), be.empty(hs * bs * nh)
+    be.matmul_f32(od, vtd, n_kv, hs, nkv, 4 * n_ctx, 4 * n_ctx * hs, pd, bs, nh, 4 * n_kv, 4 * n_kv * bs)
+    got = od.numpy().reshape(nh, bs, hs)
+    V3, P3 = vt.reshape(nkv, hs, n_ctx), p.reshape(nh, bs, n_kv)
+    for h in range(nh):
+        for i in range(bs):
+            for d in range(hs):
+                a, b = np.ascontiguousarray(V3[h // r2, d, :n_kv]), np.ascontiguousarray(P3[h, i])
+                assert L.bits(np.float32(o.ps_or_vec_dot_f32(n_kv, L.fptr(a), L.fptr(b)))) == L.bits(got[h, i, d]), (h, i, d)
+    for b in (kcd, qd, sd, vtd, pd, od):
+        b.free()
+
+
+@pytest.mark.parametrize("ne0,rows", [(1, 3), (8, 2), (37, 5), (300, 4), (4097, 1)])
+def test_softmax_plain(be, ne0, rows):
+    """GGMLBackend::softmax = soft_max with scale 1 and no mask (ggml.c:15060-15089); the oracle's softmax_ext with a zero mask
+    computes the same rows (x * 1 + 0)."""
+    o = L.oracle()
+    x = (np.random.default_rng(ne0).standard_normal(ne0 * rows) * 6).astype(np.float32)
+    ref = np.zeros_like(x)
+    o.ps_or_softmax_ext(L.fptr(ref), L.fptr(x), L.fptr(np.zeros(ne0 * rows, np.float32)), ne0, rows, 1, 1.0)
+    xd, dd = be.upload(x), be.empty(x.size)
+    be.softmax(dd, xd, ne0, rows)
+    L.assert_bit_equal(dd.numpy(), ref, "softmax")
+    xd.free(); dd.free()
+
+
 def test_kv_bookkeeping_and_cache_contents():
     d = M.model_dir("tiny-llama")
     shape = synth.PRESETS["tiny-llama"]

@@ -21,12 +21,14 @@ EXE = os.path.join(L.ROOT, "powerserve_b200", "host", "_build", "ps_cuda_run")
 needs_exe = pytest.mark.skipif(not os.path.exists(EXE), reason="ps_cuda_run not built (needs /root/reference)")
 
 
-def run_dropin(path, prompt, n_decode, batch_size, dump_logits):
+def run_dropin(path, prompt, n_decode, batch_size, dump_logits, per_op=False):
+    env = dict(os.environ)
+    env["POWERSERVE_CUDA_PER_OP"] = "1" if per_op else "0"
     with tempfile.TemporaryDirectory() as td:
         pf = os.path.join(td, "prompt.txt")
         open(pf, "w").write(" ".join(str(int(t)) for t in prompt))
         r = subprocess.run([EXE, path, "2", str(batch_size), pf, str(n_decode), os.path.join(td, "out"), "--dump-logits", str(dump_logits)],
-                           capture_output=True, text=True, timeout=600)
+                           capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         ids = [int(x) for x in open(os.path.join(td, "out.ids")).read().split()]
         vocab = json.load(open(os.path.join(path, "model.json")))["llm_config"]["vocab_size"]
@@ -54,3 +56,17 @@ def test_powerserve_stack_on_cuda_fused_decode_matches_oracle():
     om.close()
     L.assert_bit_equal(lg, lg_o, "drop-in logits vs oracle")
     assert ids == ids_o
+
+
+@needs_exe
+@pytest.mark.parametrize("preset,n_prompt,batch,n_dec", cases.MODEL_CASES)
+def test_powerserve_unfused_graph_op_by_op_on_cuda_matches_reference_golden(preset, n_prompt, batch, n_dec):
+    """POWERSERVE_CUDA_PER_OP=1: Executor::allocate_buffers / Executor::run dispatch on the CUDA backend op by op - the
+    reference's own unfused graph (VIEW / PERMUTE / TRANSPOSE / CONT / COPY into cache views / the two fp32 attention
+    mat-muls over strided views / GET_MASK / SOFTMAX_EXT ...) with every intermediate in a CUDABuffer.  Same golden vectors."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "models.npz"))
+    prompt = synth.random_prompt(synth.PRESETS[preset].vocab_size, n_prompt, seed=7 + n_prompt)
+    ids, lg = run_dropin(M.model_dir(preset), prompt, n_dec, batch, n_dec, per_op=True)
+    key = f"{preset}/{n_prompt}/{batch}"
+    assert ids == list(gold[key + "/ids"])
+    assert (L.bits(lg) == gold[key + "/logits_bits"]).all()
