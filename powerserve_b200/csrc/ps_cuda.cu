@@ -3,6 +3,7 @@
 #include "../../include/ps_cuda.h"
 #include "ps_decode.cuh"
 #include "ps_rw.cuh"
+#include "ps_mv32.cuh"
 #include "ps_tc.cuh"
 #include "ps_step.cuh"
 
@@ -67,6 +68,8 @@ struct LayerDev {
     uint8_t *rw_qkv = nullptr, *rw_o = nullptr, *rw_gu = nullptr, *rw_down = nullptr;
     // fp16-expanded tensor-core operands for the prefill GEMM (ps_tc.cuh): q|k|v rows, o, gate, up, down
     uint8_t *tc_qkv = nullptr, *tc_o = nullptr, *tc_gate = nullptr, *tc_up = nullptr, *tc_down = nullptr;
+    // octet copies for the 32-block mat-vec (ps_mv32.cuh; all-Q4_0 / all-Q8_0 models): q|k|v rows, o, gate|up rows, down
+    uint8_t *mv_qkv = nullptr, *mv_o = nullptr, *mv_gu = nullptr, *mv_down = nullptr;
 };
 
 } // namespace
@@ -126,6 +129,11 @@ struct ps_cuda_ctx {
     int64_t kt_launches = 0;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
+    bool mv_ok = false;      // every matmul weight is Q4_0 (or every one Q8_0): the fused 32-block decode path applies (ps_mv32.cuh)
+    int mv_type = 0;
+    uint8_t *mv_out = nullptr;
+    bool ops_graph_ok = false; // any supported mix of weight types: the graph-replayed operator-table decode step applies (decode_step_ops)
+    int opt_ops_graph = 1;
     int n_sm = 148;
     int32_t *ctr_dev = nullptr;
     // tensor parallelism (row sharding of every matrix + all-gather, bit-exact): local sizes of this rank
@@ -537,11 +545,13 @@ template <int R2> int launch_attn_fused(ps_cuda_ctx *ctx, int L, bool *done) {
     return 0;
 }
 
-template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
+// R2 = the template's query heads per kv head, r2 <= R2 the model's (Qwen2-0.5B has 7); q_rot = the rotated query vector
+template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L, int r2 = R2, const float *q_rot = nullptr) {
     const ps_cuda_model_desc &d = ctx->d;
     const int hs = d.head_size, nkv = ctx->nkv_l;
     const float kq_scale = 1.0f / sqrtf((float)hs);
-    {
+    if (!q_rot) q_rot = ctx->q;
+    if (r2 == R2 && q_rot == ctx->q) {
         bool done = false;
         int rc0 = launch_attn_fused<R2>(ctx, L, &done);
         if (rc0 || done) return rc0;
@@ -552,8 +562,8 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
         attr[ctx->device] = true;
     }
     int rc;
-    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], (const float *)ctx->q,
-                       (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx)))) return rc;
+    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], q_rot,
+                       (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx), r2))) return rc;
     // probabilities of the group + (when they fit) the CTA's eight V^T rows, all sized for a full context
     const size_t row = (size_t)((d.n_ctx + 31) & ~31) * 4;
     const int v_smem = (R2 + 8) * row <= 200 * 1024 && d.n_ctx % 4 == 0;
@@ -561,7 +571,14 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L) {
     if ((size_t)R2 * row > 200 * 1024 || d.n_ctx % 4) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "fused decode attention: n_ctx = %d does not fit shared memory", d.n_ctx);
     return launch_k(ctx, ps_k_attn2<R2>, dim3((unsigned)((hs + 7) / 8), (unsigned)nkv), dim3(PS_A2_THREADS), a2smem, ctx->att, (const float *)ctx->kq,
                     (const float *)ctx->vct[L], (const int32_t *)ctx->pos_dev, hs, d.n_ctx, tl_slot(ctx),
-                    tp_out(ctx, PS_TP_SLOT_ATT), v_smem);
+                    tp_out(ctx, PS_TP_SLOT_ATT), v_smem, r2);
+}
+int launch_attn_any(ps_cuda_ctx *ctx, int L, const float *q_rot = nullptr) {
+    const int r2 = ctx->d.n_heads / ctx->d.n_kv_heads;
+    if (r2 == 1) return launch_attn<1>(ctx, L, r2, q_rot);
+    if (r2 == 2) return launch_attn<2>(ctx, L, r2, q_rot);
+    if (r2 <= 4) return launch_attn<4>(ctx, L, r2, q_rot);
+    return launch_attn<8>(ctx, L, r2, q_rot);
 }
 int rw_single(ps_cuda_ctx *ctx, const uint8_t *w, int n_rows, int K, float *dst, const float *x, const float *norm_w, const float *residual,
               bool partial_argmax = false, const uint8_t *xq_in = nullptr, const float *next_norm_w = nullptr, int idx_offset = 0,
@@ -649,13 +666,7 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     for (int L = 0; L < d.n_layers; L++) {
         const LayerDev &ld = ctx->layers[L];
         if ((rc = rw_qkv(ctx, ld, L))) return rc;
-        switch (nh / nkv) {
-        case 1: rc = launch_attn<1>(ctx, L); break;
-        case 2: rc = launch_attn<2>(ctx, L); break;
-        case 4: rc = launch_attn<4>(ctx, L); break;
-        default: rc = launch_attn<8>(ctx, L); break;
-        }
-        if (rc) return rc;
+        if ((rc = launch_attn_any(ctx, L))) return rc;
         if ((rc = tp_all_gather(ctx, ctx->att, ctx->att_full, (size_t)qdim / tp))) return rc;
         const float *norm_after = (L + 1 < d.n_layers) ? ctx->layers[L + 1].attn_norm : ctx->w_out_norm;
         // x[rows of this rank] += Wo[rows] . att
@@ -696,6 +707,185 @@ int decode_step_fused(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
     }
     return 0;
 }
+
+// ---- fused decode step for the 32-element block formats (all-Q4_0 or all-Q8_0 models; ps_mv32.cuh): 7 launches per layer
+// (q|k|v, rope + cache store, scores, soft-max / P.V, Wo, gate|up, down), PDL-chained and graph-replayed like the Q4_K step
+template <int TYPE> int mv_repack(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int64_t n_rows, int64_t K, int64_t oct0) {
+    ps_k_mv32_repack<TYPE><<<(unsigned)std::min<int64_t>((n_rows * (K / 32) + 255) / 256, 148 * 16), 256, 0, ctx->stream>>>(dst, src, n_rows, K / 32, oct0);
+    PS_LAUNCH_CK();
+    return 0;
+}
+int mv_repack_t(ps_cuda_ctx *ctx, uint8_t *dst, const uint8_t *src, int64_t n_rows, int64_t K, int64_t oct0) {
+    return ctx->mv_type == 2 ? mv_repack<2>(ctx, dst, src, n_rows, K, oct0) : mv_repack<8>(ctx, dst, src, n_rows, K, oct0);
+}
+size_t mv_bytes(int type, int64_t rows, int64_t K) { return (size_t)((rows + 7) / 8) * (size_t)(K / 32) * (type == 2 ? PsMv32<2>::BLK : PsMv32<8>::BLK); }
+
+int launch_mv(ps_cuda_ctx *ctx, PsMvArgs a) {
+    const int blk = ctx->mv_type == 2 ? PsMv32<2>::BLK : PsMv32<8>::BLK;
+    const int nb = a.K / 32;
+    const int grid = std::max(1, std::min(ctx->n_sm, a.n_oct));
+    const int per_cta = (a.n_oct + grid - 1) / grid, rounds = (per_cta + PS_MV_WARPS - 1) / PS_MV_WARPS;
+    // stage = the largest divisor of the row's blocks that fits PS_MV_STAGE_CAP bytes; ring = up to PS_MV_MAX_NS stages per warp
+    int sb = 1;
+    for (int c = std::min(nb, PS_MV_STAGE_CAP / blk); c >= 1; c--)
+        if (nb % c == 0) { sb = c; break; }
+    a.sb = sb;
+    a.ns = std::max(1, std::min(PS_MV_MAX_NS, rounds * (nb / sb)));
+    a.inv_k = 1.0 / (double)a.K;
+    if ((double)a.K * a.inv_k != 1.0) a.inv_k = 0.0; // only exact reciprocals replace the division (power-of-two K)
+    const size_t act = ((size_t)a.K + (size_t)nb * 4 + 127) & ~(size_t)127;
+    const size_t smem = act + (size_t)PS_MV_WARPS * a.ns * ((size_t)sb * blk + 8);
+    if (smem > 200 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "32-block mat-vec: K = %d does not fit shared memory", a.K);
+    static bool attr[64] = {};
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_mv32<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_mv32<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        attr[ctx->device] = true;
+    }
+    if (ctx->mv_type == 2) return launch_k(ctx, ps_k_mv32<2>, dim3(grid), dim3(PS_MV_THREADS), smem, a);
+    return launch_k(ctx, ps_k_mv32<8>, dim3(grid), dim3(PS_MV_THREADS), smem, a);
+}
+
+int decode_step_mv32(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
+    int rc;
+    ctx->trace_launch = 0;
+    ps_k_get_embedding<<<1, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, (int64_t)dim, ctx->tokens_dev);
+    PS_LAUNCH_CK();
+    for (int L = 0; L < d.n_layers; L++) {
+        const LayerDev &ld = ctx->layers[L];
+        {   // q | k | v = W . rmsnorm(x) (+ bias)
+            PsMvArgs a{};
+            a.w = ld.mv_qkv; a.n_oct = (qdim + 2 * kvd) / 8; a.K = dim; a.x = ctx->x; a.norm_w = ld.attn_norm; a.eps = d.norm_eps; a.pro = PS_MV_PRO_RMSNORM;
+            a.seg[0] = {ctx->q, d.qkv_bias ? ld.q_bias : nullptr, 0, qdim};
+            a.seg[1] = {ctx->k, d.qkv_bias ? ld.k_bias : nullptr, qdim, qdim + kvd};
+            a.seg[2] = {ctx->v, d.qkv_bias ? ld.v_bias : nullptr, qdim + kvd, qdim + 2 * kvd};
+            a.n_seg = 3;
+            if ((rc = launch_mv(ctx, a))) return rc;
+        }
+        if ((rc = launch_k(ctx, ps_k_rope_kv, dim3((unsigned)(nh + 2 * nkv)), dim3(64), 0, ctx->qr, (const float *)ctx->q, (const float *)ctx->k, (const float *)ctx->v,
+                           ctx->kc[L], ctx->vct[L], hs, nh, nkv, d.rope_n_dims, d.rope_type & 2, (const int32_t *)ctx->pos_dev, (const float *)ctx->rope_table,
+                           (int64_t)d.n_ctx))) return rc;
+        if ((rc = launch_attn_any(ctx, L, ctx->qr))) return rc;
+        {   // x += Wo . att
+            PsMvArgs a{};
+            a.w = ld.mv_o; a.n_oct = dim / 8; a.K = qdim; a.x = ctx->att; a.pro = PS_MV_PRO_PLAIN;
+            a.seg[0] = {ctx->x, nullptr, 0, dim}; a.n_seg = 1; a.residual = ctx->x;
+            if ((rc = launch_mv(ctx, a))) return rc;
+        }
+        {   // g | u = Wgate | Wup . rmsnorm(x)
+            PsMvArgs a{};
+            a.w = ld.mv_gu; a.n_oct = 2 * ffn / 8; a.K = dim; a.x = ctx->x; a.norm_w = ld.ffn_norm; a.eps = d.norm_eps; a.pro = PS_MV_PRO_RMSNORM;
+            a.seg[0] = {ctx->g, nullptr, 0, ffn};
+            a.seg[1] = {ctx->u, nullptr, ffn, 2 * ffn};
+            a.n_seg = 2;
+            if ((rc = launch_mv(ctx, a))) return rc;
+        }
+        {   // x += Wdown . (silu(g) * u)
+            PsMvArgs a{};
+            a.w = ld.mv_down; a.n_oct = dim / 8; a.K = ffn; a.x = ctx->g; a.x2 = ctx->u; a.pro = PS_MV_PRO_SILU;
+            a.seg[0] = {ctx->x, nullptr, 0, dim}; a.n_seg = 1; a.residual = ctx->x;
+            if ((rc = launch_mv(ctx, a))) return rc;
+        }
+    }
+    if (lm_head) {
+        PsMvArgs a{};
+        a.w = ctx->mv_out; a.n_oct = d.vocab_size / 8; a.K = dim; a.x = ctx->x; a.norm_w = ctx->w_out_norm; a.eps = d.norm_eps; a.pro = PS_MV_PRO_RMSNORM;
+        a.seg[0] = {ctx->logits, nullptr, 0, d.vocab_size}; a.n_seg = 1;
+        if (pick) { a.part_val = ctx->part_val; a.part_idx = ctx->part_idx; }
+        if ((rc = launch_mv(ctx, a))) return rc;
+        if (pick) {
+            const int n_part = std::max(1, std::min(ctx->n_sm, a.n_oct));
+            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, (const float *)ctx->part_val, (const int *)ctx->part_idx, n_part, ctx->ids_dev, ctx->ctr_dev,
+                               ctx->tokens_dev, ctx->pos_dev, (long long *)nullptr, (const PsTpIn *)nullptr))) return rc;
+        }
+    }
+    return 0;
+}
+bool mv_usable(ps_cuda_ctx *ctx) { return ctx->mv_ok && ctx->opt_fused && ctx->tp == 1; }
+
+// ---- graph-replayed decode step for ANY supported mix of weight types (Q4_0 / Q8_0 / Q6_K / Q4_K matrices, NEOX or NORM rope,
+// q|k|v biases, 1..8 query heads per kv head): the operator-table kernels for the weight products - they hold the block
+// arithmetic of every type - plus the type-agnostic decode attention kernels of the fused path (ps_k_attn1 / ps_k_attn2),
+// which read the position from device memory.  Nothing in the step depends on a host value, so it is captured once and
+// replayed per token like the Q4_K step; the pick runs on the device.  LlamaModel::forward / Qwen2Model::forward at bs = 1.
+__global__ void __launch_bounds__(256) ps_k_argmax_parts(const float *__restrict__ logits, int n, float *__restrict__ part_val, int *__restrict__ part_idx) {
+    __shared__ float sv[8];
+    __shared__ int si[8];
+    const int per = (n + gridDim.x - 1) / gridDim.x, lo = blockIdx.x * per, hi = min(n, lo + per);
+    float best = -INFINITY;
+    int bi = 0x7fffffff;
+    for (int t = lo + threadIdx.x; t < hi; t += blockDim.x) {
+        const float v = logits[t];
+        if (v > best) { best = v; bi = t; } // ascending t per thread: the first maximum wins
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(PS_FULL, best, o);
+        const int oi = __shfl_xor_sync(PS_FULL, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if ((threadIdx.x & 31) == 0) { sv[threadIdx.x >> 5] = best; si[threadIdx.x >> 5] = bi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int t = 1; t < 8; t++)
+            if (sv[t] > best || (sv[t] == best && si[t] < bi)) { best = sv[t]; bi = si[t]; }
+        part_val[blockIdx.x] = best;
+        part_idx[blockIdx.x] = bi;
+    }
+}
+
+int decode_step_ops(ps_cuda_ctx *ctx, bool lm_head, bool pick) {
+    const ps_cuda_model_desc &d = ctx->d;
+    const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
+    int rc;
+    ctx->trace_launch = 0;
+    ps_k_get_embedding<<<1, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev); // every embedding type, token from device memory
+    PS_LAUNCH_CK();
+    for (int L = 0; L < d.n_layers; L++) {
+        const LayerDev &ld = ctx->layers[L];
+        ps_k_rmsnorm<<<1, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tq, ctx->xn, dim, 1))) return rc;
+        if ((rc = matmul_q(ctx, ctx->q, ld.wq, ld.tq, dim, qdim, 1, d.qkv_bias ? ld.q_bias : nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->k, ld.wk, ld.tk, dim, kvd, 1, d.qkv_bias ? ld.k_bias : nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->v, ld.wv, ld.tv, dim, kvd, 1, d.qkv_bias ? ld.v_bias : nullptr, nullptr))) return rc;
+        ps_k_rope<<<dim3((unsigned)nh, 1), 64, 0, ctx->stream>>>(ctx->qr, ctx->q, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_rope<<<dim3((unsigned)nkv, 1), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
+        PS_LAUNCH_CK();
+        ps_k_kv_store<<<grid1d(kvd), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, 1);
+        PS_LAUNCH_CK();
+        if ((rc = launch_attn_any(ctx, L, ctx->qr))) return rc;
+        if ((rc = quantize_act(ctx, ld.to, ctx->att, qdim, 1))) return rc;
+        if ((rc = matmul_q(ctx, ctx->x, ld.wo, ld.to, qdim, dim, 1, nullptr, ctx->x))) return rc;
+        ps_k_rmsnorm<<<1, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.ffn_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tgate, ctx->xn, dim, 1))) return rc;
+        if ((rc = matmul_q(ctx, ctx->g, ld.wgate, ld.tgate, dim, ffn, 1, nullptr, nullptr))) return rc;
+        if ((rc = matmul_q(ctx, ctx->u, ld.wup, ld.tup, dim, ffn, 1, nullptr, nullptr))) return rc;
+        ps_k_silu_hadamard<<<grid1d(ffn), 256, 0, ctx->stream>>>(ctx->g, ctx->g, ctx->u, ffn);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ld.tdown, ctx->g, ffn, 1))) return rc;
+        if ((rc = matmul_q(ctx, ctx->x, ld.wdown, ld.tdown, ffn, dim, 1, nullptr, ctx->x))) return rc;
+    }
+    if (lm_head) {
+        ps_k_rmsnorm<<<1, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ctx->w_out_norm, dim, d.norm_eps);
+        PS_LAUNCH_CK();
+        if ((rc = quantize_act(ctx, ctx->t_out, ctx->xn, dim, 1))) return rc;
+        if ((rc = matmul_q(ctx, ctx->logits, ctx->w_out, ctx->t_out, dim, d.vocab_size, 1, nullptr, nullptr))) return rc;
+        if (pick) {
+            const int n_part = std::min(ctx->n_sm, (d.vocab_size + 255) / 256);
+            ps_k_argmax_parts<<<n_part, 256, 0, ctx->stream>>>(ctx->logits, d.vocab_size, ctx->part_val, ctx->part_idx);
+            PS_LAUNCH_CK();
+            if ((rc = launch_k(ctx, ps_k_argmax_step, dim3(1), dim3(256), 0, (const float *)ctx->part_val, (const int *)ctx->part_idx, n_part, ctx->ids_dev, ctx->ctr_dev,
+                               ctx->tokens_dev, ctx->pos_dev, (long long *)nullptr, (const PsTpIn *)nullptr))) return rc;
+        }
+    }
+    return 0;
+}
+bool ops_graph_usable(ps_cuda_ctx *ctx) { return ctx->ops_graph_ok && ctx->opt_ops_graph && ctx->tp == 1 && !(ctx->fused_ok && ctx->opt_fused) && !mv_usable(ctx); }
 
 // ---- persistent per-step kernel (ps_step.cuh): the whole decode step in ONE cooperative launch
 bool step_usable(ps_cuda_ctx *ctx) { return ctx->opt_persist && ctx->opt_fused && ctx->fused_ok && ctx->step_ok && (ctx->tp == 1 || ctx->p2p); }
@@ -812,13 +1002,16 @@ int run_step(ps_cuda_ctx *ctx, bool pick, int n_kv_max) {
         ctx->kt_used += 2;
         return rc;
     }
-    if (!ctx->opt_graph || ctx->opt_ktime) return decode_step_fused(ctx, true, pick);
+    const bool ops = ops_graph_usable(ctx);
+    const bool mv = mv_usable(ctx);
+    auto build = [&]() { return mv ? decode_step_mv32(ctx, true, pick) : ops ? decode_step_ops(ctx, true, pick) : decode_step_fused(ctx, true, pick); };
+    if (!ctx->opt_graph || ctx->opt_ktime) return build();
     cudaGraphExec_t &ge = pick ? ctx->g_step : ctx->g_fwd;
     if (!ge) {
         cudaGraph_t graph = nullptr;
         const int64_t n0 = ctx->n_launch;
         PS_CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-        int rc = decode_step_fused(ctx, true, pick);
+        int rc = build();
         cudaError_t e = cudaStreamEndCapture(ctx->stream, &graph);
         (pick ? ctx->g_step_kernels : ctx->g_fwd_kernels) = ctx->n_launch - n0;
         ctx->n_launch = n0; // capture enqueued nothing
@@ -1449,6 +1642,45 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
         (size_t)(d.n_heads / d.n_kv_heads) * ((d.n_ctx + 31) & ~31) * 4 > 200 * 1024 || // the soft-max rows of a kv group live in shared memory
         !(d.n_heads / d.n_kv_heads == 1 || d.n_heads / d.n_kv_heads == 2 || d.n_heads / d.n_kv_heads == 4 || d.n_heads / d.n_kv_heads == 8))
         ctx->fused_ok = false;
+    {   // the graph-replayed operator-table step only needs the decode attention kernels to apply
+        const int r2 = d.n_heads / d.n_kv_heads, r2t = r2 <= 1 ? 1 : r2 <= 2 ? 2 : r2 <= 4 ? 4 : 8;
+        ctx->ops_graph_ok = tp == 1 && d.n_heads % d.n_kv_heads == 0 && r2 <= 8 && d.head_size % 32 == 0 && d.head_size <= 256 && d.n_ctx % 4 == 0 &&
+                            (size_t)r2t * ((d.n_ctx + 31) & ~31) * 4 <= 200 * 1024 && d.vocab_size >= 256;
+    }
+    {   // all-Q4_0 / all-Q8_0 model: octet copies for the fused 32-block decode path (ps_mv32.cuh)
+        const int t0 = ctx->t_out;
+        bool same = (t0 == 2 || t0 == 8) && ctx->ops_graph_ok;
+        for (const LayerDev &ld : ctx->layers)
+            if (ld.tq != t0 || ld.tk != t0 || ld.tv != t0 || ld.to != t0 || ld.tgate != t0 || ld.tup != t0 || ld.tdown != t0) same = false;
+        if (d.dim % 32 || d.ffn_dim % 32 || qdim % 32 || qdim % 8 || kvd % 8 || d.dim % 8 || d.ffn_dim % 8 || d.vocab_size % 8 || d.head_size % 2) same = false;
+        ctx->mv_ok = false;
+        if (same) {
+            ctx->mv_type = t0;
+            int rc;
+            auto mk = [&](uint8_t **p, int64_t rows, int64_t K) -> int {
+                const size_t bytes = mv_bytes(t0, rows, K);
+                int rc2 = dev_alloc(ctx, (void **)p, bytes);
+                if (rc2) return rc2;
+                PS_CK(cudaMemsetAsync(*p, 0, bytes, ctx->stream));
+                return 0;
+            };
+            const int64_t dim = d.dim, ffn = d.ffn_dim;
+            for (LayerDev &ld : ctx->layers) {
+                if ((rc = mk(&ld.mv_qkv, qdim + 2 * kvd, dim)) || (rc = mk(&ld.mv_o, dim, qdim)) || (rc = mk(&ld.mv_gu, 2 * ffn, dim)) || (rc = mk(&ld.mv_down, dim, ffn))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_qkv, ld.wq, qdim, dim, 0))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_qkv, ld.wk, kvd, dim, qdim / 8))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_qkv, ld.wv, kvd, dim, (qdim + kvd) / 8))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_o, ld.wo, dim, qdim, 0))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_gu, ld.wgate, ffn, dim, 0))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_gu, ld.wup, ffn, dim, ffn / 8))) return rc;
+                if ((rc = mv_repack_t(ctx, ld.mv_down, ld.wdown, dim, ffn, 0))) return rc;
+            }
+            if ((rc = mk(&ctx->mv_out, d.vocab_size, dim))) return rc;
+            if ((rc = mv_repack_t(ctx, ctx->mv_out, ctx->w_out, d.vocab_size, dim, 0))) return rc;
+            PS_CK(cudaStreamSynchronize(ctx->stream));
+            ctx->mv_ok = true;
+        }
+    }
     if (tp > 1 && !ctx->fused_ok) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "tensor parallelism needs the fused Q4_K decode path (all-Q4_K llama-style model)");
     if (ctx->fused_ok) {
         // octet-interleaved copies for the row-walker mat-vec (a permutation of the same bytes; see ps_rw.cuh)
@@ -1825,6 +2057,8 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
             }
         }
         if (lm_head) ctx->logits_last = ctx->tp_rows; // the single-token logits slot of the exchange heap holds ONE row: batches are read from tp_rows
+    } else if (bs == 1 && lm_head && (ops_graph_usable(ctx) || mv_usable(ctx))) {
+        rc = run_step(ctx, false, pos[0] + 1);
     } else if (bs == 1 && ctx->opt_fused && ctx->fused_ok) {
         if (lm_head) rc = run_step(ctx, false, pos[0] + 1);
         else rc = step_usable(ctx) ? launch_step(ctx, 0, pos[0] + 1) : decode_step_fused(ctx, false, false);
@@ -1939,7 +2173,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     ctx->h_tokens[0] = first_token;
     PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, 4, cudaMemcpyHostToDevice, ctx->stream));
     ctx->h2d += 4;
-    if (ctx->opt_fused && ctx->fused_ok) {
+    if ((ctx->opt_fused && ctx->fused_ok) || ops_graph_usable(ctx) || mv_usable(ctx)) {
         int32_t *slot = &ctx->h_ids[4096];
         slot[0] = ctx->position;
         slot[1] = 0;
@@ -2094,6 +2328,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
         if (!value && ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "option fused = 0: the table-op path is not sharded; tensor-parallel contexts run the fused path only");
         ctx->opt_fused = value;
     }
+    else if (!strcmp(name, "ops_graph")) ctx->opt_ops_graph = value; // 0: models off the Q4_K fused path decode through one launch per table op from the host (no graph replay, host-fed positions)
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "rw_ksplit")) ctx->opt_ksplit = value;   // opt-in (default 0): most warps that may share a row octet in the mat-vec launches with few octets per CTA; bit-exact but measured 3-4 % slower per step (profiles/r02_ab_matvec_ksplit_8b_ctx2048.txt)
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
@@ -2132,6 +2367,8 @@ int64_t ps_cuda_get_counter(ps_cuda_ctx *ctx, const char *name) {
     if (!strcmp(name, "graph_replays")) return ctx->n_graph;
     if (!strcmp(name, "step_launches")) return ctx->n_step;          // persistent step-kernel launches
     if (!strcmp(name, "step_ok")) return ctx->step_ok ? 1 : 0;
+    if (!strcmp(name, "mv32_ok")) return ctx->mv_ok ? 1 : 0;           // all-Q4_0 / all-Q8_0 model: the fused 32-block decode path is bound
+    if (!strcmp(name, "fused_ok")) return ctx->fused_ok ? 1 : 0;
     if (!strcmp(name, "attn_clusters")) return ctx->attn_clusters;
     if (!strcmp(name, "step_kernel_ns")) return (int64_t)(ctx->kt_ms * 1e6);   // option "ktime": summed CUDA-event time of the step-kernel launches
     if (!strcmp(name, "step_kernel_launches")) return ctx->kt_launches;

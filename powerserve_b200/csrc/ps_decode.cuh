@@ -239,7 +239,7 @@ template <int N> PS_D void ps_f32x8_reduce_n(float (&v)[N]) {
 // of the group, with all K loads of the item in flight before anything is consumed.
 template <int R2>
 __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const float *__restrict__ kc, const float *__restrict__ q,
-                                                  const int32_t *__restrict__ pos_dev, int hs, int n_kv_heads, int n_ctx, float scale, long long *tl) {
+                                                  const int32_t *__restrict__ pos_dev, int hs, int n_kv_heads, int n_ctx, float scale, long long *tl, int r2) {
     __shared__ float s_q[R2][256];
     ps_tl_min(tl, 0);
     // Everything this kernel reads except the query vector and cache row `pos` is older than the kernel before the
@@ -277,7 +277,7 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
                     if (s < steps && j0 + t == pos) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
         }
         __syncthreads(); // the previous item's queries are no longer needed
-        for (int idx = tid; idx < R2 * hs; idx += 128) s_q[idx / hs][idx % hs] = q[(int64_t)g * R2 * hs + idx];
+        for (int idx = tid; idx < R2 * hs; idx += 128) s_q[idx / hs][idx % hs] = (idx < r2 * hs) ? q[(int64_t)g * r2 * hs + idx] : 0.f; // r2 <= R2 query heads per kv head
         __syncthreads();
         float qv[R2][8];
 #pragma unroll
@@ -295,12 +295,12 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
                     if (s < steps) sum[hh] = __fmaf_rn(kv[t][s], qv[hh][s], sum[hh]); // ggml_vec_dot_f32 lane chain (ggml.c:2092-2131)
             }
             ps_f32x8_reduce_n<R2>(sum);
-            if (lane < R2 && j0 + t < n_kv) {
+            if (lane < r2 && j0 + t < n_kv) {
                 float v = sum[0];
 #pragma unroll
                 for (int hh = 1; hh < R2; hh++)
                     if (lane == hh) v = sum[hh];
-                sc[(int64_t)(g * R2 + lane) * n_ctx + j0 + t] = __fadd_rn(__fmul_rn(v, scale), 0.0f);
+                sc[(int64_t)(g * r2 + lane) * n_ctx + j0 + t] = __fadd_rn(__fmul_rn(v, scale), 0.0f);
             }
         }
     }
@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 template <int R2>
 __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ att, const float *__restrict__ sc, const float *__restrict__ vct,
                                                   const int32_t *__restrict__ pos_dev, int hs, int n_ctx, long long *tl, const PsTpOut *tpo,
-                                                  int v_smem) {
+                                                  int v_smem, int r2) {
     extern __shared__ __align__(128) float s_p[]; // [R2][stride] probabilities, then (v_smem) [8][stride] V^T rows
     __shared__ double shd[PS_A2_THREADS / 32];
     __shared__ float shf[PS_A2_THREADS / 32];
@@ -339,11 +339,11 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
     // The position (last kernel of the previous step) and the V^T rows (column `pos` comes from the q|k|v kernel, which was
     // complete before the scores kernel let this grid start) are older than this kernel's predecessor: the V^T copies are
     // requested BEFORE the dependency wait; only the score rows follow it.
-    const int64_t n_kv = (int64_t)pos_dev[0] + 1;
+    const int64_t n_kv_all = (int64_t)pos_dev[0] + 1, n_kv = n_kv_all;
     constexpr int TPH = PS_A2_THREADS / R2, WPH = TPH / 32;          // threads / warps per head
     const int hh = tid / TPH, ht = tid % TPH;
     const int64_t stride = (n_kv + 31) & ~(int64_t)31;
-    const int64_t n8 = n_kv & ~(int64_t)7;
+    const int64_t n8_all = n_kv & ~(int64_t)7;
     float *s_v = s_p + R2 * stride;
     const int n_rows = min(8, hs - (int)blockIdx.x * 8);
     // rows are 16-byte aligned (n_ctx % 4 == 0); a copy may run up to 3 floats past n_kv, still inside its row
@@ -362,14 +362,16 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
         if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
     } while (0)
     if (tid == 0) {
-        ps_mbar_expect_tx(&bar_s, bytes * R2);
+        ps_mbar_expect_tx(&bar_s, bytes * r2);
 #pragma unroll
-        for (int h2 = 0; h2 < R2; h2++) ps_bulk_g2s(s_p + h2 * stride, sc + (int64_t)(g * R2 + h2) * n_ctx, bytes, &bar_s);
+        for (int h2 = 0; h2 < R2; h2++)
+            if (h2 < r2) ps_bulk_g2s(s_p + h2 * stride, sc + (int64_t)(g * r2 + h2) * n_ctx, bytes, &bar_s);
     }
     __syncthreads(); // the barrier words are initialised for everybody
     ps_mbar_wait(&bar_s, 0);
     {
         float *pp = s_p + hh * stride;
+        const int64_t n_kv = (hh < r2) ? n_kv_all : 0, n8 = (hh < r2) ? n8_all : 0; // template heads beyond r2 (r2 <= R2 query heads per kv head) idle
         float mx = -INFINITY;
         for (int64_t j = ht; j < n_kv; j += TPH) mx = fmaxf(mx, pp[j]);
 #pragma unroll
@@ -449,16 +451,16 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
 #pragma unroll
             for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fadd_rn(sum[h2], __fmul_rn(v, s_p[h2 * stride + np + t]));
         }
-        if (lane < R2) {
+        if (lane < r2) {
             float v = sum[0];
 #pragma unroll
             for (int h2 = 1; h2 < R2; h2++)
                 if (lane == h2) v = sum[h2];
-            att[(int64_t)(g * R2 + lane) * hs + d] = v;
+            att[(int64_t)(g * r2 + lane) * hs + d] = v;
             if (tpo) { // all-gather by peer stores
-                if (tpo->peer_ll[0]) ps_tp_ll_store(tpo, (int64_t)(g * R2 + lane) * hs + d, v, ll_epoch);
+                if (tpo->peer_ll[0]) ps_tp_ll_store(tpo, (int64_t)(g * r2 + lane) * hs + d, v, ll_epoch);
                 else
-                    for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * R2 + lane) * hs + d] = v;
+                    for (int p = 0; p < tpo->n; p++) tpo->peer_dst[p][(int64_t)(g * r2 + lane) * hs + d] = v;
             }
         }
     }

@@ -59,6 +59,10 @@ PRESETS: Dict[str, ModelShape] = {
     "tiny-llama": ModelShape("tiny-llama", "llama", 512, 1536, 2, 8, 2, 64, 1024, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=512),
     "tiny-llama-hs128": ModelShape("tiny-llama-hs128", "llama", 512, 1024, 2, 4, 2, 128, 768, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=384),
     "tiny-qwen2": ModelShape("tiny-qwen2", "qwen2", 256, 608, 2, 4, 2, 64, 512, True, 2, 1e6, 1e-6, GGML_Q4_0, n_ctx=256, qkv_bias=True),
+    # query heads per kv head that are not a power of two (Qwen2-0.5B has 14 / 2 = 7): the decode attention kernels run
+    # with the next power-of-two template and r2 active heads
+    "tiny-qwen2-r7": ModelShape("tiny-qwen2-r7", "qwen2", 448, 608, 2, 7, 1, 64, 512, True, 2, 1e6, 1e-6, GGML_Q4_0, n_ctx=256, qkv_bias=True),
+    "tiny-q8-r3": ModelShape("tiny-q8-r3", "llama", 384, 512, 2, 6, 2, 64, 512, False, 0, 1e4, 1e-5, GGML_Q8_0, n_ctx=256),
     "tiny-q8": ModelShape("tiny-q8", "llama", 256, 512, 2, 4, 4, 64, 512, False, 0, 1e4, 1e-5, GGML_Q8_0, n_ctx=256),
     # real per-layer shapes of the BASELINE models with few layers / small vocab (exercise nb = 8/32 and 16/56 paths)
     "slice-1b": ModelShape("slice-1b", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),

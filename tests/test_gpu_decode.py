@@ -11,7 +11,8 @@ from tests import _model as M
 pytestmark = pytest.mark.gpu
 
 
-def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0, attn_fused=0):
+def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0, attn_fused=0, ops_graph=0):
+    cm.be.set_option("ops_graph", ops_graph)  # 0 with fused = 0: the plain table-op path (one launch per op, host-fed positions)
     cm.be.set_option("fused", fused)
     cm.be.set_option("graph", graph)
     cm.be.set_option("pdl", pdl)
@@ -108,3 +109,46 @@ def test_matvec_ksplit_and_deferred_stream_are_bit_exact(preset):
         L.assert_bit_equal(lg_f, lg_u, f"{preset}: rw_ksplit={ksplit} rw_defer={defer} rw_kb={kb}")
         assert ids_f == ids_u
     cm.close()
+
+
+@pytest.mark.parametrize("preset", ["tiny-qwen2", "tiny-qwen2-r7", "tiny-q8", "tiny-q8-r3", "tiny-mixed", "tiny-llama"])
+def test_graph_replayed_operator_table_step_for_every_weight_type(preset):
+    """Models off the all-Q4_K fused path (Q4_0 / Q8_0 matrices, a Q6_K output matrix, NEOX rope + biases, 3 or 7 query heads per
+    kv head) decode through decode_step_ops: table-op weight products + the position-from-device decode attention kernels,
+    captured once and replayed per token, greedy pick on the device.  Bit-exact vs the plain table-op path and the oracle."""
+    d = M.model_dir(preset)
+    shape = synth.PRESETS[preset]
+    prompt = synth.random_prompt(shape.vocab_size, 29, seed=13)
+    n_dec = 12
+    cm = capi.CudaModel(d, max_batch=16)
+    ids_u, lg_u = run(cm, prompt, n_dec, fused=0, graph=0, ops_graph=0)
+    ids_n, lg_n = run(cm, prompt, n_dec, fused=0, graph=0, ops_graph=1)        # the step's kernels launched one by one
+    L.assert_bit_equal(lg_n, lg_u, f"{preset}: operator-table step vs table ops")
+    n0 = cm.be.counter("graph_replays")
+    ids_g, lg_g = run(cm, prompt, n_dec, fused=0, graph=1, ops_graph=1)        # replayed as a graph, host reads the logits
+    L.assert_bit_equal(lg_g, lg_u, f"{preset}: graph-replayed operator-table step vs table ops")
+    assert ids_u == ids_n == ids_g and cm.be.counter("graph_replays") >= n0 + n_dec
+    cm.reset(); cm.prefill(prompt, 16)
+    n0 = cm.be.counter("graph_replays")
+    ids_d = list(cm.decode_greedy(int(prompt[-1]), n_dec))                     # device-resident loop: pick + feedback on the device
+    assert ids_d == ids_u and cm.be.counter("graph_replays") >= n0 + n_dec
+    L.assert_bit_equal(cm.be.read_device(cm.be.logits_dev(), shape.vocab_size), lg_u[-1], f"{preset}: last logits of the device loop")
+    # all-Q4_0 / all-Q8_0 models: the FUSED 32-block path (ps_mv32.cuh: TMA-fed octet mat-vec with the RMSNorm / SiLU.up +
+    # Q8_0 quantiser prologue and bias / residual / pick epilogue, 7 launches per layer)
+    uniform32 = shape.wtype in (synth.GGML_Q4_0, synth.GGML_Q8_0) and shape.output_type in (None, shape.wtype)
+    assert cm.be.counter("mv32_ok") == (1 if uniform32 else 0)
+    if uniform32:
+        ids_m, lg_m = run(cm, prompt, n_dec, fused=1, graph=0, pdl=0)
+        L.assert_bit_equal(lg_m, lg_u, f"{preset}: fused 32-block step vs table ops")
+        ids_p, lg_p = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1)
+        L.assert_bit_equal(lg_p, lg_u, f"{preset}: fused 32-block step, PDL + graph, vs table ops")
+        cm.reset(); cm.prefill(prompt, 16)
+        ids_l = list(cm.decode_greedy(int(prompt[-1]), n_dec))
+        assert ids_m == ids_p == ids_l == ids_u
+        L.assert_bit_equal(cm.be.read_device(cm.be.logits_dev(), shape.vocab_size), lg_u[-1], f"{preset}: last logits of the fused device loop")
+    cm.close()
+    om = M.OracleModel(d)
+    ids_o, lg_o = om.generate(prompt, n_dec, batch_size=16)
+    om.close()
+    L.assert_bit_equal(lg_u, lg_o, f"{preset}: table ops vs oracle")
+    assert ids_u == ids_o
