@@ -202,6 +202,27 @@ def extra_config1_1b(args, hbm_peak):
     return out, m, tensors, shape
 
 
+def extra_config0_qwen2(args, hbm_peak):
+    """BASELINE configs[0]: Qwen2-0.5B Q4_0 (the reference's own CPU-runnable case), 32-token prompt, greedy decode - the fused
+    32-block path (ps_mv32.cuh: Q4_0 weights x Q8_0 activations, NEOX rope, q|k|v biases, 7 query heads per kv head)."""
+    from powerserve_b200 import capi
+    shape = synth.PRESETS["qwen2-0.5b"]
+    shape.n_ctx = 4096
+    tensors = synth.generate_tensors(shape, args.seed)
+    tmap = {n: gguf.GGUFTensor(n, t, tuple(s), np.ascontiguousarray(d).view(np.uint8).reshape(-1)) for n, t, s, d in tensors}
+    desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=32, n_ctx=shape.n_ctx)
+    m = capi.CudaModel(desc=desc, tensors=tmap)
+    prompt = synth.random_prompt(shape.vocab_size, 33, seed=1234)
+    m.prefill(prompt, 32)
+    tps, ms = decode_leg(m, int(prompt[-1]), 64, 8)
+    wb = weight_bytes_per_token(shape)
+    out = {"workload": "qwen2-0.5b Q4_0 synthetic: 32-token prompt, 64 greedy decode tokens (BASELINE configs[0])", "value": tps, "unit": "tok/s", "ms_per_step": ms,
+           "fused_32_block_path": bool(m.be.counter("mv32_ok")), "weight_bytes_per_token": wb,
+           "roofline_step": {"achieved": wb / (ms * 1e-3) / 1e9, "peak": hbm_peak, "frac": wb / (ms * 1e-3) / 1e9 / hbm_peak, "unit": "GB/s"}}
+    m.close()
+    return out
+
+
 def extra_config3_spec(args, target, target_shape, draft, n_tokens=96):
     """BASELINE configs[3]: Llama-3.1-8B target + Llama-3.2-1B draft, token-tree speculative decoding (draft_batch_size 12, tree
     defaults of speculative_config.hpp:21-36), 32-token prompt.  Synthetic weights: the two models are uncorrelated, so the
@@ -455,6 +476,10 @@ def main():
             m1b.close()
         except Exception as e:
             extras["configs[1]"] = {"value": None, "why": str(e)[:300]}
+        try:
+            extras["configs[0]"] = extra_config0_qwen2(args, hbm_peak)
+        except Exception as e:
+            extras["configs[0]"] = {"value": None, "why": str(e)[:300]}
         out["extras"] = extras
     # --- parity on the benchmarked weights (every N): teacher-forced sample, ids + logits-bits hash; rank 0 checks them against
     # the compiled CPU reference (AVX2 build) run on the same weights and inputs

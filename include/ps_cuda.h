@@ -156,6 +156,23 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
  * llama_model.cpp:124-128 with top_k = 1) and logits_host receives bs int32 token ids instead. */
 int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos, int bs, const uint8_t *tree_mask, int lm_head,
                          float *logits_host);
+/* ---------------------------------------------------------------------------------------------- sessions
+ * Server-side batching (app/server/server_handler.hpp:512-720): the reference serves one generation
+ * per model at a time because the KV position is shared state (server_handler.hpp:224-240).  A context can hold several
+ * independent KV sets over one set of weights.  Session 0 is the context's own cache.  ps_cuda_session_select makes a
+ * session the target of every single-sequence call (forward / forward_tree / decode_greedy / kv_*), so prefill and KV
+ * bookkeeping work per session unchanged; ps_cuda_forward_sessions advances n DISTINCT sessions by one token each in one
+ * forward pass: one weight stream for the n columns, attention per column over its own cache and position.  logits_host
+ * ([n][vocab], may be NULL) and greedy_ids ([n], may be NULL: arg-max on the device) are in batch order.  Each column's
+ * result is bit-identical to decoding that session alone with batch 1. */
+int ps_cuda_session_create(ps_cuda_ctx *ctx, int *session_id);
+int ps_cuda_session_destroy(ps_cuda_ctx *ctx, int session_id);   /* not the selected one */
+int ps_cuda_session_select(ps_cuda_ctx *ctx, int session_id);
+int ps_cuda_session_current(ps_cuda_ctx *ctx);
+int ps_cuda_session_position(ps_cuda_ctx *ctx, int session_id);  /* -1: unknown session */
+int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const int32_t *tokens, int n, int lm_head,
+                             float *logits_host, int32_t *greedy_ids);
+
 /* Model::decode with top_k = 1 (llama_model.cpp:119-132): forward + arg-max on the device; only the token id comes
  * back.  `n_steps` > 1 keeps feeding the produced id back in without a host round trip (ids_host gets n_steps ids). */
 int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, int32_t *ids_host);

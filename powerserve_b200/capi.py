@@ -99,6 +99,12 @@ def load_library() -> C.CDLL:
         "ps_cuda_forward": (ci, [vp, i32p, i32p, ci, ci, C.c_void_p]),
         "ps_cuda_forward_tree": (ci, [vp, i32p, i32p, ci, C.c_void_p, ci, C.c_void_p]),
         "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
+        "ps_cuda_session_create": (ci, [vp, C.POINTER(ci)]),
+        "ps_cuda_session_destroy": (ci, [vp, ci]),
+        "ps_cuda_session_select": (ci, [vp, ci]),
+        "ps_cuda_session_current": (ci, [vp]),
+        "ps_cuda_session_position": (ci, [vp, ci]),
+        "ps_cuda_forward_sessions": (ci, [vp, i32p, i32p, ci, ci, fp, i32p]),
         "ps_cuda_logits_dev": (vp, [vp]),
         "ps_cuda_tp_unique_id": (ci, [vp]),
         "ps_cuda_tp_init": (ci, [vp, vp]),
@@ -393,6 +399,32 @@ class CudaModel:
         ids = np.zeros(n_steps, np.int32)
         self.be._ck(self.be.L.ps_cuda_decode_greedy(self.be.h, int(first_token), n_steps, ids.ctypes.data_as(C.POINTER(C.c_int32))))
         return ids
+
+    # ---- sessions (server-side batching): independent KV sets over this model's weights
+    def session_create(self) -> int:
+        sid = C.c_int(0)
+        self.be._ck(self.be.L.ps_cuda_session_create(self.be.h, C.byref(sid)))
+        return sid.value
+
+    def session_destroy(self, sid: int):
+        self.be._ck(self.be.L.ps_cuda_session_destroy(self.be.h, sid))
+
+    def session_select(self, sid: int):
+        self.be._ck(self.be.L.ps_cuda_session_select(self.be.h, sid))
+
+    def session_position(self, sid: int) -> int:
+        return self.be.L.ps_cuda_session_position(self.be.h, sid)
+
+    def forward_sessions(self, session_ids, tokens, lm_head: bool = True, want_logits: bool = True):
+        """one token of each session in ONE forward pass -> (logits [n][vocab] or None, device arg-max ids [n])"""
+        sids, toks = _i32(session_ids), _i32(tokens)
+        n = len(sids)
+        logits = np.empty((n, self.desc.vocab_size), np.float32) if (lm_head and want_logits) else None
+        ids = np.zeros(n, np.int32)
+        self.be._ck(self.be.L.ps_cuda_forward_sessions(self.be.h, sids.ctypes.data_as(C.POINTER(C.c_int32)), toks.ctypes.data_as(C.POINTER(C.c_int32)), n,
+                                                       1 if lm_head else 0, logits.ctypes.data_as(C.POINTER(C.c_float)) if logits is not None else None,
+                                                       ids.ctypes.data_as(C.POINTER(C.c_int32)) if lm_head else None))
+        return logits, ids
 
     def prefill(self, prompt, batch_size: int = 128):
         """ModelTokenIterator's prefill loop (src/model/model.hpp:147-160): prompt[:-1] in chunks, lm_head = false."""

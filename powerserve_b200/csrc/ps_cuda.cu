@@ -92,6 +92,12 @@ struct ps_cuda_ctx {
     // kv cache
     std::vector<float *> kc, vct;
     int position = 0;
+    // server-side batching: independent KV sets over one set of weights; the ACTIVE session's state lives in kc / vct /
+    // position / slot_mask above, the others are parked here
+    struct KvSet { std::vector<float *> kc, vct; int position = 0; std::vector<uint8_t> slot_mask; };
+    std::unordered_map<int, KvSet> sessions;
+    int cur_session = 0, next_session = 1;
+    float **sess_ptrs_dev = nullptr, **h_sess_ptrs = nullptr; // [n_layers][2][max_batch] cache pointers of the current session batch
     // speculative decode (kv_cache.hpp:97-276): per-slot mask, last batch kept aside for KVCacheInterface::copy
     std::vector<uint8_t> slot_mask;      // host copy, 1 = masked (not attended)
     bool slot_mask_dirty = true;
@@ -1755,11 +1761,12 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
 // path lives in ps_decode.cuh and is bit-identical).
 // `tree_base` >= 0: a tree batch (ps_cuda_forward_tree) - K / V rows go to cache SLOTS tree_base .. tree_base + bs - 1 whatever the
 // token positions are, and the attention bias is ctx->tree_bias (slot mask + in-batch tree mask) instead of the causal `pos` mask.
-static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree_base = -1) {
+struct SessRun { int n_kv_max; };
+static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree_base = -1, const SessRun *sess = nullptr) {
     const ps_cuda_model_desc &d = ctx->d;
     const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
     const bool tree = tree_base >= 0;
-    const int64_t n_kv = tree ? (int64_t)tree_base + bs : (int64_t)pos0 + bs; // pos.back() + 1
+    const int64_t n_kv = sess ? (int64_t)sess->n_kv_max : tree ? (int64_t)tree_base + bs : (int64_t)pos0 + bs; // pos.back() + 1 (session batch: the longest row)
     const float kq_scale = 1.0f / sqrtf((float)hs);
     const bool tc = ctx->tc_ok && ctx->opt_tc && ctx->opt_fused && bs >= 16; // tensor-core GEMM on the fp16-expanded operands
     const bool rw = ctx->fused_ok && ctx->opt_fused && (bs > 1 || tree); // octet-interleaved copies exist: multi-column row-walker
@@ -1767,7 +1774,11 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
     PS_LAUNCH_CK();
     static bool attr[64] = {};
-    if (!attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr[ctx->device] = true; }
+    if (!attr[ctx->device]) {
+        PS_CK(cudaFuncSetAttribute(ps_k_softmax_ext, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_sess_softmax, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        attr[ctx->device] = true;
+    }
     for (int L = 0; L < d.n_layers; L++) {
         const LayerDev &ld = ctx->layers[L];
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ld.attn_norm, dim, d.norm_eps);
@@ -1796,7 +1807,10 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
         PS_LAUNCH_CK();
         ps_k_rope<<<dim3((unsigned)nkv, (unsigned)bs), 64, 0, ctx->stream>>>(ctx->kr, ctx->k, (int)hs, d.rope_n_dims, d.rope_type & 2, ctx->pos_dev, ctx->rope_table);
         PS_LAUNCH_CK();
-        if (tree) {
+        if (sess) {
+            float **pl = ctx->sess_ptrs_dev + (size_t)L * 2 * d.max_batch;
+            ps_k_sess_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(pl, pl + d.max_batch, ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
+        } else if (tree) {
             const size_t lstride = (size_t)std::min<int64_t>(d.max_batch, 32) * (size_t)kvd;
             ps_k_kv_store_at<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->k_stage + L * lstride, ctx->v_stage + L * lstride, ctx->kr, ctx->v,
                                                                          kvd, d.n_ctx, tree_base, bs);
@@ -1804,6 +1818,16 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
             ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
         }
         PS_LAUNCH_CK();
+        if (sess) { // every column attends over its own session's cache at its own position
+            float **pl = ctx->sess_ptrs_dev + (size_t)L * 2 * d.max_batch;
+            const int64_t cs = nh * (int64_t)d.n_ctx;
+            ps_k_sess_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv, (unsigned)bs), 128, 0, ctx->stream>>>(ctx->kq, pl, ctx->qr, (int)hs, (int)nh, (int)nkv, ctx->pos_dev, cs);
+            PS_LAUNCH_CK();
+            ps_k_sess_softmax<<<dim3((unsigned)nh, (unsigned)bs), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->pos_dev, cs, kq_scale);
+            PS_LAUNCH_CK();
+            ps_k_sess_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv, (unsigned)bs), 128, 0, ctx->stream>>>(ctx->att, pl + d.max_batch, ctx->kq, (int)hs, (int)nh, (int)nkv, ctx->pos_dev, d.n_ctx, cs);
+            PS_LAUNCH_CK();
+        } else {
         if (bs >= 8) {
             const int r2 = (int)(nh / nkv);
             const int qb = std::max(1, std::min(bs, (int)(8192 / (r2 * hs))));
@@ -1824,6 +1848,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
             ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
         }
         PS_LAUNCH_CK();
+        }
         if (tc) {
             if ((rc = tc_prep_b(ctx, ctx->att, (int)qdim, bs))) return rc;
             if ((rc = tc_single(ctx, ld.tc_o, (int)dim, (int)qdim, ctx->x, bs, ctx->x))) return rc;
@@ -2086,6 +2111,178 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
     ctx->position = pos[0] + bs; // m_kv->advance(batch_size), llama_model.cpp:109
     kv_set_mask(ctx, 0, ctx->position, 0);
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------- sessions (server-side batching)
+// SURVEY section 8 f4 (app/server/server_handler.hpp:512-720): the reference serves one generation per model at a time - its
+// KV position is shared state.  Here a context can hold several independent KV sets ("sessions") over ONE set of weights:
+// ps_cuda_session_select makes one of them the target of every single-sequence call (forward / decode_greedy / kv_*: prefill
+// and bookkeeping work unchanged), and ps_cuda_forward_sessions advances n sessions by one token each in ONE forward pass -
+// the weight stream is read once for the n columns (multi-column row-walker for n < 16, tcgen05 GEMM from 16 up), attention
+// runs per column over its own session's cache.  A session's logits are bit-identical to decoding it alone with batch 1.
+static int refresh_kv_tables(ps_cuda_ctx *ctx) {
+    const ps_cuda_model_desc &d = ctx->d;
+    std::vector<float *> ptrs(2 * (size_t)d.n_layers);
+    for (int L = 0; L < d.n_layers; L++) { ptrs[L] = ctx->kc[L]; ptrs[d.n_layers + L] = ctx->vct[L]; }
+    PS_CK(cudaMemcpyAsync(ctx->kv_ptrs_dev, ptrs.data(), sizeof(float *) * ptrs.size(), cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->st_layers && ctx->bound && ctx->fused_ok) {
+        std::vector<PsStLayer> tab(d.n_layers);
+        for (int L = 0; L < d.n_layers; L++) {
+            const LayerDev &ld = ctx->layers[L];
+            tab[L] = PsStLayer{ld.rw_qkv, ld.rw_o, ld.rw_gu, ld.rw_down, ld.attn_norm, ld.ffn_norm, d.qkv_bias ? ld.q_bias : nullptr,
+                               d.qkv_bias ? ld.k_bias : nullptr, d.qkv_bias ? ld.v_bias : nullptr, ctx->kc[L], ctx->vct[L]};
+        }
+        PS_CK(cudaMemcpyAsync(ctx->st_layers, tab.data(), sizeof(PsStLayer) * (size_t)d.n_layers, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    PS_CK(cudaStreamSynchronize(ctx->stream)); // the host vectors die here
+    if (ctx->g_step) { cudaGraphExecDestroy(ctx->g_step); ctx->g_step = nullptr; } // the captured steps hold the old cache pointers
+    if (ctx->g_fwd) { cudaGraphExecDestroy(ctx->g_fwd); ctx->g_fwd = nullptr; }
+    return 0;
+}
+
+int ps_cuda_session_create(ps_cuda_ctx *ctx, int *session_id) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (!session_id) return fail(ctx, PS_CUDA_ERR_INVALID, "session_create: null argument");
+    if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "sessions are single-GPU");
+    PS_CK(cudaSetDevice(ctx->device));
+    const ps_cuda_model_desc &d = ctx->d;
+    const size_t bytes = 4 * (size_t)d.n_kv_heads * d.head_size * d.n_ctx;
+    ps_cuda_ctx::KvSet ks;
+    ks.kc.resize(d.n_layers); ks.vct.resize(d.n_layers);
+    for (int L = 0; L < d.n_layers; L++) {
+        int rc;
+        if ((rc = dev_alloc(ctx, (void **)&ks.kc[L], bytes)) || (rc = dev_alloc(ctx, (void **)&ks.vct[L], bytes))) return rc;
+        PS_CK(cudaMemsetAsync(ks.kc[L], 0, bytes, ctx->stream));
+        PS_CK(cudaMemsetAsync(ks.vct[L], 0, bytes, ctx->stream));
+    }
+    ks.slot_mask.assign((size_t)d.n_ctx, 1);
+    const int id = ctx->next_session++;
+    ctx->sessions.emplace(id, std::move(ks));
+    *session_id = id;
+    return 0;
+}
+
+int ps_cuda_session_destroy(ps_cuda_ctx *ctx, int session_id) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (session_id == ctx->cur_session) return fail(ctx, PS_CUDA_ERR_INVALID, "session_destroy: session %d is selected", session_id);
+    auto it = ctx->sessions.find(session_id);
+    if (it == ctx->sessions.end()) return fail(ctx, PS_CUDA_ERR_INVALID, "session_destroy: unknown session %d", session_id);
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    for (auto *vec : {&it->second.kc, &it->second.vct})
+        for (float *p : *vec) {
+            for (size_t i = 0; i < ctx->owned.size(); i++)
+                if (ctx->owned[i] == p) { ctx->owned.erase(ctx->owned.begin() + i); break; }
+            PS_CK(cudaFree(p));
+        }
+    ctx->sessions.erase(it);
+    return 0;
+}
+
+int ps_cuda_session_current(ps_cuda_ctx *ctx) { return ctx->cur_session; }
+
+int ps_cuda_session_select(ps_cuda_ctx *ctx, int session_id) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (session_id == ctx->cur_session) return 0;
+    auto it = ctx->sessions.find(session_id);
+    if (it == ctx->sessions.end() && session_id != 0) return fail(ctx, PS_CUDA_ERR_INVALID, "session_select: unknown session %d", session_id);
+    PS_CK(cudaSetDevice(ctx->device));
+    // park the active state under its id, then load the requested one (session 0 = the context's own cache)
+    ps_cuda_ctx::KvSet cur;
+    cur.kc = ctx->kc; cur.vct = ctx->vct; cur.position = ctx->position; cur.slot_mask = ctx->slot_mask;
+    ps_cuda_ctx::KvSet next = std::move(ctx->sessions.at(session_id));
+    ctx->sessions.erase(session_id);
+    ctx->sessions.emplace(ctx->cur_session, std::move(cur));
+    ctx->kc = next.kc; ctx->vct = next.vct; ctx->position = next.position; ctx->slot_mask = next.slot_mask;
+    ctx->slot_mask_dirty = true;
+    ctx->last_batch = 0;
+    ctx->cur_session = session_id;
+    return refresh_kv_tables(ctx);
+}
+
+int ps_cuda_session_position(ps_cuda_ctx *ctx, int session_id) {
+    if (session_id == ctx->cur_session) return ctx->position;
+    auto it = ctx->sessions.find(session_id);
+    return it == ctx->sessions.end() ? -1 : it->second.position;
+}
+
+int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const int32_t *tokens, int n, int lm_head, float *logits_host, int32_t *greedy_ids) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const ps_cuda_model_desc &d = ctx->d;
+    if (!ctx->bound) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: no model bound");
+    if (ctx->tp > 1) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward_sessions: sessions are single-GPU");
+    if (!session_ids || !tokens || n <= 0 || n > d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: batch %d outside [1,%d]", n, d.max_batch);
+    if ((size_t)d.n_ctx * 4 > 160 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "forward_sessions: n_ctx = %d exceeds the soft-max kernel's shared memory", d.n_ctx);
+    PS_CK(cudaSetDevice(ctx->device));
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    if (!ctx->sess_ptrs_dev) {
+        const size_t bytes = sizeof(float *) * 2 * (size_t)d.n_layers * (size_t)d.max_batch;
+        int rc = dev_alloc(ctx, (void **)&ctx->sess_ptrs_dev, bytes);
+        if (rc) return rc;
+        PS_CK(cudaMallocHost(&ctx->h_sess_ptrs, bytes));
+    }
+    std::vector<ps_cuda_ctx::KvSet *> sets(n);
+    ps_cuda_ctx::KvSet active; // a view of the selected session's state
+    int n_kv_max = 0;
+    for (int i = 0; i < n; i++) {
+        if (tokens[i] < 0 || tokens[i] >= d.vocab_size) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: token %d outside the vocabulary", tokens[i]);
+        for (int j = 0; j < i; j++)
+            if (session_ids[j] == session_ids[i]) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: session %d appears twice", session_ids[i]);
+        int pos;
+        const std::vector<float *> *kc, *vct;
+        if (session_ids[i] == ctx->cur_session) { pos = ctx->position; kc = &ctx->kc; vct = &ctx->vct; sets[i] = nullptr; }
+        else {
+            auto it = ctx->sessions.find(session_ids[i]);
+            if (it == ctx->sessions.end()) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: unknown session %d", session_ids[i]);
+            pos = it->second.position; kc = &it->second.kc; vct = &it->second.vct; sets[i] = &it->second;
+        }
+        if (pos >= d.n_ctx) return fail(ctx, PS_CUDA_ERR_KV_FULL, "the length of kvcache is up to the preset threshold: %d", d.n_ctx);
+        ctx->h_tokens[i] = tokens[i];
+        ctx->h_pos[i] = pos;
+        n_kv_max = std::max(n_kv_max, pos + 1);
+        for (int L = 0; L < d.n_layers; L++) {
+            ctx->h_sess_ptrs[((size_t)L * 2 + 0) * d.max_batch + i] = (*kc)[L];
+            ctx->h_sess_ptrs[((size_t)L * 2 + 1) * d.max_batch + i] = (*vct)[L];
+        }
+    }
+    PS_CK(cudaMemcpyAsync(ctx->tokens_dev, ctx->h_tokens, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->pos_dev, ctx->h_pos, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->sess_ptrs_dev, ctx->h_sess_ptrs, sizeof(float *) * 2 * (size_t)d.n_layers * (size_t)d.max_batch, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->h2d += (int64_t)n * 8 + (int64_t)sizeof(float *) * 2 * d.n_layers * d.max_batch;
+    PS_CK(cudaEventRecord(ctx->ev0, ctx->stream));
+    SessRun sr{n_kv_max};
+    int rc = forward_ops(ctx, n, lm_head, 0, -1, &sr);
+    if (rc) return rc;
+    ctx->logits_last = ctx->logits;
+    if (lm_head && greedy_ids) {
+        for (int i = 0; i < n; i++) {
+            ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits + (size_t)i * d.vocab_size, d.vocab_size, ctx->ids_dev + i, ctx->ids_dev + d.max_batch + i);
+            PS_LAUNCH_CK();
+        }
+        PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
+    if (lm_head && logits_host) {
+        const size_t bytes = (size_t)n * d.vocab_size * 4;
+        if (bytes > ctx->h_logits_cap) {
+            if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
+            ctx->h_logits = nullptr;
+            ctx->h_logits_cap = 0;
+            PS_CK(cudaMallocHost(&ctx->h_logits, bytes));
+            ctx->h_logits_cap = bytes;
+        }
+        PS_CK(cudaMemcpyAsync(ctx->h_logits, ctx->logits, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+        if ((rc = sync_and_check(ctx))) return rc;
+        memcpy(logits_host, ctx->h_logits, bytes);
+        ctx->d2h += (int64_t)bytes;
+    } else if ((rc = sync_and_check(ctx))) return rc;
+    if (lm_head && greedy_ids) { memcpy(greedy_ids, ctx->h_ids, (size_t)n * 4); ctx->d2h += (int64_t)n * 4; }
+    { float ms = 0.f; PS_CK(cudaEventElapsedTime(&ms, ctx->ev0, ctx->ev1)); ctx->last_ms = ms; }
+    for (int i = 0; i < n; i++) { // m_kv->advance(1) of every session in the batch
+        if (!sets[i]) { kv_set_mask(ctx, ctx->position, ctx->position + 1, 0); ctx->position += 1; }
+        else { sets[i]->slot_mask[sets[i]->position] = 0; sets[i]->position += 1; }
+    }
     return 0;
 }
 

@@ -853,6 +853,110 @@ __global__ void __launch_bounds__(128) ps_k_matmul_f32(float *__restrict__ dst, 
     }
 }
 
+// ====================================================================================================================
+// Server-side batching: one token of each of n independent SESSIONS per forward pass.  The weight
+// products run once for the n columns (one weight stream); attention is per column over that session's OWN cache at its OWN
+// position.  Column `c` = blockIdx.z; kc_ptrs / vct_ptrs hold the session's cache of the current layer, pos[c] its
+// position.  The arithmetic of every column is that of the bs = 1 operator-table kernels above (ps_k_kv_store,
+// ps_k_attn_scores, ps_k_softmax_ext with the position mask, ps_k_attn_pv), so a session's result does not depend on which
+// other sessions share the batch.
+// ====================================================================================================================
+__global__ void ps_k_sess_kv_store(float *const *__restrict__ kc_ptrs, float *const *__restrict__ vct_ptrs, const float *__restrict__ k,
+                                   const float *__restrict__ v, int64_t kv_dim, int64_t n_ctx, const int32_t *__restrict__ pos, int n) {
+    for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < kv_dim * n; t += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = t / kv_dim, e = t % kv_dim, p = pos[c];
+        kc_ptrs[c][p * kv_dim + e] = k[t];
+        vct_ptrs[c][e * n_ctx + p] = v[t];
+    }
+}
+
+// scores of column c: kq_c {n_kv_c, 1, n_heads} at kq + c * col_stride; one warp per (cache position, kv head)
+__global__ void __launch_bounds__(128) ps_k_sess_scores(float *__restrict__ kq, const float *const *__restrict__ kc_ptrs, const float *__restrict__ q, int hs,
+                                                        int n_heads, int n_kv_heads, const int32_t *__restrict__ pos, int64_t col_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.z, g = blockIdx.y;
+    const int64_t n_kv = (int64_t)pos[c] + 1, j = (int64_t)blockIdx.x * 4 + warp;
+    if (j >= n_kv) return;
+    const int r2 = n_heads / n_kv_heads, steps = hs / 32;
+    const float *krow = kc_ptrs[c] + j * (int64_t)(hs * n_kv_heads) + g * hs;
+    float kv[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) kv[s] = (s < steps) ? krow[32 * s + lane] : 0.f;
+    for (int hh = 0; hh < r2; hh++) {
+        const int h = g * r2 + hh;
+        const float *qv = q + ((int64_t)c * n_heads + h) * hs;
+        float sum = 0.f;
+#pragma unroll
+        for (int s = 0; s < 8; s++)
+            if (s < steps) sum = __fmaf_rn(kv[s], qv[32 * s + lane], sum); // ggml_vec_dot_f32 lane chain
+        sum = ps_f32x8_reduce(sum);
+        if (lane == 0) kq[c * col_stride + (int64_t)h * n_kv + j] = sum;
+    }
+}
+
+// softmax_ext of column c with the position mask of GET_MASK (every j <= pos: + 0.0f), rows of n_kv_c; grid (n_heads, n)
+__global__ void __launch_bounds__(256) ps_k_sess_softmax(float *__restrict__ kq, const int32_t *__restrict__ pos, int64_t col_stride, float scale) {
+    extern __shared__ float wp[];
+    __shared__ double sh[32];
+    __shared__ float shf[32];
+    const int c = blockIdx.y;
+    const int64_t ne0 = (int64_t)pos[c] + 1;
+    float *dp = kq + c * col_stride + (int64_t)blockIdx.x * ne0;
+    float mx = -INFINITY;
+    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) {
+        const float v = __fadd_rn(__fmul_rn(dp[j], scale), 0.f);
+        wp[j] = v;
+        mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
+    if ((threadIdx.x & 31) == 0) shf[threadIdx.x >> 5] = mx;
+    __syncthreads();
+    mx = shf[0];
+    for (int t = 1; t < (int)((blockDim.x + 31) >> 5); t++) mx = fmaxf(mx, shf[t]);
+    const int64_t n8 = ne0 & ~(int64_t)7;
+    double s = 0.0;
+    for (int64_t gi = threadIdx.x; gi < n8 / 8; gi += blockDim.x) {
+        float v[8];
+#pragma unroll
+        for (int l = 0; l < 8; l++) {
+            v[l] = ps_v_expf(__fadd_rn(wp[gi * 8 + l], -mx));
+            dp[gi * 8 + l] = v[l];
+        }
+        const float r0 = __fadd_rn(v[4], v[0]), r1 = __fadd_rn(v[5], v[1]), r2 = __fadd_rn(v[6], v[2]), r3 = __fadd_rn(v[7], v[3]);
+        s += (double)__fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
+    }
+    for (int64_t j = n8 + threadIdx.x; j < ne0; j += blockDim.x) {
+        const float v = ps_expf_glibc(__fadd_rn(wp[j], -mx));
+        dp[j] = v;
+        s += (double)v;
+    }
+    const double sum = ps_block_sum_double(s, sh);
+    const float inv = (float)(1.0 / sum);
+    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) dp[j] = __fmul_rn(dp[j], inv);
+}
+
+// P.V of column c: out[c][h * hs + d]; one warp per (kv head g, d)
+__global__ void __launch_bounds__(128) ps_k_sess_pv(float *__restrict__ out, const float *const *__restrict__ vct_ptrs, const float *__restrict__ kq, int hs,
+                                                    int n_heads, int n_kv_heads, const int32_t *__restrict__ pos, int64_t n_ctx, int64_t col_stride) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, c = blockIdx.z;
+    const int d = blockIdx.x * 4 + warp, g = blockIdx.y;
+    if (d >= hs) return;
+    const int r2 = n_heads / n_kv_heads;
+    const int64_t n_kv = (int64_t)pos[c] + 1, np = n_kv & ~(int64_t)31;
+    const float *vrow = vct_ptrs[c] + ((int64_t)g * hs + d) * n_ctx;
+    for (int hh = 0; hh < r2; hh++) {
+        const int h = g * r2 + hh;
+        const float *pr = kq + c * col_stride + (int64_t)h * n_kv;
+        float sum = 0.f;
+        for (int64_t s = 0; s < np; s += 32) sum = __fmaf_rn(vrow[s + lane], pr[s + lane], sum);
+        sum = ps_f32x8_reduce(sum);
+        if (lane == 0) {
+            for (int64_t j = np; j < n_kv; j++) sum = __fadd_rn(sum, __fmul_rn(vrow[j], pr[j])); // leftovers: mul, then add
+            out[((int64_t)c * n_heads + h) * hs + d] = sum;
+        }
+    }
+}
+
 // greedy pick (Model::decode with top_k = 1: ProbArray + greedy_sample, src/model/llama/llama_model.cpp:124-128):
 // first maximum wins.  One CTA; writes the id to `out[step]` and to `next_token` (device feedback for the next step).
 __global__ void __launch_bounds__(1024) ps_k_argmax(const float *__restrict__ logits, int64_t n, int32_t *__restrict__ out, int32_t *__restrict__ next_token) {
