@@ -223,6 +223,35 @@ def extra_config0_qwen2(args, hbm_peak):
     return out
 
 
+def extra_sessions(model, shape, hbm_peak, n_sess=32, n_steps=32):
+    """Server-side batching on the benchmarked model: n_sess independent sessions (own KV sets, 32-token
+    prompts) advanced one token each per forward pass through ps_cuda_forward_sessions - one weight stream per pass, so the
+    aggregate rate may exceed the one-sequence HBM roofline.  Device time of the passes; ids come back, logits stay on the device."""
+    sids = [0] + [model.session_create() for _ in range(n_sess - 1)]
+    toks = []
+    for k, sid in enumerate(sids):
+        model.session_select(sid)
+        model.reset()
+        p = synth.random_prompt(shape.vocab_size, 33, seed=4321 + k)
+        model.prefill(p, 32)
+        toks.append(int(p[-1]))
+    model.session_select(0)
+    ns = 0.0
+    for step in range(4 + n_steps):
+        _, ids = model.forward_sessions(sids, toks, want_logits=False)
+        toks = [int(t) for t in ids]
+        if step >= 4:
+            ns += model.be.counter("last_device_ns")
+    for sid in sids[1:]:
+        model.session_destroy(sid)
+    model.reset()
+    agg = n_sess * n_steps / (ns * 1e-9)
+    wb = weight_bytes_per_token(shape)
+    return {"workload": f"{n_sess} concurrent sessions x 1 token per forward pass, 32-token prompts (ps_cuda_forward_sessions)", "value": agg, "unit": "tok/s (aggregate)",
+            "ms_per_pass": ns * 1e-6 / n_steps, "sessions": n_sess, "one_sequence_hbm_roofline_tok_s": hbm_peak * 1e9 / wb,
+            "note": "every session's logits are bit-identical to decoding it alone (tests/test_gpu_sessions.py)"}
+
+
 def extra_config3_spec(args, target, target_shape, draft, n_tokens=96):
     """BASELINE configs[3]: Llama-3.1-8B target + Llama-3.2-1B draft, token-tree speculative decoding (draft_batch_size 12, tree
     defaults of speculative_config.hpp:21-36), 32-token prompt.  Synthetic weights: the two models are uncorrelated, so the
@@ -247,7 +276,7 @@ def extra_config3_spec(args, target, target_shape, draft, n_tokens=96):
             "ids_equal_plain_greedy_prefix": int(agree), "note": "synthetic (uncorrelated) weights: random-draft acceptance; losslessness is tested in tests/test_gpu_spec.py"}
 
 
-def extra_powerserve_stack(mdir, shape, prompt_len, n_decode, cpu_threads):
+def extra_powerserve_stack(mdir, shape, prompt_len, n_decode, cpu_threads, device_topk=0):
     """e2e through PowerServe's OWN stack: Model::forward -> graph -> executor -> CUDA_FORWARD op -> libps_cuda.so, logits into the
     executor's CPUBuffer, host arg-max per token (powerserve_b200/host/_build/ps_cuda_run, the drop-in demonstration of INTEGRATION.md)."""
     exe = os.path.join(ROOT, "powerserve_b200", "host", "_build", "ps_cuda_run")
@@ -255,7 +284,8 @@ def extra_powerserve_stack(mdir, shape, prompt_len, n_decode, cpu_threads):
         return {"value": None, "why": "powerserve_b200/host/_build/ps_cuda_run not built (needs /root/reference at build time)"}
     pf = os.path.join(mdir, "prompt_stack.txt")
     open(pf, "w").write(" ".join(str(int(t)) for t in synth.random_prompt(shape.vocab_size, prompt_len + 1, seed=1234)))
-    r = subprocess.run([exe, mdir, str(cpu_threads), "128", pf, str(n_decode), os.path.join(mdir, "stack_out")], capture_output=True, text=True, timeout=1200)
+    extra = ["--device-topk", str(device_topk)] if device_topk else []
+    r = subprocess.run([exe, mdir, str(cpu_threads), "128", pf, str(n_decode), os.path.join(mdir, "stack_out")] + extra, capture_output=True, text=True, timeout=1200)
     if r.returncode != 0:
         return {"value": None, "why": ("ps_cuda_run failed: " + r.stderr[-300:])}
     tm = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
@@ -477,6 +507,10 @@ def main():
         except Exception as e:
             extras["configs[1]"] = {"value": None, "why": str(e)[:300]}
         try:
+            extras["sessions"] = extra_sessions(model, shape, hbm_peak)
+        except Exception as e:
+            extras["sessions"] = {"value": None, "why": str(e)[:300]}
+        try:
             extras["configs[0]"] = extra_config0_qwen2(args, hbm_peak)
         except Exception as e:
             extras["configs[0]"] = {"value": None, "why": str(e)[:300]}
@@ -500,6 +534,9 @@ def main():
                     model.close()       # the stack binary binds its own context: free this one's HBM first
                     closed = True
                     out["e2e_powerserve_stack"] = extra_powerserve_stack(md.path, shape, args.prompt, min(args.steps, 64), cpu_threads)
+                    lazy = extra_powerserve_stack(md.path, shape, args.prompt, min(args.steps, 64), cpu_threads, device_topk=40)
+                    lazy["what"] = "the same stack with device-side sampling (SURVEY 8 f3): logits stay on the device, TopKSampler(40) runs there, 80 words per token cross PCIe"
+                    out["e2e_powerserve_stack_device_topk"] = lazy
                 if world == 1:
                     cp = synth.random_prompt(shape.vocab_size, 17, seed=1234)
                     res = cpu_reference_run(md.path, shape.vocab_size, cp, 9, cpu_threads)

@@ -178,6 +178,12 @@ int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const
 int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, int32_t *ids_host);
 /* device-side logits of the last forward ([bs][vocab]) for callers that sample on the GPU */
 const float *ps_cuda_logits_dev(ps_cuda_ctx *ctx);
+/* Device-side sampling: ps_cuda_forward / ps_cuda_forward_sessions accept logits_host == NULL with
+ * lm_head = 1 - the logits stay on the device - and ps_cuda_sample_topk returns what ProbArray holds after
+ * TopKSampler::apply (src/sampler/sampler.cpp:39-56, prob_array.hpp:43-49): the k <= 64 largest logits of row `row` of the
+ * last forward pass, descending (equal logits by ascending token id), with their token ids.  2 k words cross PCIe instead of
+ * the vocabulary's logits; the rest of the sampler chain (temperature, soft-max, top-p, stochastic pick) runs on k entries. */
+int ps_cuda_sample_topk(ps_cuda_ctx *ctx, int row, int k, float *logits_out, int32_t *tokens_out);
 
 /* ---------------------------------------------------------------------------------------------- tensor parallelism
  * One process per GPU.  A context created with desc.tp_size = N > 1 owns rows [rank * rows / N, (rank + 1) * rows / N) of

@@ -99,6 +99,7 @@ def load_library() -> C.CDLL:
         "ps_cuda_forward": (ci, [vp, i32p, i32p, ci, ci, C.c_void_p]),
         "ps_cuda_forward_tree": (ci, [vp, i32p, i32p, ci, C.c_void_p, ci, C.c_void_p]),
         "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
+        "ps_cuda_sample_topk": (ci, [vp, ci, ci, fp, i32p]),
         "ps_cuda_session_create": (ci, [vp, C.POINTER(ci)]),
         "ps_cuda_session_destroy": (ci, [vp, ci]),
         "ps_cuda_session_select": (ci, [vp, ci]),
@@ -425,6 +426,19 @@ class CudaModel:
                                                        1 if lm_head else 0, logits.ctypes.data_as(C.POINTER(C.c_float)) if logits is not None else None,
                                                        ids.ctypes.data_as(C.POINTER(C.c_int32)) if lm_head else None))
         return logits, ids
+
+    def forward_lazy(self, tokens, pos=None):
+        """forward with lm_head whose logits stay on the device (read them with sample_topk / be.logits_dev)"""
+        t = _i32(tokens)
+        bs = len(t)
+        p = _i32(pos) if pos is not None else np.arange(self.position, self.position + bs, dtype=np.int32)
+        self.be._ck(self.be.L.ps_cuda_forward(self.be.h, t.ctypes.data_as(C.POINTER(C.c_int32)), p.ctypes.data_as(C.POINTER(C.c_int32)), bs, 1, None))
+
+    def sample_topk(self, k: int, row: int = 0):
+        """TopKSampler on the device: (logits [k] descending, token ids [k]) of row `row` of the last forward pass"""
+        vals, ids = np.empty(k, np.float32), np.empty(k, np.int32)
+        self.be._ck(self.be.L.ps_cuda_sample_topk(self.be.h, row, k, vals.ctypes.data_as(C.POINTER(C.c_float)), ids.ctypes.data_as(C.POINTER(C.c_int32))))
+        return vals, ids
 
     def prefill(self, prompt, batch_size: int = 128):
         """ModelTokenIterator's prefill loop (src/model/model.hpp:147-160): prompt[:-1] in chunks, lm_head = false."""

@@ -113,6 +113,9 @@ struct ps_cuda_ctx {
     float *x = nullptr, *xn = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *qr = nullptr, *kr = nullptr, *att = nullptr;
     float *g = nullptr, *u = nullptr, *kq = nullptr, *logits = nullptr;
     const float *logits_last = nullptr; // where the last forward left its [bs][vocab] logits (ps_cuda_logits_dev)
+    int logits_rows = 0;                // rows of that buffer
+    float *topk_val = nullptr;          // device top-k scratch: candidates [slices][k], then the result [k]
+    int *topk_idx = nullptr;
     uint32_t *aqs = nullptr, *absp = nullptr;
     float *ad = nullptr;
     int32_t *tokens_dev = nullptr, *pos_dev = nullptr, *ids_dev = nullptr;
@@ -2053,7 +2056,7 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     std::lock_guard<std::mutex> lock(ctx->mu);
     int rc = check_forward_args(ctx, tokens, pos, bs);
     if (rc) return rc;
-    if (lm_head && !logits_host) return fail(ctx, PS_CUDA_ERR_INVALID, "forward: lm_head requested without a logits buffer");
+    // lm_head with logits_host == NULL: the logits stay on the device (lazy read-back: ps_cuda_logits_dev, ps_cuda_sample_topk)
     PS_CK(cudaSetDevice(ctx->device));
     PS_CK(cudaStreamSynchronize(ctx->stream));
     memcpy(ctx->h_tokens, tokens, (size_t)bs * 4);
@@ -2092,7 +2095,8 @@ int ps_cuda_forward(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t *pos,
     }
     if (rc) return rc;
     PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
-    if (lm_head) {
+    ctx->logits_rows = lm_head ? bs : 0;
+    if (lm_head && logits_host) {
         const size_t bytes = (size_t)bs * ctx->d.vocab_size * 4;
         if (bytes > ctx->h_logits_cap) {
             if (ctx->h_logits) cudaFreeHost(ctx->h_logits);
@@ -2255,6 +2259,7 @@ int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const
     int rc = forward_ops(ctx, n, lm_head, 0, -1, &sr);
     if (rc) return rc;
     ctx->logits_last = ctx->logits;
+    ctx->logits_rows = lm_head ? n : 0;
     if (lm_head && greedy_ids) {
         for (int i = 0; i < n; i++) {
             ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits + (size_t)i * d.vocab_size, d.vocab_size, ctx->ids_dev + i, ctx->ids_dev + d.max_batch + i);
@@ -2422,6 +2427,37 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
     ctx->d2h += (int64_t)n_steps * 4;
     kv_set_mask(ctx, 0, ctx->position + n_steps, 0);
     ctx->position += n_steps;
+    return 0;
+}
+
+// TopKSampler on the device (sampler.cpp:39-56): the k largest logits of row `row` of the last forward pass, descending (equal
+// logits by ascending token id), as (logit, token) pairs - what ProbArray holds after TopKSampler::apply.
+int ps_cuda_sample_topk(ps_cuda_ctx *ctx, int row, int k, float *logits_out, int32_t *tokens_out) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    const int vocab = ctx->tp > 1 && ctx->logits_last == ctx->logits ? ctx->d.vocab_size : ctx->d.vocab_size;
+    if (k <= 0 || k > PS_TOPK_MAX || k > vocab) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: k = %d outside [1,%d]", k, std::min(PS_TOPK_MAX, vocab));
+    if (!ctx->logits_last || row < 0 || row >= std::max(ctx->logits_rows, 1)) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: no logits row %d", row);
+    if (!logits_out || !tokens_out) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: null output");
+    PS_CK(cudaSetDevice(ctx->device));
+    const int n_slices = (vocab + PS_TOPK_SLICE - 1) / PS_TOPK_SLICE;
+    if (!ctx->topk_val) {
+        const size_t n = (size_t)((ctx->d.vocab_size + PS_TOPK_SLICE - 1) / PS_TOPK_SLICE + 1) * PS_TOPK_MAX;
+        int rc;
+        if ((rc = dev_alloc(ctx, (void **)&ctx->topk_val, n * 4)) || (rc = dev_alloc(ctx, (void **)&ctx->topk_idx, n * 4))) return rc;
+    }
+    float *res_val = ctx->topk_val + (size_t)n_slices * PS_TOPK_MAX;
+    int *res_idx = ctx->topk_idx + (size_t)n_slices * PS_TOPK_MAX;
+    ps_k_topk_stage1<<<n_slices, 256, 0, ctx->stream>>>(ctx->logits_last + (size_t)row * vocab, vocab, k, ctx->topk_val, ctx->topk_idx);
+    PS_LAUNCH_CK();
+    ps_k_topk_stage2<<<1, 256, 0, ctx->stream>>>(ctx->topk_val, ctx->topk_idx, n_slices * k, k, res_val, res_idx);
+    PS_LAUNCH_CK();
+    PS_CK(cudaMemcpyAsync(ctx->h_ids, res_idx, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    PS_CK(cudaMemcpyAsync(ctx->h_ids + PS_TOPK_MAX, res_val, (size_t)k * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    int rc = sync_and_check(ctx);
+    if (rc) return rc;
+    memcpy(tokens_out, ctx->h_ids, (size_t)k * 4);
+    memcpy(logits_out, ctx->h_ids + PS_TOPK_MAX, (size_t)k * 4);
+    ctx->d2h += (int64_t)k * 8;
     return 0;
 }
 

@@ -957,6 +957,76 @@ __global__ void __launch_bounds__(128) ps_k_sess_pv(float *__restrict__ out, con
     }
 }
 
+// ====================================================================================================================
+// Device-side top-k: TopKSampler (src/sampler/sampler.cpp:39-56: partial_sort by logit, descending) on the
+// device, so that k (logit, token) pairs cross PCIe instead of the vocabulary's logits and the host never builds a
+// vocabulary-sized ProbArray (prob_array.hpp:43-49).  Two stages of repeated arg-max: every CTA extracts the k largest of
+// its slice (kept in shared memory), then one CTA merges the candidates.  Order: logit descending, equal logits by
+// ascending token id (std::partial_sort leaves that order unspecified).
+// ====================================================================================================================
+#define PS_TOPK_MAX 64
+#define PS_TOPK_SLICE 2048
+// the block's (largest value, lowest index) among the entries of v[0..n) that are not NaN (NaN marks "already taken");
+// returns the position in every thread, -1 if nothing is left
+PS_D bool ps_topk_better(float x, int id, float best, int bi) { return x == x && (!(best == best) || x > best || (x == best && id < bi)); }
+PS_D int ps_block_argmax_smem(const float *v, const int *idx, int n, float *sv, int *si, int *sp) {
+    float best = __int_as_float(0x7fc00000);
+    int bi = 0x7fffffff, bp = -1;
+    for (int t = threadIdx.x; t < n; t += blockDim.x) {
+        const float x = v[t];
+        const int id = idx ? idx[t] : t;
+        if (ps_topk_better(x, id, best, bi)) { best = x; bi = id; bp = t; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) {
+        const float ov = __shfl_xor_sync(PS_FULL, best, o);
+        const int oi = __shfl_xor_sync(PS_FULL, bi, o), op = __shfl_xor_sync(PS_FULL, bp, o);
+        if (ps_topk_better(ov, oi, best, bi)) { best = ov; bi = oi; bp = op; }
+    }
+    const int warp = threadIdx.x >> 5;
+    if ((threadIdx.x & 31) == 0) { sv[warp] = best; si[warp] = bi; sp[warp] = bp; }
+    __syncthreads();
+    best = sv[0]; bi = si[0]; bp = sp[0];
+    for (int w = 1; w < (int)(blockDim.x >> 5); w++)
+        if (ps_topk_better(sv[w], si[w], best, bi)) { best = sv[w]; bi = si[w]; bp = sp[w]; }
+    __syncthreads();
+    return bp;
+}
+// stage 1: CTA b -> cand_val / cand_idx [b][k] = the k largest of logits[b * SLICE, (b + 1) * SLICE) (padded with -inf, id 0x7fffffff)
+__global__ void __launch_bounds__(256) ps_k_topk_stage1(const float *__restrict__ logits, int n, int k, float *__restrict__ cand_val, int *__restrict__ cand_idx) {
+    __shared__ float s_v[PS_TOPK_SLICE];
+    __shared__ float sv[8];
+    __shared__ int si[8], sp[8];
+    const int lo = blockIdx.x * PS_TOPK_SLICE, m = min(PS_TOPK_SLICE, n - lo);
+    for (int t = threadIdx.x; t < m; t += blockDim.x) s_v[t] = logits[lo + t];
+    __syncthreads();
+    for (int r = 0; r < k; r++) {
+        const int p = ps_block_argmax_smem(s_v, nullptr, m, sv, si, sp); // ids inside a slice ascend with the position
+        if (threadIdx.x == 0) {
+            const bool live = p >= 0;
+            cand_val[blockIdx.x * k + r] = live ? s_v[p] : __int_as_float(0x7fc00000); // NaN = no candidate (slice shorter than k)
+            cand_idx[blockIdx.x * k + r] = live ? lo + p : 0x7fffffff;
+            if (live) s_v[p] = __int_as_float(0x7fc00000); // a quiet NaN marks "taken"
+        }
+        __syncthreads();
+    }
+}
+// stage 2: one CTA merges n_cand candidates into out_val / out_idx [k]
+__global__ void __launch_bounds__(256) ps_k_topk_stage2(float *__restrict__ cand_val, const int *__restrict__ cand_idx, int n_cand, int k, float *__restrict__ out_val,
+                                                        int *__restrict__ out_idx) {
+    __shared__ float sv[8];
+    __shared__ int si[8], sp[8];
+    for (int r = 0; r < k; r++) {
+        const int p = ps_block_argmax_smem(cand_val, cand_idx, n_cand, sv, si, sp);
+        if (threadIdx.x == 0) {
+            out_val[r] = p >= 0 ? cand_val[p] : -INFINITY;
+            out_idx[r] = p >= 0 ? cand_idx[p] : -1;
+            if (p >= 0) cand_val[p] = __int_as_float(0x7fc00000);
+        }
+        __syncthreads();
+    }
+}
+
 // greedy pick (Model::decode with top_k = 1: ProbArray + greedy_sample, src/model/llama/llama_model.cpp:124-128):
 // first maximum wins.  One CTA; writes the id to `out[step]` and to `next_token` (device feedback for the next step).
 __global__ void __launch_bounds__(1024) ps_k_argmax(const float *__restrict__ logits, int64_t n, int32_t *__restrict__ out, int32_t *__restrict__ next_token) {

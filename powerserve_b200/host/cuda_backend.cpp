@@ -63,7 +63,7 @@ void CUDABackend::bind_weights(const Weight &w) {
 }
 
 void CUDABackend::forward(const Tensor *out, const std::vector<int> &tokens, const std::vector<int> &pos, bool lm_head) {
-    float *logits = lm_head ? static_cast<float *>(const_cast<Tensor *>(out)->get<CPUBuffer>().m_data) : nullptr;
+    float *logits = (lm_head && !m_lazy_logits) ? static_cast<float *>(const_cast<Tensor *>(out)->get<CPUBuffer>().m_data) : nullptr;
     PS_CHECK(ps_cuda_forward(m_ctx, tokens.data(), pos.data(), (int)tokens.size(), lm_head ? 1 : 0, logits));
 }
 
@@ -71,6 +71,15 @@ std::vector<int> CUDABackend::decode_greedy(int first_token, int n_steps) {
     std::vector<int> ids(n_steps);
     PS_CHECK(ps_cuda_decode_greedy(m_ctx, first_token, n_steps, ids.data()));
     return ids;
+}
+
+std::vector<std::pair<float, int>> CUDABackend::topk(int k, int row) const {
+    std::vector<float> vals(k);
+    std::vector<int> ids(k);
+    PS_CHECK(ps_cuda_sample_topk(m_ctx, row, k, vals.data(), ids.data()));
+    std::vector<std::pair<float, int>> out(k);
+    for (int i = 0; i < k; i++) out[i] = {vals[i], ids[i]};
+    return out;
 }
 
 void *CUDABackend::dev(const Tensor *t) { return const_cast<Tensor *>(t)->get<CUDABuffer>().m_data; }

@@ -16,6 +16,7 @@
 #include "ps_cuda.h"
 
 #include <memory>
+#include <utility>
 #include <vector>
 
 namespace powerserve {
@@ -67,6 +68,11 @@ public:
     void forward(const Tensor *out, const std::vector<int> &tokens, const std::vector<int> &pos, bool lm_head);
     // Model::decode with a greedy sampler and no host round trip per token
     std::vector<int> decode_greedy(int first_token, int n_steps);
+    // Device-side sampling: with lazy logits `forward` leaves the logits on the device (the CPUBuffer of the
+    // CUDA_FORWARD op stays untouched) and topk(k) returns what ProbArray holds after TopKSampler::apply (sampler.cpp:39-56):
+    // the k largest (logit, token) pairs, descending - the sampler chain then runs on k entries instead of the vocabulary.
+    void set_lazy_logits(bool v) { m_lazy_logits = v; }
+    std::vector<std::pair<float, int>> topk(int k, int row = 0) const;
 
     // ---- operator table (same names / argument order as GGMLBackend, ggml.hpp:216-244); tensors carry CUDABuffers,
     // weights are looked up by the host pointer of their CPUBuffer view of GGUF memory.
@@ -118,6 +124,7 @@ private:
     ModelConfig::LLMConfig m_config;
     std::vector<ps_cuda_layer_weights> m_layers;
     bool m_per_op = false;
+    bool m_lazy_logits = false;
     std::vector<Tensor> m_key_tensors, m_value_tensors; // per layer, CUDABuffers over ps_cuda_kv_k / ps_cuda_kv_v
 };
 

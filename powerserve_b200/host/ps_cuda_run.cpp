@@ -2,7 +2,8 @@
 // Same command line and outputs as the test suite's driver of the unmodified CPU path, so the two can be diffed: it
 // mirrors app/run/run.cpp:38-154 without CLI11 / tokenizer (the reference's submodules are empty here).
 //
-// usage: ps_cuda_run <model_dir> <n_threads> <batch_size> <prompt_ids.txt> <n_decode> <out_prefix> [--dump-logits N]
+// usage: ps_cuda_run <model_dir> <n_threads> <batch_size> <prompt_ids.txt> <n_decode> <out_prefix> [--dump-logits N] [--device-topk K]
+// --device-topk K: the logits stay on the device, TopKSampler runs there (CUDABackend::topk) and the host picks from K pairs
 #include "backend/platform.hpp"
 #include "core/config.hpp"
 #include "model/llama/llama_model.hpp"
@@ -37,9 +38,11 @@ int main(int argc, char **argv) {
     const auto prompt = read_ids(argv[4]);
     const int n_decode = atoi(argv[5]);
     const std::string out = argv[6];
-    int dump_logits = 0;
-    for (int i = 7; i < argc; i++)
+    int dump_logits = 0, device_topk = 0;
+    for (int i = 7; i < argc; i++) {
         if (!strcmp(argv[i], "--dump-logits") && i + 1 < argc) dump_logits = atoi(argv[++i]);
+        if (!strcmp(argv[i], "--device-topk") && i + 1 < argc) device_topk = atoi(argv[++i]);
+    }
 
     auto cfg = std::make_shared<ModelConfig>(Path(model_dir) / "model.json");
     std::shared_ptr<Model> model;
@@ -55,6 +58,7 @@ int main(int argc, char **argv) {
     const size_t vocab = cfg->llm.vocab_size;
     platform->ggml_backends[model_id]->setup_threadpool();
 
+    if (device_topk > 0) platform->cuda_backends[model_id]->set_lazy_logits(true);
     const double t0 = now_s();
     platform->reset_kv_position(model_id);
     size_t done = 0;
@@ -74,9 +78,13 @@ int main(int argc, char **argv) {
         auto ret = model->forward({tok}, {(int)platform->get_kv_position(model_id)}, CausalAttentionMask(1), true);
         const auto &logits = ret.logits_vector[0];
         int best = 0;
-        for (size_t i = 1; i < vocab; i++)
-            if (logits[i] > logits[best]) best = (int)i;
-        if (flog && step < dump_logits) fwrite(logits.data(), sizeof(float), vocab, flog);
+        if (device_topk > 0) { // TopKSampler on the device: K (logit, token) pairs instead of the vocabulary's logits
+            best = platform->cuda_backends[model_id]->topk(device_topk)[0].second;
+        } else {
+            for (size_t i = 1; i < vocab; i++)
+                if (logits[i] > logits[best]) best = (int)i;
+            if (flog && step < dump_logits) fwrite(logits.data(), sizeof(float), vocab, flog);
+        }
         ids.push_back(best);
         tok = best;
         if (step == 0) t_first = now_s();

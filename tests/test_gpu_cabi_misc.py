@@ -154,3 +154,29 @@ def test_kv_bookkeeping_and_cache_contents():
     with pytest.raises(capi.PsCudaError):
         cm.be.kv_rollback(cm.position + 1)
     cm.close(); om.close()
+
+
+@pytest.mark.parametrize("preset,k", [("tiny-llama", 1), ("tiny-llama", 40), ("tiny-bigvocab", 64), ("tiny-qwen2", 7)])
+def test_device_topk_equals_host_partial_sort(preset, k):
+    """ps_cuda_sample_topk = ProbArray + TopKSampler::apply (prob_array.hpp:43-49, sampler.cpp:39-56) on the device: the k largest
+    logits of the last forward pass, descending, ties by ascending id - compared with a host sort of the same logits (which
+    are themselves bit-exact vs the oracle in the model tests), with lazy logits (nothing but 2k words crosses PCIe)."""
+    d = M.model_dir(preset)
+    shape = synth.PRESETS[preset]
+    cm = capi.CudaModel(d, max_batch=8)
+    prompt = synth.random_prompt(shape.vocab_size, 11, seed=21)
+    cm.prefill(prompt, 8)
+    tok = int(prompt[-1])
+    for step in range(4):
+        d2h0 = cm.be.counter("d2h_bytes")
+        cm.forward_lazy([tok])
+        vals, ids = cm.sample_topk(k)
+        assert cm.be.counter("d2h_bytes") - d2h0 == 8 * k            # the logits stayed on the device
+        lg = cm.be.read_device(cm.be.logits_dev(), shape.vocab_size)
+        order = np.lexsort((np.arange(shape.vocab_size), -lg.astype(np.float64)))[:k]   # logit descending, then id ascending
+        assert list(ids) == [int(i) for i in order]
+        L.assert_bit_equal(vals, lg[order], "top-k logits")
+        tok = int(ids[0])
+    # duplicate logits: ties resolve by ascending id (checked on a crafted row through the same kernels is not possible from
+    # the C ABI; equal logits inside real rows are covered by the lexsort comparison above)
+    cm.close()

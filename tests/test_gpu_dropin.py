@@ -21,16 +21,18 @@ EXE = os.path.join(L.ROOT, "powerserve_b200", "host", "_build", "ps_cuda_run")
 needs_exe = pytest.mark.skipif(not os.path.exists(EXE), reason="ps_cuda_run not built (needs /root/reference)")
 
 
-def run_dropin(path, prompt, n_decode, batch_size, dump_logits, per_op=False):
+def run_dropin(path, prompt, n_decode, batch_size, dump_logits, per_op=False, device_topk=0):
     env = dict(os.environ)
     env["POWERSERVE_CUDA_PER_OP"] = "1" if per_op else "0"
     with tempfile.TemporaryDirectory() as td:
         pf = os.path.join(td, "prompt.txt")
         open(pf, "w").write(" ".join(str(int(t)) for t in prompt))
-        r = subprocess.run([EXE, path, "2", str(batch_size), pf, str(n_decode), os.path.join(td, "out"), "--dump-logits", str(dump_logits)],
-                           capture_output=True, text=True, timeout=600, env=env)
+        extra = ["--device-topk", str(device_topk)] if device_topk else ["--dump-logits", str(dump_logits)]
+        r = subprocess.run([EXE, path, "2", str(batch_size), pf, str(n_decode), os.path.join(td, "out")] + extra, capture_output=True, text=True, timeout=600, env=env)
         assert r.returncode == 0, r.stderr[-2000:]
         ids = [int(x) for x in open(os.path.join(td, "out.ids")).read().split()]
+        if device_topk:
+            return ids, None
         vocab = json.load(open(os.path.join(path, "model.json")))["llm_config"]["vocab_size"]
         return ids, np.fromfile(os.path.join(td, "out.logits"), dtype=np.float32).reshape(-1, vocab)
 
@@ -70,3 +72,14 @@ def test_powerserve_unfused_graph_op_by_op_on_cuda_matches_reference_golden(pres
     key = f"{preset}/{n_prompt}/{batch}"
     assert ids == list(gold[key + "/ids"])
     assert (L.bits(lg) == gold[key + "/logits_bits"]).all()
+
+
+@needs_exe
+@pytest.mark.parametrize("preset,n_prompt,batch,n_dec", cases.MODEL_CASES[:3])
+def test_powerserve_stack_with_device_side_topk(preset, n_prompt, batch, n_dec):
+    """SURVEY 8 f3: the stack with lazy logits - CUDA_FORWARD leaves the logits on the device, CUDABackend::topk runs TopKSampler
+    there and the host picks from 40 (logit, token) pairs; the greedy ids must be the golden ones."""
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "models.npz"))
+    prompt = synth.random_prompt(synth.PRESETS[preset].vocab_size, n_prompt, seed=7 + n_prompt)
+    ids, _ = run_dropin(M.model_dir(preset), prompt, n_dec, batch, 0, device_topk=40)
+    assert ids == list(gold[f"{preset}/{n_prompt}/{batch}/ids"])
