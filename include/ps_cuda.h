@@ -95,6 +95,10 @@ int ps_cuda_get_embedding(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype
 int ps_cuda_rmsnorm(ps_cuda_ctx *ctx, float *dst, const float *x, const float *w, int64_t dim, int64_t bs, float eps);
 int ps_cuda_matmul(ps_cuda_ctx *ctx, float *dst, const void *w, int wtype, int64_t K, int64_t N, const float *x, int64_t bs);
 int ps_cuda_rope(ps_cuda_ctx *ctx, float *dst, const float *src, int64_t head_size, int64_t n_heads, int64_t bs, const int32_t *pos);
+/* RoPE frequency factors (rope_freqs.weight of Llama-3.1 / 3.2 GGUFs; ggml_rope_cache_init, ggml.c:15342-15356: theta / ff).
+ * The reference never passes them (ggml_wrapper.cpp:104-106), so the default - and parity - is WITHOUT;
+ * factors == NULL restores that.  n must be rope_n_dims / 2.  Rebuilds the context's cos / sin table. */
+int ps_cuda_set_rope_freq_factors(ps_cuda_ctx *ctx, const float *factors, int n);
 int ps_cuda_add(ps_cuda_ctx *ctx, float *dst, const float *a, const float *b, int64_t n, int64_t nb); /* b row-broadcast */
 int ps_cuda_silu_hadamard(ps_cuda_ctx *ctx, float *dst, const float *gate, const float *up, int64_t n);
 int ps_cuda_get_mask(ps_cuda_ctx *ctx, float *mask, int64_t n_kv, int64_t bs, const int32_t *pos);

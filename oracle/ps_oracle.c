@@ -44,6 +44,7 @@ static void par_for(int64_t n, int64_t min_chunk, par_fn fn, void *ctx) {
 typedef struct { uint16_t d; uint8_t qs[16]; } blk_q4_0;                                  /* 18 B / 32 */
 typedef struct { uint16_t d; int8_t qs[32]; } blk_q8_0;                                   /* 34 B / 32 */
 typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qs[128]; } blk_q4_K; /* 144 B / 256 */
+typedef struct { uint16_t d; uint16_t dmin; uint8_t scales[12]; uint8_t qh[32]; uint8_t qs[128]; } blk_q5_K; /* 176 B / 256 (ggml-common.h: block_q5_K) */
 typedef struct { uint8_t ql[128]; uint8_t qh[64]; int8_t scales[16]; uint16_t d; } blk_q6_K; /* 210 B / 256 */
 typedef struct { float d; int8_t qs[256]; int16_t bsums[16]; } blk_q8_K;                  /* 292 B / 256 */
 #pragma pack(pop)
@@ -105,6 +106,7 @@ size_t ps_or_row_size(int type, int64_t k) {
     case PS_OR_Q4_0: return (size_t)(k / 32) * sizeof(blk_q4_0);
     case PS_OR_Q8_0: return (size_t)(k / 32) * sizeof(blk_q8_0);
     case PS_OR_Q4_K: return (size_t)(k / 256) * sizeof(blk_q4_K);
+    case PS_OR_Q5_K: return (size_t)(k / 256) * sizeof(blk_q5_K);
     case PS_OR_Q6_K: return (size_t)(k / 256) * sizeof(blk_q6_K);
     case PS_OR_Q8_K: return (size_t)(k / 256) * sizeof(blk_q8_K);
     default: return 0;
@@ -115,7 +117,7 @@ size_t ps_or_row_size(int type, int64_t k) {
 int ps_or_vec_dot_type(int wtype) {
     switch (wtype) {
     case PS_OR_Q4_0: case PS_OR_Q8_0: return PS_OR_Q8_0;
-    case PS_OR_Q4_K: case PS_OR_Q6_K: return PS_OR_Q8_K;
+    case PS_OR_Q4_K: case PS_OR_Q5_K: case PS_OR_Q6_K: return PS_OR_Q8_K;
     default: return PS_OR_F32;
     }
 }
@@ -249,6 +251,26 @@ void ps_or_dequantize_row(int type, const void *vx, float *y, int64_t k) {
             }
         }
     } break;
+    case PS_OR_Q5_K: { /* dequantize_row_q5_K, ggml-quants.c:2771-2798: y = d1 * ((q & 0xF) + (high bit ? 16 : 0)) - m1, the
+                          same contracted FMA as Q4_K (checked against oracle/_ref) */
+        const blk_q5_K *x = (const blk_q5_K *)vx;
+        for (int64_t i = 0; i < k / QK_K; i++) {
+            const uint8_t *ql = x[i].qs, *qh = x[i].qh;
+            const float d = ps_or_fp16_to_fp32(x[i].d), min = ps_or_fp16_to_fp32(x[i].dmin);
+            int is = 0;
+            uint8_t sc, m, u1 = 1, u2 = 2;
+            for (int j = 0; j < QK_K; j += 64) {
+                get_scale_min_k4(is + 0, x[i].scales, &sc, &m);
+                const float d1 = d * sc, m1 = min * m;
+                get_scale_min_k4(is + 1, x[i].scales, &sc, &m);
+                const float d2 = d * sc, m2 = min * m;
+                for (int l = 0; l < 32; ++l) *y++ = fmaf(d1, (float)((ql[l] & 0xF) + (qh[l] & u1 ? 16 : 0)), -m1);
+                for (int l = 0; l < 32; ++l) *y++ = fmaf(d2, (float)((ql[l] >> 4) + (qh[l] & u2 ? 16 : 0)), -m2);
+                ql += 32; is += 2;
+                u1 <<= 2; u2 <<= 2;
+            }
+        }
+    } break;
     case PS_OR_Q6_K: { /* dequantize_row_q6_K, ggml-quants.c:2991-3019 */
         const blk_q6_K *x = (const blk_q6_K *)vx;
         for (int64_t i = 0; i < k / QK_K; i++) {
@@ -314,6 +336,43 @@ static float vec_dot_q4_K_q8_K(int64_t n, const blk_q4_K *x, const blk_q8_K *y) 
     /* acc_m = add(acc_m, movehl) ; add_ss(acc_m, movehdup) */
     const float m02 = acc_m[0] + acc_m[2], m13 = acc_m[1] + acc_m[3];
     return hsum8(acc) + (m02 + m13);
+}
+
+/* ggml_vec_dot_q5_K_q8_K, AVX2 branch, ggml-quants.c:8382-8460: the lane sums of Q4_K with the fifth bit from qh (sub-block s
+ * takes bit s of qh[e]), ONE fused multiply-add per block into the 8-lane accumulator - and the mins through a SCALAR float:
+ * summs += dmin * (sum_j m_j * (bsums_2j + bsums_2j+1)), a separate multiply and add in the reference build. */
+static float vec_dot_q5_K_q8_K(int64_t n, const blk_q5_K *x, const blk_q8_K *y) {
+    const int64_t nb = n / QK_K;
+    float acc[8] = {0}, summs = 0.f;
+    for (int64_t i = 0; i < nb; ++i) {
+        const float d = y[i].d * ps_or_fp16_to_fp32(x[i].d);
+        const float dmin = -y[i].d * ps_or_fp16_to_fp32(x[i].dmin);
+        uint8_t sc[8], mn[8];
+        for (int j = 0; j < 8; j++) get_scale_min_k4(j, x[i].scales, &sc[j], &mn[j]);
+        int32_t hsum = 0; /* hadd_epi32(hadd_epi32(madd_epi16(mins, hadd_epi16(bsums)))) element 0 = the sum of all four products */
+        for (int kk = 0; kk < 4; kk++) {
+            const int16_t s0 = (int16_t)(y[i].bsums[4 * kk + 0] + y[i].bsums[4 * kk + 1]);
+            const int16_t s1 = (int16_t)(y[i].bsums[4 * kk + 2] + y[i].bsums[4 * kk + 3]);
+            hsum += (int32_t)mn[2 * kk] * s0 + (int32_t)mn[2 * kk + 1] * s1;
+        }
+        summs += dmin * (float)hsum; /* NOT contracted in the reference build: vmulss + vaddss (checked against oracle/_ref) */
+        int32_t sumi[8] = {0};
+        for (int j = 0; j < QK_K / 64; ++j) {
+            const uint8_t *q5 = x[i].qs + 32 * j;
+            const int8_t *q8l = y[i].qs + 64 * j, *q8h = q8l + 32;
+            for (int l = 0; l < 8; l++) {
+                uint8_t lo[4], hi[4];
+                for (int b = 0; b < 4; b++) {
+                    const uint8_t hb = x[i].qh[4 * l + b];
+                    lo[b] = (uint8_t)((q5[4 * l + b] & 0xF) + (((hb >> (2 * j)) & 1) << 4));
+                    hi[b] = (uint8_t)((q5[4 * l + b] >> 4) + (((hb >> (2 * j + 1)) & 1) << 4));
+                }
+                sumi[l] += (int32_t)sc[2 * j] * dot4_u8_s8(lo, q8l + 4 * l) + (int32_t)sc[2 * j + 1] * dot4_u8_s8(hi, q8h + 4 * l);
+            }
+        }
+        for (int l = 0; l < 8; l++) acc[l] = fmaf(d, (float)sumi[l], acc[l]);
+    }
+    return hsum8(acc) + summs;
 }
 
 /* ggml_vec_dot_q6_K_q8_K, AVX2 branch, ggml-quants.c:9039-9116 */
@@ -383,6 +442,7 @@ static float vec_dot_q8_0_q8_0(int64_t n, const blk_q8_0 *x, const blk_q8_0 *y) 
 float ps_or_vec_dot(int wtype, int64_t k, const void *w, const void *xq) {
     switch (wtype) {
     case PS_OR_Q4_K: return vec_dot_q4_K_q8_K(k, (const blk_q4_K *)w, (const blk_q8_K *)xq);
+    case PS_OR_Q5_K: return vec_dot_q5_K_q8_K(k, (const blk_q5_K *)w, (const blk_q8_K *)xq);
     case PS_OR_Q6_K: return vec_dot_q6_K_q8_K(k, (const blk_q6_K *)w, (const blk_q8_K *)xq);
     case PS_OR_Q4_0: return vec_dot_q4_0_q8_0(k, (const blk_q4_0 *)w, (const blk_q8_0 *)xq);
     case PS_OR_Q8_0: return vec_dot_q8_0_q8_0(k, (const blk_q8_0 *)w, (const blk_q8_0 *)xq);

@@ -20,7 +20,7 @@ extern "C" {
 #endif
 
 /* ggml type ids (libs/ggml/include/ggml.h:386-401) */
-enum { PS_OR_F32 = 0, PS_OR_F16 = 1, PS_OR_Q4_0 = 2, PS_OR_Q8_0 = 8, PS_OR_Q4_K = 12, PS_OR_Q6_K = 14, PS_OR_Q8_K = 15 };
+enum { PS_OR_F32 = 0, PS_OR_F16 = 1, PS_OR_Q4_0 = 2, PS_OR_Q8_0 = 8, PS_OR_Q4_K = 12, PS_OR_Q5_K = 13, PS_OR_Q6_K = 14, PS_OR_Q8_K = 15 };
 
 float    ps_or_fp16_to_fp32(uint16_t h);
 uint16_t ps_or_fp32_to_fp16(float f);

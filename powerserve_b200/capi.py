@@ -100,6 +100,7 @@ def load_library() -> C.CDLL:
         "ps_cuda_forward_tree": (ci, [vp, i32p, i32p, ci, C.c_void_p, ci, C.c_void_p]),
         "ps_cuda_decode_greedy": (ci, [vp, C.c_int32, ci, i32p]),
         "ps_cuda_sample_topk": (ci, [vp, ci, ci, fp, i32p]),
+        "ps_cuda_set_rope_freq_factors": (ci, [vp, fp, ci]),
         "ps_cuda_session_create": (ci, [vp, C.POINTER(ci)]),
         "ps_cuda_session_destroy": (ci, [vp, ci]),
         "ps_cuda_session_select": (ci, [vp, ci]),
@@ -244,6 +245,14 @@ class CudaBackend:
     def copy_2d(self, dst, ds0, ds1, src, ss0, ss1, ne0, ne1):
         """GGMLBackend::copy / cont on 2-D fp32 views (byte strides; powerserve_compute_forward_dup)."""
         self._ck(self.L.ps_cuda_copy_2d(self.h, dst.ptr, ds0, ds1, src.ptr, ss0, ss1, ne0, ne1))
+
+    def set_rope_freq_factors(self, factors):
+        """rope_freqs.weight (off by default: the reference ignores it); None restores the default"""
+        if factors is None:
+            self._ck(self.L.ps_cuda_set_rope_freq_factors(self.h, None, 0))
+        else:
+            f = np.ascontiguousarray(factors, dtype=np.float32)
+            self._ck(self.L.ps_cuda_set_rope_freq_factors(self.h, f.ctypes.data_as(C.POINTER(C.c_float)), len(f)))
 
     def copy_4d(self, dst, dst_ne, dst_nb, src, src_ne, src_nb, dst_off=0, src_off=0):
         """GGMLBackend::copy / cont on views of up to four dims whose shapes may differ (shapes in elements, strides in bytes)."""

@@ -247,13 +247,16 @@ int sync_and_check(ps_cuda_ctx *ctx) {
     return 0;
 }
 
-bool type_ok(int t) { return t == 0 || t == 2 || t == 8 || t == 12 || t == 14; }
-int blk_elems(int t) { return (t == 12 || t == 14) ? 256 : (t == 0 ? 1 : 32); }
+bool type_ok(int t) { return t == 0 || t == 1 || t == 2 || t == 8 || t == 12 || t == 13 || t == 14; } // F16 (1): embedding tables only
+int blk_elems(int t) { return (t == 12 || t == 13 || t == 14) ? 256 : (t <= 1 ? 1 : 32); }
 
 // ggml_rope_cache_init (libs/ggml/src/ggml.c:15342-15356) + rope_yarn (:15319-15336) at ext_factor == 0,
 // freq_factors == NULL (src/backend/ggml/ggml_wrapper.cpp:104-106), evaluated with the platform libm for
 // every position once.
-void build_rope_table(const ps_cuda_model_desc &d, std::vector<float> &t) {
+// `ff` (optional, n_dims / 2 entries): the freq_factors of ggml_rope_cache_init - theta / ff[i0 / 2] enters rope_yarn (the
+// "llama3" rope scaling of Llama-3.1 / 3.2 GGUFs, rope_freqs.weight).  The reference never passes them, so they
+// are off unless ps_cuda_set_rope_freq_factors is called.
+void build_rope_table(const ps_cuda_model_desc &d, std::vector<float> &t, const float *ff = nullptr) {
     const int hs = d.head_size;
     t.resize((size_t)d.n_ctx * hs);
     const float theta_scale = powf(d.rope_freq_base, -2.0f / d.rope_n_dims);
@@ -261,7 +264,8 @@ void build_rope_table(const ps_cuda_model_desc &d, std::vector<float> &t) {
         volatile float theta = (float)(int64_t)p;
         float *cache = t.data() + (size_t)p * hs;
         for (int i0 = 0; i0 < hs; i0 += 2) {
-            volatile float th = d.rope_freq_scale * theta;
+            volatile float tx = ff ? theta / ff[i0 / 2] : (float)theta;
+            volatile float th = d.rope_freq_scale * tx;
             volatile float c = cosf(th) * d.rope_attn_factor;
             volatile float s = sinf(th) * d.rope_attn_factor;
             s = s * 1.0f;
@@ -302,7 +306,7 @@ int launch_mm_t(ps_cuda_ctx *ctx, float *dst, const uint8_t *w, int64_t K, int64
 // quantise bs activation columns of K elements into the context's scratch (type of the WEIGHT decides the format)
 int quantize_act(ps_cuda_ctx *ctx, int wtype, const float *x, int64_t K, int64_t bs) {
     if (K > ctx->maxK || bs > ctx->d.max_batch) return fail(ctx, PS_CUDA_ERR_INVALID, "activation %lldx%lld exceeds workspace", (long long)K, (long long)bs);
-    if (wtype == 12 || wtype == 14) {
+    if (wtype == 12 || wtype == 13 || wtype == 14) {
         if (K % 256) return fail(ctx, PS_CUDA_ERR_INVALID, "K=%lld is not a multiple of 256", (long long)K);
         dim3 grid((unsigned)((K / 256 + 3) / 4), (unsigned)bs);
         ps_k_quantize_q8k<<<grid, 128, 0, ctx->stream>>>(x, K, ctx->aqs, ctx->ad, ctx->absp);
@@ -320,6 +324,7 @@ int quantize_act(ps_cuda_ctx *ctx, int wtype, const float *x, int64_t K, int64_t
 int matmul_q(ps_cuda_ctx *ctx, float *dst, const uint8_t *w, int wtype, int64_t K, int64_t N, int64_t bs, const float *bias, const float *residual) {
     switch (wtype) {
     case 12: return launch_mm_t<12>(ctx, dst, w, K, N, bs, bias, residual);
+    case 13: return launch_mm_t<13>(ctx, dst, w, K, N, bs, bias, residual);
     case 14: return launch_mm_t<14>(ctx, dst, w, K, N, bs, bias, residual);
     case 2: return launch_mm_t<2>(ctx, dst, w, K, N, bs, bias, residual);
     case 8: return launch_mm_t<8>(ctx, dst, w, K, N, bs, bias, residual);
@@ -1389,6 +1394,19 @@ int ps_cuda_rope(ps_cuda_ctx *ctx, float *dst, const float *src, int64_t head_si
     return 0;
 }
 
+int ps_cuda_set_rope_freq_factors(ps_cuda_ctx *ctx, const float *factors, int n) {
+    std::lock_guard<std::mutex> lock(ctx->mu);
+    if (factors && n != ctx->d.rope_n_dims / 2) return fail(ctx, PS_CUDA_ERR_INVALID, "rope_freq_factors: %d entries, expected rope_n_dims / 2 = %d", n, ctx->d.rope_n_dims / 2);
+    for (int i = 0; factors && i < n; i++)
+        if (!(factors[i] > 0.f)) return fail(ctx, PS_CUDA_ERR_INVALID, "rope_freq_factors: entry %d is not positive", i);
+    PS_CK(cudaSetDevice(ctx->device));
+    std::vector<float> t;
+    build_rope_table(ctx->d, t, factors);
+    PS_CK(cudaStreamSynchronize(ctx->stream));
+    PS_CK(cudaMemcpy(ctx->rope_table, t.data(), t.size() * 4, cudaMemcpyHostToDevice));
+    return 0;
+}
+
 int ps_cuda_add(ps_cuda_ctx *ctx, float *dst, const float *a, const float *b, int64_t n, int64_t nb) {
     if (nb <= 0 || n % nb) return fail(ctx, PS_CUDA_ERR_INVALID, "add: broadcast size %lld does not divide %lld", (long long)nb, (long long)n);
     ps_k_add<<<grid1d(n), 256, 0, ctx->stream>>>(dst, a, b, n, nb);
@@ -1638,7 +1656,7 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
             REG(rows_of(lw.attn_v_bias, 1, kvd_l), kvd_l, 1, ld.v_bias, nullptr);
         }
         // q/k/v (and gate/up) share one quantised activation: their vec_dot_type must agree
-        auto kq = [](int t) { return t == 12 || t == 14; };
+        auto kq = [](int t) { return t == 12 || t == 13 || t == 14; };
         if (kq(ld.tq) != kq(ld.tk) || kq(ld.tq) != kq(ld.tv) || kq(ld.tgate) != kq(ld.tup))
             return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "layer %d mixes K-quant and 32-block weights on one input", L);
     }

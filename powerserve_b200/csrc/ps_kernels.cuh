@@ -13,14 +13,17 @@
 #define PS_Q4_0_BYTES 18
 #define PS_Q8_0_BYTES 34
 #define PS_Q4_K_BYTES 144
+#define PS_Q5_K_BYTES 176
 #define PS_Q6_K_BYTES 210
 
 __host__ __device__ inline int64_t ps_row_bytes(int type, int64_t k) {
     switch (type) {
     case 0: return k * 4;
+    case 1: return k * 2;
     case 2: return k / 32 * PS_Q4_0_BYTES;
     case 8: return k / 32 * PS_Q8_0_BYTES;
     case 12: return k / 256 * PS_Q4_K_BYTES;
+    case 13: return k / 256 * PS_Q5_K_BYTES;
     case 14: return k / 256 * PS_Q6_K_BYTES;
     default: return 0;
     }
@@ -175,7 +178,7 @@ template <int TYPE> struct PsBlk;
 // ggml_vec_dot_q4_K_q8_K, AVX2 branch (libs/ggml/src/ggml-quants.c:7809-7872)
 template <> struct PsBlk<12> {
     static constexpr int BYTES = PS_Q4_K_BYTES, ELEMS = 256;
-    static constexpr bool HAS_MIN = true;
+    static constexpr bool HAS_MIN = true, MIN_SCALAR = false;
     uint32_t q4[4], scA, scB, mA, mB;
     float xd, xmin;
     PS_D void load(const uint8_t *blk, int l) {
@@ -216,10 +219,56 @@ template <> struct PsBlk<12> {
     }
 };
 
+// ggml_vec_dot_q5_K_q8_K, AVX2 branch (libs/ggml/src/ggml-quants.c:8382-8460): block_q5_K = d, dmin, scales[12], qh[32], qs[128]
+// (ggml-common.h); the lane sums of Q4_K with the fifth bit of sub-block s taken from bit s of qh[e]; the mins go through a
+// SCALAR float, summs += dmin * sum_k prod_k - a separate multiply and add in the reference build (vmulss + vaddss; pinned against the compiled reference on the CPU).
+template <> struct PsBlk<13> {
+    static constexpr int BYTES = PS_Q5_K_BYTES, ELEMS = 256;
+    static constexpr bool HAS_MIN = true, MIN_SCALAR = true;
+    uint32_t q4[4], qh, scA, scB, mA, mB;
+    float xd, xmin;
+    PS_D void load(const uint8_t *blk, int l) {
+        const uint4 h = *reinterpret_cast<const uint4 *>(blk);
+        xd = ps_half_bits_to_float(h.x & 0xffffu);
+        xmin = ps_half_bits_to_float(h.x >> 16);
+        const uint32_t k1 = 0x3f3f3f3fu, k2 = 0x0f0f0f0fu, k3 = 0x03030303u;
+        mB = ((h.w >> 4) & k2) | (((h.z >> 6) & k3) << 4);
+        mA = h.z & k1;
+        scB = (h.w & k2) | (((h.y >> 6) & k3) << 4);
+        scA = h.y & k1;
+        qh = reinterpret_cast<const uint32_t *>(blk + 16)[l];
+        const uint32_t *q = reinterpret_cast<const uint32_t *>(blk + 48) + l;
+#pragma unroll
+        for (int j = 0; j < 4; j++) q4[j] = q[8 * j];
+    }
+    PS_D void partial(const PsActQ8K &a, int64_t i, int l, int &S, float &d, int &P, float &dm) const {
+        const uint4 lo = a.qs[(i * 2 + 0) * 8 + l], hi = a.qs[(i * 2 + 1) * 8 + l];
+        const int q8[8] = {(int)lo.x, (int)lo.y, (int)lo.z, (int)lo.w, (int)hi.x, (int)hi.y, (int)hi.z, (int)hi.w};
+        S = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+            const uint32_t v0 = (q4[j] & 0x0f0f0f0fu) | (((qh >> (2 * j)) & 0x01010101u) << 4);
+            const uint32_t v1 = ((q4[j] >> 4) & 0x0f0f0f0fu) | (((qh >> (2 * j + 1)) & 0x01010101u) << 4);
+            const int p0 = __dp4a((int)v0, q8[2 * j], 0), p1 = __dp4a((int)v1, q8[2 * j + 1], 0); // 5-bit values: fine as signed bytes
+            const uint32_t scw = (j < 2) ? scA : scB;
+            const int s0 = (scw >> (16 * (j & 1))) & 0xff, s1 = (scw >> (16 * (j & 1) + 8)) & 0xff;
+            S += s0 * p0 + s1 * p1;
+        }
+        const float yd = a.d[i];
+        d = __fmul_rn(yd, xd);
+        dm = __fmul_rn(-yd, xmin);
+        const int k = l & 3;
+        const uint32_t mw = (k < 2) ? mA : mB;
+        const int m0 = (mw >> (16 * (k & 1))) & 0xff, m1 = (mw >> (16 * (k & 1) + 8)) & 0xff;
+        const uint32_t bs = a.bsp[i * 4 + k];
+        P = m0 * (int)(short)(bs & 0xffffu) + m1 * (int)(short)(bs >> 16);
+    }
+};
+
 // ggml_vec_dot_q6_K_q8_K, AVX2 branch (libs/ggml/src/ggml-quants.c:9039-9116)
 template <> struct PsBlk<14> {
     static constexpr int BYTES = PS_Q6_K_BYTES, ELEMS = 256;
-    static constexpr bool HAS_MIN = false;
+    static constexpr bool HAS_MIN = false, MIN_SCALAR = false;
     uint32_t ql[4], qh[2];
     int sc[8];
     float xd;
@@ -256,7 +305,7 @@ template <> struct PsBlk<14> {
 // ggml_vec_dot_q4_0_q8_0, AVX2 branch (libs/ggml/src/ggml-quants.c:4205-4228)
 template <> struct PsBlk<2> {
     static constexpr int BYTES = PS_Q4_0_BYTES, ELEMS = 32;
-    static constexpr bool HAS_MIN = false;
+    static constexpr bool HAS_MIN = false, MIN_SCALAR = false;
     uint32_t q;
     float xd;
     PS_D void load(const uint8_t *blk, int l) {
@@ -275,7 +324,7 @@ template <> struct PsBlk<2> {
 // ggml_vec_dot_q8_0_q8_0, AVX2 branch (libs/ggml/src/ggml-quants.c:5761-5782)
 template <> struct PsBlk<8> {
     static constexpr int BYTES = PS_Q8_0_BYTES, ELEMS = 32;
-    static constexpr bool HAS_MIN = false;
+    static constexpr bool HAS_MIN = false, MIN_SCALAR = false;
     uint32_t q;
     float xd;
     PS_D void load(const uint8_t *blk, int l) {
@@ -350,7 +399,13 @@ __global__ void __launch_bounds__(256) ps_k_matmul_q(const uint8_t *__restrict__
                     const int Sb = __shfl_sync(PS_FULL, S, bb * 8 + l);
                     const float db = __shfl_sync(PS_FULL, d, bb * 8 + l);
                     acc[c] = __fmaf_rn(db, __int2float_rn(Sb), acc[c]);
-                    if constexpr (B::HAS_MIN) {
+                    if constexpr (B::HAS_MIN && B::MIN_SCALAR) { // summs += dmin * hsum(prod): multiply, then add (Q5_K)
+                        int Pt = 0;
+#pragma unroll
+                        for (int k = 0; k < 4; k++) Pt += __shfl_sync(PS_FULL, P, bb * 8 + k);
+                        const float dmb = __shfl_sync(PS_FULL, dm, bb * 8 + l);
+                        accm[c] = __fadd_rn(accm[c], __fmul_rn(dmb, __int2float_rn(Pt)));
+                    } else if constexpr (B::HAS_MIN) {
                         const int Pb = __shfl_sync(PS_FULL, P, bb * 8 + (l & 3));
                         const float dmb = __shfl_sync(PS_FULL, dm, bb * 8 + l);
                         accm[c] = __fmaf_rn(dmb, __int2float_rn(Pb), accm[c]);
@@ -363,7 +418,9 @@ __global__ void __launch_bounds__(256) ps_k_matmul_q(const uint8_t *__restrict__
     for (int c = 0; c < C; c++) {
         if (c < ncol) {
             float r = ps_hsum8_lanes(acc[c]);
-            if constexpr (B::HAS_MIN) {
+            if constexpr (B::HAS_MIN && B::MIN_SCALAR) {
+                r = __fadd_rn(r, accm[c]); // hsum_float_8(acc) + summs
+            } else if constexpr (B::HAS_MIN) {
                 // acc_m = add(acc_m, movehl(acc_m)); add_ss(acc_m, movehdup(acc_m))   (ggml-quants.c:7868-7871)
                 const float m0 = __shfl_sync(PS_FULL, accm[c], 0), m1 = __shfl_sync(PS_FULL, accm[c], 1);
                 const float m2 = __shfl_sync(PS_FULL, accm[c], 2), m3 = __shfl_sync(PS_FULL, accm[c], 3);
@@ -415,6 +472,20 @@ __global__ void __launch_bounds__(256) ps_k_get_embedding(float *__restrict__ ds
             const uint8_t qb = blk[16 + 32 * (j / 2) + el];
             const int q = (j & 1) ? (qb >> 4) : (qb & 0xF);
             // `d1 * q - m1` is one FMA in the reference build (gcc -O3 -mfma contracts it)
+            v = __fmaf_rn(__fmul_rn(d, (float)s), (float)q, -__fmul_rn(mn, (float)m));
+        } else if (type == 1) { // F16 table (GGML_FP16_TO_FP32)
+            v = ps_half_bits_to_float(reinterpret_cast<const unsigned short *>(row)[e]);
+        } else if (type == 13) { // dequantize_row_q5_K (ggml-quants.c:2776-2803)
+            const uint8_t *blk = row + (e / 256) * PS_Q5_K_BYTES;
+            const int r = (int)(e % 256), j = r / 32, el = r % 32;
+            const float d = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk));
+            const float mn = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk + 2));
+            const uint8_t *sc = blk + 4;
+            int s, m;
+            if (j < 4) { s = sc[j] & 63; m = sc[j + 4] & 63; }
+            else { s = (sc[j + 4] & 0xF) | ((sc[j - 4] >> 6) << 4); m = (sc[j + 4] >> 4) | ((sc[j] >> 6) << 4); }
+            const uint8_t qb = blk[48 + 32 * (j / 2) + el];
+            const int q = ((j & 1) ? (qb >> 4) : (qb & 0xF)) + (((blk[16 + el] >> j) & 1) << 4);
             v = __fmaf_rn(__fmul_rn(d, (float)s), (float)q, -__fmul_rn(mn, (float)m));
         } else { // 14: Q6_K
             const uint8_t *blk = row + (e / 256) * PS_Q6_K_BYTES;

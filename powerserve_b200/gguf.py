@@ -22,18 +22,19 @@ GGUF_VERSION = 3
 GGUF_ALIGNMENT = 32
 
 # ggml type ids (libs/ggml/include/ggml.h:386-401) -> (block elements, block bytes)
-GGML_F32, GGML_F16, GGML_Q4_0, GGML_Q8_0, GGML_Q4_K, GGML_Q6_K, GGML_Q8_K, GGML_I32 = 0, 1, 2, 8, 12, 14, 15, 26
+GGML_F32, GGML_F16, GGML_Q4_0, GGML_Q8_0, GGML_Q4_K, GGML_Q5_K, GGML_Q6_K, GGML_Q8_K, GGML_I32 = 0, 1, 2, 8, 12, 13, 14, 15, 26
 TYPE_INFO: Dict[int, Tuple[int, int]] = {
     GGML_F32: (1, 4),
     GGML_F16: (1, 2),
     GGML_Q4_0: (32, 18),
     GGML_Q8_0: (32, 34),
     GGML_Q4_K: (256, 144),
+    GGML_Q5_K: (256, 176),
     GGML_Q6_K: (256, 210),
     GGML_Q8_K: (256, 292),
     GGML_I32: (1, 4),
 }
-TYPE_NAME = {GGML_F32: "F32", GGML_F16: "F16", GGML_Q4_0: "Q4_0", GGML_Q8_0: "Q8_0", GGML_Q4_K: "Q4_K",
+TYPE_NAME = {GGML_F32: "F32", GGML_F16: "F16", GGML_Q4_0: "Q4_0", GGML_Q8_0: "Q8_0", GGML_Q4_K: "Q4_K", GGML_Q5_K: "Q5_K",
              GGML_Q6_K: "Q6_K", GGML_Q8_K: "Q8_K", GGML_I32: "I32"}
 
 # gguf metadata value types

@@ -21,7 +21,7 @@ from typing import Dict, List, Optional, Tuple
 import numpy as np
 
 from . import gguf
-from .gguf import GGML_F32, GGML_Q4_0, GGML_Q8_0, GGML_Q4_K, GGML_Q6_K
+from .gguf import GGML_F32, GGML_Q4_0, GGML_Q8_0, GGML_Q4_K, GGML_Q5_K, GGML_Q6_K
 
 
 @dataclass
@@ -63,6 +63,7 @@ PRESETS: Dict[str, ModelShape] = {
     # with the next power-of-two template and r2 active heads
     "tiny-qwen2-r7": ModelShape("tiny-qwen2-r7", "qwen2", 448, 608, 2, 7, 1, 64, 512, True, 2, 1e6, 1e-6, GGML_Q4_0, n_ctx=256, qkv_bias=True),
     "tiny-q8-r3": ModelShape("tiny-q8-r3", "llama", 384, 512, 2, 6, 2, 64, 512, False, 0, 1e4, 1e-5, GGML_Q8_0, n_ctx=256),
+    "tiny-q5k": ModelShape("tiny-q5k", "llama", 512, 1024, 2, 8, 2, 64, 768, True, 0, 5e5, 1e-5, GGML_Q5_K, n_ctx=256),   # real-file coverage
     "tiny-q8": ModelShape("tiny-q8", "llama", 256, 512, 2, 4, 4, 64, 512, False, 0, 1e4, 1e-5, GGML_Q8_0, n_ctx=256),
     # real per-layer shapes of the BASELINE models with few layers / small vocab (exercise nb = 8/32 and 16/56 paths)
     "slice-1b": ModelShape("slice-1b", "llama", 2048, 8192, 2, 32, 8, 64, 2048, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=1024),
@@ -112,6 +113,18 @@ def random_blocks(rng: np.random.Generator, ggml_type: int, n_rows: int, k: int,
         out[:, 0:2] = _f16_bytes(d)
         out[:, 2:4] = _f16_bytes(8.0 * d)
         # inverse of get_scale_min_k4 (ggml-quants.c:1912-1919)
+        out[:, 4:8] = (sc[:, 0:4] & 63) | ((sc[:, 4:8] >> 4) << 6)
+        out[:, 8:12] = (m[:, 0:4] & 63) | ((m[:, 4:8] >> 4) << 6)
+        out[:, 12:16] = (sc[:, 4:8] & 0xF) | ((m[:, 4:8] & 0xF) << 4)
+    elif ggml_type == GGML_Q5_K:
+        # block_q5_K = d, dmin, scales[12], qh[32], qs[128]: w = d*sc_j*q - dmin*m_j with q 5-bit uniform (mean 15.5, std 9.23);
+        # m_j ~ 15.5*sc_j*(d/dmin) with dmin = 16 d keeps every sub-block (nearly) zero-mean; std(w) ~ d * 41 * 9.23 ~ 380 d
+        d = std / 380.0 * jitter
+        r = out[:, 4:12].copy()
+        sc = (16 + (r & 31) + ((r >> 5) & 7) * 2).astype(np.uint8)             # 16 .. 61
+        m = np.minimum(63, ((sc.astype(np.uint16) * 31 + 16) >> 5) + ((r >> 3) & 3)).astype(np.uint8) - 1
+        out[:, 0:2] = _f16_bytes(d)
+        out[:, 2:4] = _f16_bytes(16.0 * d)
         out[:, 4:8] = (sc[:, 0:4] & 63) | ((sc[:, 4:8] >> 4) << 6)
         out[:, 8:12] = (m[:, 0:4] & 63) | ((m[:, 4:8] >> 4) << 6)
         out[:, 12:16] = (sc[:, 4:8] & 0xF) | ((m[:, 4:8] & 0xF) << 4)

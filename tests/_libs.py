@@ -13,7 +13,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 REF_DIR = os.path.join(ORACLE_DIR, "_ref")
 
-F32, Q4_0, Q8_0, Q4_K, Q6_K, Q8_K = 0, 2, 8, 12, 14, 15
+F32, Q4_0, Q8_0, Q4_K, Q5_K, Q6_K, Q8_K = 0, 2, 8, 12, 13, 14, 15
 
 c_f = C.POINTER(C.c_float)
 c_i32 = C.POINTER(C.c_int32)
@@ -134,9 +134,9 @@ def ref_ggml() -> C.CDLL:
         L._ctx = L.ggml_init(InitParams(1 << 20, None, True))
         for n in ("quantize_row_q8_K", "quantize_row_q8_0"):
             getattr(L, n).argtypes = [c_f, C.c_void_p, C.c_int64]
-        for n in ("dequantize_row_q4_0", "dequantize_row_q8_0", "dequantize_row_q4_K", "dequantize_row_q6_K"):
+        for n in ("dequantize_row_q4_0", "dequantize_row_q8_0", "dequantize_row_q4_K", "dequantize_row_q5_K", "dequantize_row_q6_K"):
             getattr(L, n).argtypes = [C.c_void_p, c_f, C.c_int64]
-        for n in ("ggml_vec_dot_q4_K_q8_K", "ggml_vec_dot_q6_K_q8_K", "ggml_vec_dot_q4_0_q8_0", "ggml_vec_dot_q8_0_q8_0"):
+        for n in ("ggml_vec_dot_q4_K_q8_K", "ggml_vec_dot_q5_K_q8_K", "ggml_vec_dot_q6_K_q8_K", "ggml_vec_dot_q4_0_q8_0", "ggml_vec_dot_q8_0_q8_0"):
             getattr(L, n).argtypes = [C.c_int, c_f, C.c_size_t, C.c_void_p, C.c_size_t, C.c_void_p, C.c_size_t, C.c_int]
         L.ggml_fp16_to_fp32.restype = C.c_float
         L.ggml_fp16_to_fp32.argtypes = [C.c_uint16]

@@ -111,7 +111,7 @@ def test_matvec_ksplit_and_deferred_stream_are_bit_exact(preset):
     cm.close()
 
 
-@pytest.mark.parametrize("preset", ["tiny-qwen2", "tiny-qwen2-r7", "tiny-q8", "tiny-q8-r3", "tiny-mixed", "tiny-llama"])
+@pytest.mark.parametrize("preset", ["tiny-qwen2", "tiny-qwen2-r7", "tiny-q8", "tiny-q8-r3", "tiny-mixed", "tiny-llama", "tiny-q5k"])
 def test_graph_replayed_operator_table_step_for_every_weight_type(preset):
     """Models off the all-Q4_K fused path (Q4_0 / Q8_0 matrices, a Q6_K output matrix, NEOX rope + biases, 3 or 7 query heads per
     kv head) decode through decode_step_ops: table-op weight products + the position-from-device decode attention kernels,

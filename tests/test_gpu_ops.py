@@ -9,7 +9,7 @@ from tests import _libs as L
 
 pytestmark = pytest.mark.gpu
 
-QTYPES = [(L.Q4_K, 256), (L.Q6_K, 256), (L.Q4_0, 32), (L.Q8_0, 32)]
+QTYPES = [(L.Q4_K, 256), (L.Q6_K, 256), (L.Q4_0, 32), (L.Q8_0, 32), (L.Q5_K, 256)]   # Q5_K: real-file coverage
 
 
 @pytest.fixture(scope="module")
@@ -196,3 +196,58 @@ def test_error_behaviour(be):
         be.rope(x, x, 64, 1, 1, [0])             # head_size mismatch with the model's rope dims
     with pytest.raises(capi.PsCudaError):
         be.kv_rollback(1)                        # POWERSERVE_ASSERT_KVCACHE(position >= n_tokens)
+
+
+def test_get_embedding_f16_table(be):
+    """an F16 token_embd table (real GGUFs of the F16 / some K-quant recipes): GGML_FP16_TO_FP32 per element"""
+    rng = np.random.default_rng(31)
+    dim, vocab = 96, 40
+    w16 = rng.standard_normal(vocab * dim).astype(np.float16)
+    toks = np.array([0, 39, 5, 5], np.int32)
+    w = w16.view(np.uint8)
+    wd = be.register_weight(w, 1, dim, vocab)
+    dd = be.empty(dim * 4)
+    be.get_embedding(dd, wd, 1, dim, toks)
+    L.assert_bit_equal(dd.numpy(), w16.reshape(vocab, dim)[toks].astype(np.float32).reshape(-1), "f16 embedding")
+    be.unregister_weight(w)
+
+
+def test_rope_freq_factors(be):
+    """rope_freqs.weight (ggml_rope_cache_init with freq_factors, ggml.c:15342-15356: rope_yarn(theta / ff, ...)); off by default
+    because the reference never passes it.  Checked against a float32 restatement evaluated with the platform
+    libm (the table is built on the host with cosf / sinf / powf), then switched off again (bit-exact vs the oracle)."""
+    import ctypes as C
+    libm = C.CDLL("libm.so.6")
+    for f in ("cosf", "sinf"):
+        getattr(libm, f).restype = C.c_float
+        getattr(libm, f).argtypes = [C.c_float]
+    libm.powf.restype = C.c_float
+    libm.powf.argtypes = [C.c_float, C.c_float]
+    hs, nh, base = 128, 3, 5e5
+    rng = np.random.default_rng(17)
+    ff = np.concatenate([np.ones(20), np.linspace(1.0, 8.0, 24), np.full(20, 8.0)]).astype(np.float32)     # llama3-style: low frequencies stretched
+    pos = np.array([0, 1, 5, 100, 2047, 4095], np.int32)
+    x = act(rng, hs * nh * len(pos))
+    be.set_rope_freq_factors(ff)
+    xd, dd = be.upload(x), be.empty(x.size)
+    be.rope(dd, xd, hs, nh, len(pos), pos)
+    got = dd.numpy().reshape(len(pos), nh, hs)
+    theta_scale = np.float32(libm.powf(np.float32(base), np.float32(-2.0 / hs)))
+    want = np.zeros_like(got)
+    X = x.reshape(len(pos), nh, hs)
+    for a, p in enumerate(pos):
+        theta = np.float32(p)
+        for i0 in range(0, hs, 2):
+            th = np.float32(np.float32(1.0) * np.float32(theta / ff[i0 // 2]))
+            c, s = np.float32(libm.cosf(th)), np.float32(libm.sinf(th))
+            x0, x1 = X[a, :, i0], X[a, :, i0 + 1]
+            want[a, :, i0] = (x0 * c).astype(np.float32) - (x1 * s).astype(np.float32)
+            want[a, :, i0 + 1] = (x0 * s).astype(np.float32) + (x1 * c).astype(np.float32)
+            theta = np.float32(theta * theta_scale)
+    L.assert_bit_equal(got.reshape(-1), want.reshape(-1), "rope with freq factors")
+    be.set_rope_freq_factors(None)
+    o = L.oracle()
+    ref = np.zeros_like(x)
+    o.ps_or_rope(L.fptr(ref), L.fptr(x), hs, nh, len(pos), L.iptr(pos), hs, 0, base, 1.0, 1.0)
+    be.rope(dd, xd, hs, nh, len(pos), pos)
+    L.assert_bit_equal(dd.numpy(), ref, "rope, factors off again")

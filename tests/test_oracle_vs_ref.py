@@ -13,6 +13,8 @@ from tests import _libs as L
 pytestmark = pytest.mark.skipif(not L.have_ref(), reason="oracle/_ref not built (needs /root/reference)")
 
 QTYPES = [(L.Q4_K, 256), (L.Q6_K, 256), (L.Q4_0, 32), (L.Q8_0, 32)]
+# Q5_K (real Q4_K_S / Q5_K_M files): pinned at the block level - the reference's own DataType layer cannot carry it
+BLOCK_TYPES = QTYPES + [(L.Q5_K, 256)]
 
 
 def rand_act(rng, n, kind):
@@ -68,7 +70,7 @@ def test_quantize_q8_0(kind):
     assert (a == b).all()
 
 
-@pytest.mark.parametrize("t,blk", QTYPES)
+@pytest.mark.parametrize("t,blk", BLOCK_TYPES)
 def test_dequantize(t, blk):
     o, r = L.oracle(), L.ref_ggml()
     rng = np.random.default_rng(3)
@@ -79,17 +81,17 @@ def test_dequantize(t, blk):
     for ww in (w, w2):
         a, b = np.zeros(5 * k, np.float32), np.zeros(5 * k, np.float32)
         o.ps_or_dequantize_row(t, L.vptr(ww), L.fptr(a), 5 * k)
-        getattr(r, {L.Q4_0: "dequantize_row_q4_0", L.Q8_0: "dequantize_row_q8_0", L.Q4_K: "dequantize_row_q4_K", L.Q6_K: "dequantize_row_q6_K"}[t])(L.vptr(ww), L.fptr(b), 5 * k)
+        getattr(r, {L.Q4_0: "dequantize_row_q4_0", L.Q8_0: "dequantize_row_q8_0", L.Q4_K: "dequantize_row_q4_K", L.Q5_K: "dequantize_row_q5_K", L.Q6_K: "dequantize_row_q6_K"}[t])(L.vptr(ww), L.fptr(b), 5 * k)
         fin = np.isfinite(b)
         L.assert_bit_equal(np.where(fin, a, 0), np.where(fin, b, 0), f"dequant {t}")
 
 
-@pytest.mark.parametrize("t,blk", QTYPES)
+@pytest.mark.parametrize("t,blk", BLOCK_TYPES)
 @pytest.mark.parametrize("kind", ["normal", "wide"])
 def test_vec_dot(t, blk, kind):
     o, r = L.oracle(), L.ref_ggml()
     rng = np.random.default_rng(4)
-    fn = {L.Q4_0: "ggml_vec_dot_q4_0_q8_0", L.Q8_0: "ggml_vec_dot_q8_0_q8_0", L.Q4_K: "ggml_vec_dot_q4_K_q8_K", L.Q6_K: "ggml_vec_dot_q6_K_q8_K"}[t]
+    fn = {L.Q4_0: "ggml_vec_dot_q4_0_q8_0", L.Q8_0: "ggml_vec_dot_q8_0_q8_0", L.Q4_K: "ggml_vec_dot_q4_K_q8_K", L.Q5_K: "ggml_vec_dot_q5_K_q8_K", L.Q6_K: "ggml_vec_dot_q6_K_q8_K"}[t]
     qt = L.Q8_K if blk == 256 else L.Q8_0
     for k in (blk, blk * 3, blk * 16, blk * 56):
         for _ in range(8):
