@@ -138,6 +138,10 @@ struct ps_cuda_ctx {
     int64_t kt_launches = 0;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
+    int opt_attn_group = 0;  // opt-in: decode attention as ONE group-synchronised kernel per layer (ps_k_attn_group); bit-exact, but 23 us vs 11.7 us per layer at ctx 2048
+    unsigned long long *ag_ctr = nullptr; // [n_layers][n_kv_heads] arrival counters of the kv-head groups
+    float *ag_max = nullptr;              // [n_kv_heads][hs / 8][8] chunk maxima
+    double *ag_sum = nullptr;             // [n_kv_heads][hs / 8][8] chunk sums
     bool mv_ok = false;      // every matmul weight is Q4_0 (or every one Q8_0): the fused 32-block decode path applies (ps_mv32.cuh)
     int mv_type = 0;
     uint8_t *mv_out = nullptr;
@@ -241,6 +245,7 @@ int sync_and_check(ps_cuda_ctx *ctx) {
         const int tc = ctx->h_err[0], tp = ctx->h_err[1], st = ctx->h_err[2];
         for (int k = 0; k < 3; k++) ctx->err_seen[k] |= ctx->h_err[k];
         PS_CK(cudaMemsetAsync(ctx->err_dev, 0, 16, ctx->stream));
+        if (ctx->ag_ctr) PS_CK(cudaMemsetAsync(ctx->ag_ctr, 0, (size_t)ctx->d.n_layers * ctx->nkv_l * 8, ctx->stream)); // a group that gave up leaves its counter mid-instance
         return fail(ctx, PS_CUDA_ERR_CUDA, "device-side failure:%s%s%s (wait site %d; results of this call are invalid)", tc ? " tcgen05 pipeline time-out" : "",
                     tp ? " tensor-parallel peer wait gave up" : "", st ? " decode-step wait gave up" : "", st);
     }
@@ -573,9 +578,23 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L, int r2 = R2, const fl
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
         PS_CK(cudaFuncSetAttribute(ps_k_attn2<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
+        PS_CK(cudaFuncSetAttribute(ps_k_attn_group<R2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 215 * 1024));
         attr[ctx->device] = true;
     }
     int rc;
+    {   // one group-synchronised kernel per layer when every CTA of every kv-head group is resident at once
+        const int NC = hs / 8;
+        const size_t row_b = (size_t)((d.n_ctx + 31) & ~31) * 4;
+        const int chunk_cap = (((d.n_ctx + NC - 1) / NC) + 7) & ~7;
+        const size_t smem_g = (size_t)(R2 + 8) * row_b + (size_t)R2 * chunk_cap * 4;
+        if (ctx->opt_attn_group && ctx->ag_ctr && ctx->tp == 1 && hs % 8 == 0 && NC >= 1 && NC * nkv <= ctx->n_sm && d.n_ctx % 4 == 0 && smem_g <= 212 * 1024) {
+            if ((rc = launch_k(ctx, ps_k_attn_group<R2>, dim3((unsigned)NC, (unsigned)nkv), dim3(PS_AG_THREADS), smem_g, ctx->att, (const float *)ctx->kc[L],
+                               (const float *)ctx->vct[L], q_rot, ctx->kq, (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, r2, ctx->ag_ctr + (size_t)L * nkv,
+                               ctx->ag_max, ctx->ag_sum, ctx->err_dev + 2, chunk_cap, tl_slot(ctx)))) return rc;
+            if (ctx->trace_dev) tl_slot(ctx); // keep the timeline's six slots per layer
+            return 0;
+        }
+    }
     if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], q_rot,
                        (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx), r2))) return rc;
     // probabilities of the group + (when they fit) the CTA's eight V^T rows, all sized for a full context
@@ -1197,6 +1216,13 @@ int ps_cuda_create(ps_cuda_ctx **out, int device, const ps_cuda_model_desc *desc
         PS_AL(ctx->vct[L], 4 * kvd_l * d.n_ctx);
         PS_CKC(cudaMemsetAsync(ctx->kc[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
         PS_CKC(cudaMemsetAsync(ctx->vct[L], 0, 4 * kvd_l * d.n_ctx, ctx->stream));
+    }
+    if (tp == 1 && d.head_size % 8 == 0) { // group-synchronised decode attention: arrival counters and the chunk maxima / sums of every kv-head group
+        const size_t nc = (size_t)d.n_layers * d.n_kv_heads, np = (size_t)d.n_kv_heads * (d.head_size / 8) * 8;
+        PS_AL(ctx->ag_ctr, nc * 8);
+        PS_AL(ctx->ag_max, np * 4);
+        PS_AL(ctx->ag_sum, np * 8);
+        PS_CKC(cudaMemsetAsync(ctx->ag_ctr, 0, nc * 8, ctx->stream));
     }
     {   // speculative decode: slot mask, staging rows of the last batch, cache pointer table, tree bias
         const int64_t kvd_l = kvd / tp, tb = std::min<int64_t>(B, 32);
@@ -2584,6 +2610,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "rw_ksplit")) ctx->opt_ksplit = value;   // opt-in (default 0): most warps that may share a row octet in the mat-vec launches with few octets per CTA; bit-exact but measured 3-4 % slower per step (profiles/r02_ab_matvec_ksplit_8b_ctx2048.txt)
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA
+    else if (!strcmp(name, "attn_group")) ctx->opt_attn_group = value; // 1: decode attention as one group-synchronised kernel per layer (bit-exact, slower so far: DESIGN.md 5b); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "attn_fused")) ctx->opt_attn_fused = value; // 1: decode attention as ONE cluster kernel per layer (bit-exact, but slower so far: DESIGN.md); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "l2_ahead")) ctx->opt_l2_ahead = value;     // tuning: L2 look-ahead of the step kernel's weight stream, in 4736-byte stages per CTA
     else if (!strcmp(name, "attn_chunk")) ctx->opt_attn_chunk = value; // testing: soft-max positions resident in shared memory (multiple of 256)

@@ -475,6 +475,258 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
     ps_tl_max(tl, 1);
 }
 
+// ====================================================================================================================
+// Decode attention in ONE kernel without clusters ("group-synchronised"): the hs / 8 CTAs of a kv head form a GROUP that
+// meets twice at a counter in global memory.  CTA (c, g) first scores ITS chunk of the cache positions against the R2
+// query heads (K rows requested before the dependency wait, 8 rows per warp in registers, as ps_k_attn1), publishes the
+// chunk maxima, meets the group (1), turns its chunk into exponentials with the ROW maximum - ggml_v_expf on the row's full
+// 8-groups, libm expf on its tail - publishes them and the chunk sums, meets the group (2), gathers the R2 rows of
+// exponentials, scales them and walks its eight V^T rows (staged by TMA right after the dependency wait) as ps_k_attn2 does.
+// One kernel boundary per layer disappears and the soft-max row is built ONCE per kv head instead of once per CTA (16x for
+// head size 128).  All CTAs of a group are co-resident by construction (grid <= SM count, one CTA per SM; the dependent
+// grid starts only after every CTA of this one has started), the waits are bounded all the same (error flag, no hang).
+// Arithmetic = ps_k_attn1 + ps_k_attn2: ggml_vec_dot_f32 lane chains, GGML_F32x8_REDUCE, scale, + 0.0f mask, soft-max with
+// double sums (tree order), position-ordered FMA chains for P.V.  norm_attention.cpp:115-151.
+// ====================================================================================================================
+#define PS_AG_THREADS 512
+PS_D unsigned long long ps_ag_ld_acquire(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// every thread of the CTA calls this; returns false if the group did not arrive in time
+PS_D bool ps_ag_meet(unsigned long long *ctr, unsigned long long *s_target, int step, int n_cta, int *err) {
+    __syncthreads(); // the CTA's global stores of this phase are issued
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned long long old = atomicAdd(ctr, 1ull);
+        // a kernel instance adds 2 * n_cta to its group's counter, and instances of one layer never overlap
+        if (step == 0) *s_target = old / (2ull * n_cta) * (2ull * n_cta) + n_cta;
+        else *s_target += n_cta;
+        const unsigned long long target = *s_target;
+        int spins = 0;
+        while (ps_ag_ld_acquire(ctr) < target)
+            if (++spins > (1 << 22)) { *err = 5; break; }
+        __threadfence();
+    }
+    __syncthreads();
+    return true;
+}
+
+template <int R2>
+__global__ void __launch_bounds__(PS_AG_THREADS, 1) ps_k_attn_group(float *__restrict__ att, const float *__restrict__ kc, const float *__restrict__ vct,
+                                                                     const float *__restrict__ q, float *__restrict__ ex, const int32_t *__restrict__ pos_dev, int hs,
+                                                                     int n_kv_heads, int n_ctx, float scale, int r2, unsigned long long *__restrict__ sync_ctr,
+                                                                     float *__restrict__ part_max, double *__restrict__ part_sum, int *__restrict__ err,
+                                                                     int chunk_cap, long long *tl) {
+    extern __shared__ __align__(128) float s_dyn[]; // [R2][stride] exponentials / probabilities, [8][stride] V^T rows, [R2][chunk_cap] chunk scores
+    __shared__ float s_q[R2][256];
+    __shared__ double shd[PS_AG_THREADS / 32];
+    __shared__ float shf[PS_AG_THREADS / 32];
+    __shared__ __align__(8) uint64_t bar_v;
+    __shared__ unsigned long long s_target;
+    const int c = blockIdx.x, g = blockIdx.y, NC = gridDim.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int steps = hs / 32, kvd = hs * n_kv_heads;
+    if (tid == 0) {
+        ps_mbar_init(&bar_v, 1);
+        ps_fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    ps_tl_min(tl, 0);
+    // ---- before the dependency wait: position and the chunk's K rows except row `pos` (see ps_k_attn1)
+    const int pos = pos_dev[0];
+    const int64_t n_kv = (int64_t)pos + 1, stride = (n_kv + 31) & ~(int64_t)31, n8 = n_kv & ~(int64_t)7;
+    const int P = (int)((((n_kv + NC - 1) / NC) + 7) & ~(int64_t)7); // positions per chunk, a multiple of 8
+    const int j_lo = c * P, j_hi = (int)min((int64_t)j_lo + P, n_kv), len = max(j_hi - j_lo, 0);
+    float *s_p = s_dyn, *s_v = s_dyn + (size_t)R2 * stride, *s_sc = s_v + (size_t)8 * stride;
+    const int n_rows = min(8, hs - c * 8);
+    const uint32_t row_bytes = (uint32_t)(((n_kv + 3) & ~(int64_t)3) * 4);
+    constexpr int RPB = (PS_AG_THREADS / 32) * 8; // cache rows per batch: 8 per warp
+    float kv[8][8];
+    {
+        const int j0 = j_lo + warp * 8;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int s = 0; s < 8; s++) {
+                kv[t][s] = 0.f;
+                if (s < steps && j0 + t < j_hi && j0 + t < pos) kv[t][s] = kc[(int64_t)(j0 + t) * kvd + g * hs + 32 * s + lane];
+            }
+    }
+    ps_grid_dep_wait();
+    ps_grid_dep_launch();
+    ps_tl_min(tl, 2);
+    const long long t_dep = (tl && tid == 0) ? ps_globaltimer() : 0;
+#define PS_AG_PROBE(k)                                                                                                   \
+    do {                                                                                                                 \
+        if (tl && tid == 0) atomicMax(reinterpret_cast<unsigned long long *>(tl + (k)), (unsigned long long)(ps_globaltimer() - t_dep)); \
+    } while (0)
+    // the V^T rows only now: their column `pos` comes from the kernel this one waits for (they are needed last, so the copy
+    // still hides behind the two score phases)
+    if (tid == 0) {
+        ps_mbar_expect_tx(&bar_v, row_bytes * n_rows);
+        for (int w = 0; w < n_rows; w++) ps_bulk_g2s(s_v + w * stride, vct + ((int64_t)g * hs + c * 8 + w) * n_ctx, row_bytes, &bar_v);
+    }
+    for (int idx = tid; idx < R2 * hs; idx += PS_AG_THREADS) s_q[idx / hs][idx % hs] = (idx < r2 * hs) ? q[(int64_t)g * r2 * hs + idx] : 0.f;
+    __syncthreads();
+    // ---- phase 1: scores of this chunk -> s_sc[h][j - j_lo]
+    for (int b0 = 0; b0 < len; b0 += RPB) {
+        const int j0 = j_lo + b0 + warp * 8;
+        if (b0 > 0) { // chunks longer than one batch (contexts beyond RPB * NC positions): further batches are loaded here
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int s = 0; s < 8; s++) {
+                    kv[t][s] = 0.f;
+                    if (s < steps && j0 + t < j_hi && j0 + t < pos) kv[t][s] = kc[(int64_t)(j0 + t) * kvd + g * hs + 32 * s + lane];
+                }
+        }
+        if (j0 <= pos && pos < j0 + 8 && pos < j_hi) { // warp-uniform: the row the q|k|v kernel has just written
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < steps && j0 + t == pos) kv[t][s] = kc[(int64_t)(j0 + t) * kvd + g * hs + 32 * s + lane];
+        }
+        float qv[R2][8];
+#pragma unroll
+        for (int hh = 0; hh < R2; hh++)
+#pragma unroll
+            for (int s = 0; s < 8; s++) qv[hh][s] = (s < steps) ? s_q[hh][32 * s + lane] : 0.f;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+            float sum[R2];
+#pragma unroll
+            for (int hh = 0; hh < R2; hh++) {
+                sum[hh] = 0.f;
+#pragma unroll
+                for (int s = 0; s < 8; s++)
+                    if (s < steps) sum[hh] = __fmaf_rn(kv[t][s], qv[hh][s], sum[hh]);
+            }
+            ps_f32x8_reduce_n<R2>(sum);
+            if (lane < r2 && j0 + t < j_hi) {
+                float v = sum[0];
+#pragma unroll
+                for (int hh = 1; hh < R2; hh++)
+                    if (lane == hh) v = sum[hh];
+                s_sc[lane * chunk_cap + (j0 + t - j_lo)] = __fadd_rn(__fmul_rn(v, scale), 0.0f);
+            }
+        }
+    }
+    __syncthreads();
+    constexpr int TPH = PS_AG_THREADS / R2, WPH = TPH / 32; // threads / warps per head
+    const int hh = tid / TPH, ht = tid % TPH;
+    const int my_len = (hh < r2) ? len : 0;
+    float *sc_row = s_sc + hh * chunk_cap;
+    {
+        float mx = -INFINITY;
+        for (int j = ht; j < my_len; j += TPH) mx = fmaxf(mx, sc_row[j]);
+#pragma unroll
+        for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
+        if (lane == 0) shf[warp] = mx;
+        __syncthreads();
+        if (ht == 0 && hh < r2) {
+            mx = shf[hh * WPH];
+#pragma unroll
+            for (int t = 1; t < WPH; t++) mx = fmaxf(mx, shf[hh * WPH + t]);
+            part_max[((size_t)g * NC + c) * R2 + hh] = mx;
+        }
+    }
+    unsigned long long *ctr = sync_ctr + g;
+    PS_AG_PROBE(4);
+    ps_ag_meet(ctr, &s_target, 0, NC, err);
+    PS_AG_PROBE(5);
+    // ---- phase 2: exponentials of this chunk with the row maximum
+    {
+        float mx = -INFINITY;
+        if (hh < r2)
+            for (int cc = 0; cc < NC; cc++) mx = fmaxf(mx, __ldcg(part_max + ((size_t)g * NC + cc) * R2 + hh));
+        float *erow = ex + (int64_t)(g * r2 + hh) * n_ctx + j_lo;
+        double sdb = 0.0;
+        const int n8l = (int)max(min((int64_t)j_hi, n8) - j_lo, (int64_t)0); // the chunk's share of the row's full 8-groups (chunks start on multiples of 8)
+        for (int gi = ht; gi < (my_len ? n8l / 8 : 0); gi += TPH) {
+            float4 *p4 = reinterpret_cast<float4 *>(sc_row + gi * 8);
+            const float4 xa = p4[0], xb = p4[1];
+            float vv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
+#pragma unroll
+            for (int l = 0; l < 8; l++) vv[l] = ps_v_expf(__fadd_rn(vv[l], -mx));
+            *reinterpret_cast<float4 *>(erow + gi * 8) = make_float4(vv[0], vv[1], vv[2], vv[3]);
+            *reinterpret_cast<float4 *>(erow + gi * 8 + 4) = make_float4(vv[4], vv[5], vv[6], vv[7]);
+            const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
+            sdb += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
+        }
+        for (int j = n8l + ht; j < my_len; j += TPH) { // the row's scalar tail (only in the chunk that holds it): libm expf
+            const float vv = ps_expf_glibc(__fadd_rn(sc_row[j], -mx));
+            erow[j] = vv;
+            sdb += (double)vv;
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) sdb += __shfl_xor_sync(PS_FULL, sdb, o);
+        if (lane == 0) shd[warp] = sdb;
+        __syncthreads();
+        if (ht == 0 && hh < r2) {
+            double sum = shd[hh * WPH];
+#pragma unroll
+            for (int t = 1; t < WPH; t++) sum += shd[hh * WPH + t];
+            part_sum[((size_t)g * NC + c) * R2 + hh] = sum;
+        }
+    }
+    PS_AG_PROBE(6);
+    ps_ag_meet(ctr, &s_target, 1, NC, err);
+    PS_AG_PROBE(7);
+    // ---- phase 3: gather the R2 rows of exponentials, scale, P.V for this CTA's eight output dims
+    {
+        const int64_t n4 = (n_kv + 3) >> 2;
+        for (int h2 = 0; h2 < r2; h2++) {
+            const float4 *src = reinterpret_cast<const float4 *>(ex + (int64_t)(g * r2 + h2) * n_ctx);
+            float4 *dst = reinterpret_cast<float4 *>(s_p + (size_t)h2 * stride);
+            for (int64_t t = tid; t < n4; t += PS_AG_THREADS) dst[t] = __ldcg(src + t);
+        }
+        double sum = 0.0;
+        if (hh < r2)
+            for (int cc = 0; cc < NC; cc++) sum += __ldcg(part_sum + ((size_t)g * NC + cc) * R2 + hh);
+        const float inv = (float)(1.0 / sum);
+        __syncthreads();
+        if (hh < r2) {
+            float *pp = s_p + (size_t)hh * stride;
+            for (int64_t j = ht; j < n_kv; j += TPH) pp[j] = __fmul_rn(pp[j], inv);
+        }
+    }
+    __syncthreads();
+    ps_tl_max(tl, 3);
+    const int d = c * 8 + warp;
+    if (warp < 8 && d < hs) {
+        const int64_t np = n_kv & ~(int64_t)31;
+        float sum[R2];
+#pragma unroll
+        for (int h2 = 0; h2 < R2; h2++) sum[h2] = 0.f;
+        const int ntail = (int)(n_kv - np);
+        ps_mbar_wait(&bar_v, 0);
+        const float *vs = s_v + warp * stride;
+        const float vtail = (lane < ntail) ? vs[np + lane] : 0.f;
+#pragma unroll 8
+        for (int64_t s0 = 0; s0 < np; s0 += 32) { // the FMA chains stay in position order
+            const float v = vs[s0 + lane];
+#pragma unroll
+            for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(v, s_p[h2 * stride + s0 + lane], sum[h2]);
+        }
+        ps_f32x8_reduce_n<R2>(sum);
+        for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order
+            const float v = __shfl_sync(PS_FULL, vtail, t);
+#pragma unroll
+            for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fadd_rn(sum[h2], __fmul_rn(v, s_p[h2 * stride + np + t]));
+        }
+        if (lane < r2) {
+            float v = sum[0];
+#pragma unroll
+            for (int h2 = 1; h2 < R2; h2++)
+                if (lane == h2) v = sum[h2];
+            att[(int64_t)(g * r2 + lane) * hs + d] = v;
+        }
+    }
+    ps_tl_max(tl, 1);
+}
+
 // GGMLBackend::get_embedding for the token held in device memory (decode feedback loop)
 __global__ void __launch_bounds__(256) ps_k_embed_dev(float *__restrict__ dst, const uint8_t *__restrict__ w, int type, int64_t dim,
                                                       const int32_t *__restrict__ tokens, long long *tl) {

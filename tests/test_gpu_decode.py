@@ -11,7 +11,8 @@ from tests import _model as M
 pytestmark = pytest.mark.gpu
 
 
-def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0, attn_fused=0, ops_graph=0):
+def run(cm, prompt, n_dec, fused, graph, pdl=1, persist=0, attn_chunk=0, attn_fused=0, ops_graph=0, attn_group=0):
+    cm.be.set_option("attn_group", attn_group)  # 1 = decode attention as ONE group-synchronised kernel per layer (opt-in), 0 = scores kernel + soft-max / P.V kernel (default)
     cm.be.set_option("ops_graph", ops_graph)  # 0 with fused = 0: the plain table-op path (one launch per op, host-fed positions)
     cm.be.set_option("fused", fused)
     cm.be.set_option("graph", graph)
@@ -37,6 +38,11 @@ def test_fused_equals_table_ops_and_oracle(preset):
     ids_g, lg_g = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1)
     L.assert_bit_equal(lg_g, lg_u, f"{preset}: fused+PDL+graph vs table ops")
     assert ids_u == ids_f == ids_p == ids_g
+    for g_, p_ in ((0, 0), (1, 1)):     # the group-synchronised one-kernel decode attention (the runs above use the two-kernel default)
+        ids_k, lg_k = run(cm, prompt, n_dec, fused=1, graph=g_, pdl=p_, attn_group=1)
+        L.assert_bit_equal(lg_k, lg_u, f"{preset}: group-synchronised attention (graph {g_}, pdl {p_}) vs table ops")
+        assert ids_k == ids_u
+    assert cm.be.counter("step_error") == 0
     ids_2, lg_2 = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1, attn_fused=1)
     L.assert_bit_equal(lg_2, lg_u, f"{preset}: one-kernel (cluster) attention vs table ops")
     assert ids_2 == ids_u

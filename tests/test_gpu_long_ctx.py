@@ -46,4 +46,10 @@ def test_long_context_decode_matches_reference(case, n_ctx, persist):
     assert dev_ids == ids
     assert cm.be.counter("tc_error") == 0 and cm.be.counter("step_error") == 0
     assert (cm.be.counter("step_launches") > 0) == bool(persist)
+    if not persist:   # the opt-in group-synchronised attention kernel (applies at n_ctx 4096; falls back to the two kernels beyond)
+        cm.be.set_option("attn_group", 1)
+        for _ in range(3):   # repeated: its cross-CTA hand-offs are timing dependent
+            ids2, lg2 = cm.generate(prompt, n_dec, batch_size=batch)
+            assert ids2 == ids and (L.bits(lg2) == gold[key + "/logits_bits"]).all(), "group-synchronised attention differs from the compiled reference"
+        assert cm.be.counter("step_error") == 0
     cm.close()
