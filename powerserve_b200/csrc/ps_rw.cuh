@@ -181,17 +181,21 @@ PS_D float ps_rw_row_result(const PsRwAcc &acc) {
 // ---------------------------------------------------------------------------------------------------- the kernel
 // quantise one 256-block held as e[8] per lane (see ps_quant_block_q8k_regs) into the shared-memory image the block
 // math reads: qa[i][j2][q] = {sub-block 2*j2 words 2q, 2q+1 ; sub-block 2*j2+1 words 2q, 2q+1}, meta[i][q] = {d, bsums pair q}
-__device__ __noinline__ void ps_rw_quant_store(const float *e, int lane, uint32_t *qw, uint2 *meta) {
+// (the eight elements travel BY VALUE: a pointer to the caller's register array would force it through local memory - two
+// STL.128 + two LDL.128 per call, L2 round trips when the 24 KB of L1 left beside the shared-memory carve-out miss)
+__device__ __noinline__ void ps_rw_quant_store_v(float4 ea, float4 eb, int lane, uint32_t *qw, uint2 *meta) {
     uint32_t words[2], bsp4;
     float yd;
-    float v[8];
-#pragma unroll
-    for (int t = 0; t < 8; t++) v[t] = e[t];
+    const float v[8] = {ea.x, ea.y, ea.z, ea.w, eb.x, eb.y, eb.z, eb.w};
     ps_quant_block_q8k_regs(v, lane, words, yd, bsp4);
     const int l = lane & 7, jA = lane >> 3, jB = 4 + (lane >> 3); // natural words: (sub-block L/8, word L%8), (4 + L/8, L%8)
     qw[((jA >> 1) * 4 + (l >> 1)) * 4 + (jA & 1) * 2 + (l & 1)] = words[0];
     qw[((jB >> 1) * 4 + (l >> 1)) * 4 + (jB & 1) * 2 + (l & 1)] = words[1];
     if (lane < 4) meta[lane] = make_uint2(__float_as_uint(yd), bsp4);
+}
+
+PS_D void ps_rw_quant_store(const float *e, int lane, uint32_t *qw, uint2 *meta) {
+    ps_rw_quant_store_v(make_float4(e[0], e[1], e[2], e[3]), make_float4(e[4], e[5], e[6], e[7]), lane, qw, meta);
 }
 
 // the same eight elements from an in-band-flag vector: poll until all eight words carry epoch `ep`
