@@ -371,9 +371,15 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
     ps_mbar_wait(&bar_s, 0);
     {
         float *pp = s_p + hh * stride;
-        const int64_t n_kv = (hh < r2) ? n_kv_all : 0, n8 = (hh < r2) ? n8_all : 0; // template heads beyond r2 (r2 <= R2 query heads per kv head) idle
+        // 32-bit loop counters and 16-byte shared-memory accesses: this kernel is instruction-bound (two warps per scheduler)
+        const int n_kv = (hh < r2) ? (int)n_kv_all : 0, n8 = (hh < r2) ? (int)n8_all : 0; // template heads beyond r2 (r2 <= R2 query heads per kv head) idle
+        const int n4 = n_kv & ~3;
         float mx = -INFINITY;
-        for (int64_t j = ht; j < n_kv; j += TPH) mx = fmaxf(mx, pp[j]);
+        for (int j = 4 * ht; j < n4; j += 4 * TPH) {
+            const float4 x = *reinterpret_cast<const float4 *>(pp + j);
+            mx = fmaxf(fmaxf(mx, fmaxf(x.x, x.y)), fmaxf(x.z, x.w));
+        }
+        for (int j = n4 + ht; j < n_kv; j += TPH) mx = fmaxf(mx, pp[j]);
 #pragma unroll
         for (int o = 16; o; o >>= 1) mx = fmaxf(mx, __shfl_xor_sync(PS_FULL, mx, o));
         if (lane == 0) shf[warp] = mx;
@@ -383,7 +389,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
 #pragma unroll
         for (int t = 1; t < WPH; t++) mx = fmaxf(mx, shf[hh * WPH + t]);
         double s = 0.0;
-        for (int64_t gi = ht; gi < n8 / 8; gi += TPH) {
+        for (int gi = ht; gi < n8 / 8; gi += TPH) {
             float4 *p4 = reinterpret_cast<float4 *>(pp + gi * 8);
             const float4 xa = p4[0], xb = p4[1];
             float vv[8] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
@@ -394,7 +400,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
             const float r0 = __fadd_rn(vv[4], vv[0]), r1 = __fadd_rn(vv[5], vv[1]), r2_ = __fadd_rn(vv[6], vv[2]), r3 = __fadd_rn(vv[7], vv[3]);
             s += (double)__fadd_rn(__fadd_rn(r0, r2_), __fadd_rn(r1, r3));
         }
-        for (int64_t j = n8 + ht; j < n_kv; j += TPH) { // scalar tail: libm expf
+        for (int j = n8 + ht; j < n_kv; j += TPH) { // scalar tail: libm expf
             const float vv = ps_expf_glibc(__fadd_rn(pp[j], -mx));
             pp[j] = vv;
             s += (double)vv;
@@ -408,7 +414,12 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
 #pragma unroll
         for (int t = 1; t < WPH; t++) sum += shd[hh * WPH + t];
         const float inv = (float)(1.0 / sum);
-        for (int64_t j = ht; j < n_kv; j += TPH) pp[j] = __fmul_rn(pp[j], inv);
+        for (int j = 4 * ht; j < n4; j += 4 * TPH) {
+            float4 x = *reinterpret_cast<const float4 *>(pp + j);
+            x.x = __fmul_rn(x.x, inv); x.y = __fmul_rn(x.y, inv); x.z = __fmul_rn(x.z, inv); x.w = __fmul_rn(x.w, inv);
+            *reinterpret_cast<float4 *>(pp + j) = x;
+        }
+        for (int j = n4 + ht; j < n_kv; j += TPH) pp[j] = __fmul_rn(pp[j], inv);
     }
     __syncthreads();
     ps_tl_max(tl, 3);
@@ -426,7 +437,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
             const float *vs = s_v + warp * stride;
             vtail = (lane < ntail) ? vs[np + lane] : 0.f;
 #pragma unroll 8
-            for (int64_t s0 = 0; s0 < np; s0 += 32) { // the FMA chains stay in position order
+            for (int s0 = 0; s0 < (int)np; s0 += 32) { // the FMA chains stay in position order
                 const float v = vs[s0 + lane];
 #pragma unroll
                 for (int h2 = 0; h2 < R2; h2++) sum[h2] = __fmaf_rn(v, s_p[h2 * stride + s0 + lane], sum[h2]);
