@@ -165,4 +165,9 @@ OP_CASES = {"quantize": case_quantize, "matmul": case_matmul, "small": case_smal
 # (gguf-py type name, ggml type id, block elements, rows, blocks per row, seed, scale) for make_golden_gguf_py.py: the
 # reference's Python dequantisers (pinned against libggml by its own gguf-py/tests/test_quants.py) on seeded random blocks
 GGUF_PY_CASES = [("Q4_K", L.Q4_K, 256, 24, 4, 101, 1.0), ("Q4_K", L.Q4_K, 256, 3, 56, 102, 0.02), ("Q6_K", L.Q6_K, 256, 24, 4, 103, 1.0),
-                 ("Q4_0", L.Q4_0, 32, 24, 16, 104, 1.0), ("Q8_0", L.Q8_0, 32, 24, 16, 105, 1.0), ("Q8_0", L.Q8_0, 32, 5, 152, 106, 30.0)]
+                 ("Q4_0", L.Q4_0, 32, 24, 16, 104, 1.0), ("Q8_0", L.Q8_0, 32, 24, 16, 105, 1.0), ("Q8_0", L.Q8_0, 32, 5, 152, 106, 30.0),
+                 ("Q5_K", L.Q5_K, 256, 24, 4, 107, 1.0), ("Q5_K", L.Q5_K, 256, 3, 56, 108, 0.02)]
+# Q5_K dot products (real-file coverage): (K, rows, seed) - golden values from the compiled reference's ggml_vec_dot_q5_K_q8_K
+# (tests/golden/make_golden_q5k.py -> q5k_dot.npz); the reference's DataType layer cannot carry Q5_K, so its operator
+# table is not involved
+Q5K_DOT_CASES = [(256, 9, 201), (256 * 16, 7, 202), (256 * 56, 5, 203)]
