@@ -137,6 +137,7 @@ struct ps_cuda_ctx {
     double kt_ms = 0.0;                 // summed mat-vec kernel time of the last decode call
     int64_t kt_launches = 0;
     uint8_t *rw_out = nullptr; // lm_head, octet-interleaved
+    uint8_t *tc_out = nullptr; // lm_head, fp16-expanded tensor-core operand (batches of 16+ columns that want logits: session batches, verify batches)
     bool fused_ok = false;   // every matmul weight (and the embedding) is Q4_K: the fused decode path applies
     int opt_attn_group = 0;  // opt-in: decode attention as ONE group-synchronised kernel per layer (ps_k_attn_group); bit-exact, but 23 us vs 11.7 us per layer at ctx 2048
     unsigned long long *ag_ctr = nullptr; // [n_layers][n_kv_heads] arrival counters of the kv-head groups
@@ -1780,6 +1781,10 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
                 PS_CK(cudaMemsetAsync(ctx->tc_b, 0, bb, ctx->stream)); // the mins tiles are zero outside each lane's four K positions
                 ctx->tc_b_bytes = bb;
                 ctx->tc_ok = true;
+                if (tp == 1 && a_bytes(vocab_l, dim) + ((size_t)8 << 30) < free_b - per_layer * (size_t)d.n_layers) { // lm_head too (1 GB for the 8B model)
+                    if ((rc = dev_alloc(ctx, (void **)&ctx->tc_out, a_bytes(vocab_l, dim)))) return rc;
+                    if ((rc = tc_expand(ctx, ctx->tc_out, ctx->w_out, vocab_l, dim, 0))) return rc;
+                }
             }
         }
         if ((rc = dev_alloc(ctx, (void **)&ctx->rw_out, oct_bytes(vocab_l, dim, 1)))) return rc;
@@ -1937,7 +1942,10 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
     if (lm_head) {
         ps_k_rmsnorm<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->xn, ctx->x, ctx->w_out_norm, dim, d.norm_eps);
         PS_LAUNCH_CK();
-        if (rw) {
+        if (tc && ctx->tc_out) {
+            if ((rc = tc_prep_b(ctx, ctx->xn, (int)dim, bs))) return rc;
+            if ((rc = tc_single(ctx, ctx->tc_out, d.vocab_size, (int)dim, ctx->logits, bs, nullptr))) return rc;
+        } else if (rw) {
             if ((rc = rwm_quantize(ctx, ctx->xn, (int)dim, bs))) return rc;
             if ((rc = rwm_single(ctx, ctx->rw_out, d.vocab_size, (int)dim, 0, 1, ctx->logits, bs, nullptr, nullptr))) return rc;
         } else {
