@@ -223,7 +223,7 @@ def extra_config0_qwen2(args, hbm_peak):
     return out
 
 
-def extra_sessions(model, shape, hbm_peak, n_sess=32, n_steps=32):
+def extra_sessions(model, shape, hbm_peak, n_sess=64, n_steps=24):
     """Server-side batching on the benchmarked model: n_sess independent sessions (own KV sets, 32-token
     prompts) advanced one token each per forward pass through ps_cuda_forward_sessions - one weight stream per pass, so the
     aggregate rate may exceed the one-sequence HBM roofline.  Device time of the passes; ids come back, logits stay on the device."""

@@ -2313,10 +2313,8 @@ int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const
     ctx->logits_last = ctx->logits;
     ctx->logits_rows = lm_head ? n : 0;
     if (lm_head && greedy_ids) {
-        for (int i = 0; i < n; i++) {
-            ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits + (size_t)i * d.vocab_size, d.vocab_size, ctx->ids_dev + i, ctx->ids_dev + d.max_batch + i);
-            PS_LAUNCH_CK();
-        }
+        ps_k_argmax<<<n, 1024, 0, ctx->stream>>>(ctx->logits, d.vocab_size, ctx->ids_dev, ctx->ids_dev + d.max_batch); // one CTA per column
+        PS_LAUNCH_CK();
         PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
     }
     PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
@@ -2387,10 +2385,8 @@ int ps_cuda_forward_tree(ps_cuda_ctx *ctx, const int32_t *tokens, const int32_t 
     PS_CK(cudaEventRecord(ctx->ev1, ctx->stream));
     ctx->logits_last = ctx->logits;
     if (lm_head == 2) { // greedy ids only (ProbArray + greedy_sample with top_k = 1 per row, first maximum): bs ints come back instead of bs x vocab floats
-        for (int i = 0; i < bs; i++) {
-            ps_k_argmax<<<1, 1024, 0, ctx->stream>>>(ctx->logits + (size_t)i * ctx->d.vocab_size, ctx->d.vocab_size, ctx->ids_dev + i, ctx->ids_dev + 2048 + i);
-            PS_LAUNCH_CK();
-        }
+        ps_k_argmax<<<bs, 1024, 0, ctx->stream>>>(ctx->logits, ctx->d.vocab_size, ctx->ids_dev, ctx->ids_dev + 2048); // one CTA per tree node
+        PS_LAUNCH_CK();
         PS_CK(cudaMemcpyAsync(ctx->h_ids, ctx->ids_dev, (size_t)bs * 4, cudaMemcpyDeviceToHost, ctx->stream));
         if ((rc = sync_and_check(ctx))) return rc;
         memcpy(logits_host, ctx->h_ids, (size_t)bs * 4);

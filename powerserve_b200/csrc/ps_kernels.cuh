@@ -1103,6 +1103,10 @@ __global__ void __launch_bounds__(256) ps_k_topk_stage2(float *__restrict__ cand
 __global__ void __launch_bounds__(1024) ps_k_argmax(const float *__restrict__ logits, int64_t n, int32_t *__restrict__ out, int32_t *__restrict__ next_token) {
     __shared__ float sv[32];
     __shared__ int si[32];
+    // one CTA per logits row (gridDim.x rows: the columns of a session batch); a single row for the decode loop
+    logits += (int64_t)blockIdx.x * n;
+    out += blockIdx.x;
+    next_token += blockIdx.x;
     float best = -INFINITY;
     int bi = 0x7fffffff;
     for (int64_t t = threadIdx.x; t < n; t += blockDim.x) {

@@ -12,12 +12,13 @@ tensors = synth.generate_tensors(shape, 0)
 tmap = {n: gguf.GGUFTensor(n, t, tuple(s), np.ascontiguousarray(d).view(np.uint8).reshape(-1)) for n, t, s, d in tensors}
 desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=128, n_ctx=4096)
 m = capi.CudaModel(desc=desc, tensors=tmap)
-sids = [0] + [m.session_create() for _ in range(63)]
+n_max = max([int(a) for a in sys.argv[3:]] or [64])
+sids = [0] + [m.session_create() for _ in range(n_max - 1)]
 for sid in sids:
     m.session_select(sid); m.reset()
     m.prefill(synth.random_prompt(shape.vocab_size, 33, seed=sid), 32)
 m.session_select(0)
-for n in (1, 2, 4, 8, 15, 16, 32, 64):
+for n in ([int(a) for a in sys.argv[3:]] or [1, 2, 4, 8, 15, 16, 32, 64]):
     toks = [1] * n
     best = 1e9
     for _ in range(4):
