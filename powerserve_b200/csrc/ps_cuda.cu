@@ -123,7 +123,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -653,7 +653,12 @@ template <int C> int launch_rwm_c(ps_cuda_ctx *ctx, PsRwmArgs a) {
     if (fixed + (size_t)PS_RW_WARPS * 2 * (stage + 8) > budget) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "row-walker matmul: K=%d does not fit", a.K);
     a.ns = (int)std::min<size_t>(PS_RW_MAX_NS, (budget - fixed) / ((size_t)PS_RW_WARPS * (stage + 8)));
     const size_t smem = fixed + (size_t)PS_RW_WARPS * a.ns * (stage + 8);
-    const int n_units = ((a.bs + C - 1) / C) * ((a.n_oct + PS_RW_WARPS - 1) / PS_RW_WARPS);
+    // the smallest tile (octets per unit) whose units still fit into one wave of CTAs: fewer walking warps per scheduler
+    const int n_cg = (a.bs + C - 1) / C;
+    int tile = PS_RW_WARPS;
+    while (ctx->opt_rwm_tile && tile > 2 && ((a.n_oct + tile / 2 - 1) / (tile / 2)) * n_cg <= ctx->n_sm) tile >>= 1;
+    a.tile = tile;
+    const int n_units = n_cg * ((a.n_oct + tile - 1) / tile);
     const int grid = std::min(ctx->n_sm, n_units);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
@@ -1891,7 +1896,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
         PS_LAUNCH_CK();
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, tree ? ctx->tree_bias : nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
-        if (bs > 1 && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
+        if (bs >= ctx->opt_pv_batch_min && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
             static bool pv_attr[64] = {};
             if (!pv_attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr[ctx->device] = true; }
             ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
@@ -2613,6 +2618,8 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "rw_ksplit")) ctx->opt_ksplit = value;   // opt-in (default 0): most warps that may share a row octet in the mat-vec launches with few octets per CTA; bit-exact but measured 3-4 % slower per step (profiles/r02_ab_matvec_ksplit_8b_ctx2048.txt)
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
+    else if (!strcmp(name, "rwm_tile")) ctx->opt_rwm_tile = value;       // 1 (default): the multi-column row-walker shrinks its row tile so that narrow batches use every SM; 0: 16-octet tiles
+    else if (!strcmp(name, "pv_batch_min")) ctx->opt_pv_batch_min = value; // batches at least this wide use the query-blocked P.V kernel (prefill), narrower ones the per-(head, dim) warp kernel
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA
     else if (!strcmp(name, "attn_group")) ctx->opt_attn_group = value; // 1: decode attention as one group-synchronised kernel per layer (bit-exact, slower so far: DESIGN.md 5b); 0 (default): scores kernel + soft-max / P.V kernel
     else if (!strcmp(name, "attn_fused")) ctx->opt_attn_fused = value; // 1: decode attention as ONE cluster kernel per layer (bit-exact, but slower so far: DESIGN.md); 0 (default): scores kernel + soft-max / P.V kernel

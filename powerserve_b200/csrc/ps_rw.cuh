@@ -589,6 +589,7 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matvec(const Ps
 struct PsRwmArgs {
     const uint8_t *w;      // repacked weights: [n_oct][nb][n_slots][1184]
     int n_oct, K, kb, ns, n_act;
+    int tile;              // octets per work unit (<= PS_RW_WARPS): warps >= tile idle
     int slot, n_slots;     // which interleaved matrix of the buffer (gate | up)
     PsRwSeg seg[3];        // dst of a segment is [bs][rows of the segment]; mode unused
     int n_seg;
@@ -608,9 +609,11 @@ __global__ void __launch_bounds__(128) ps_k_rw_quant_img(const float *__restrict
     ps_rw_quant_store(e, lane, reinterpret_cast<uint32_t *>(base) + i * 64, reinterpret_cast<uint2 *>(base + K) + i * 4);
 }
 
-// Work decomposition: a UNIT is (tile of PS_RW_WARPS octets = 128 rows, column group of C columns); units are dealt
-// round-robin to the persistent CTAs, and inside a unit warp w owns octet w of the tile, so all warps are busy however
-// few rows the matrix has.  A warp's weight stream is simply the concatenation of its octets over the CTA's units.
+// Work decomposition: a UNIT is (tile of `tile` <= PS_RW_WARPS octets, column group of C columns); units are dealt
+// round-robin to the persistent CTAs, and inside a unit warp w < tile owns octet w of the tile.  The host picks the
+// smallest tile that still fits the units into one wave of CTAs: a narrow batch over a 4096-row matrix then runs 4 walking
+// warps on each of 128 SMs (one per scheduler) instead of 16 on 32 SMs - the walk is issue-bound per scheduler.
+// A warp's weight stream is simply the concatenation of its octets over the CTA's units.
 template <int C>
 __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const PsRwmArgs a) {
     extern __shared__ __align__(128) uint8_t ps_rw_smem[];
@@ -623,13 +626,14 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
     uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + (size_t)PS_RW_WARPS * ns * stage_bytes);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, q = lane & 3;
     const int spo = nb / kb;
-    const int n_cg = (a.bs + C - 1) / C, n_tiles = (a.n_oct + PS_RW_WARPS - 1) / PS_RW_WARPS;
+    const int tile = a.tile;
+    const int n_cg = (a.bs + C - 1) / C, n_tiles = (a.n_oct + tile - 1) / tile;
     const int n_units = n_cg * n_tiles;                            // unit u = (tile u / n_cg, column group u % n_cg)
     const int my_units = (n_units > (int)blockIdx.x) ? (n_units - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     // stage #s of warp w: unit s / spo of this CTA (octets beyond n_oct are skipped by both sides: they own no stages)
     auto issue = [&](int w, int s) {
         const int u = (int)blockIdx.x + (s / spo) * (int)gridDim.x;
-        const int oct = (u / n_cg) * PS_RW_WARPS + w;
+        const int oct = (u / n_cg) * tile + w;
         uint64_t *bar = s_bar + w * ns + (s % ns);
         uint8_t *dst = s_ring + ((size_t)w * ns + (s % ns)) * stage_bytes;
         ps_mbar_expect_tx(bar, stage_bytes);
@@ -641,14 +645,14 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
     };
     const int n_stages = my_units * spo;
     if (warp == PS_RW_WARPS) { // helper warp: barrier init + first ring fill (lane w serves warp w)
-        if (lane < PS_RW_WARPS)
+        if (lane < tile)
             for (int s = 0; s < ns; s++) ps_mbar_init(s_bar + lane * ns + s, 1);
         if (lane == 0) ps_mbar_init(&xbar, 1);
         ps_fence_barrier_init();
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         __syncwarp();
         asm volatile("bar.arrive 1, %0;" ::"n"(PS_RW_THREADS + 32) : "memory");
-        if (lane < PS_RW_WARPS)
+        if (lane < tile)
             for (int s = 0; s < ns && s < n_stages; s++) issue(lane, s);
         return;
     }
@@ -660,14 +664,14 @@ __global__ void __launch_bounds__(PS_RW_THREADS + 32, 1) ps_k_rw_matmul(const Ps
     for (int mu = 0; mu < my_units; mu++) {
         const int u = (int)blockIdx.x + mu * (int)gridDim.x;
         const int col0 = (u % n_cg) * C, ncol = min(C, a.bs - col0);
-        const int oct = (u / n_cg) * PS_RW_WARPS + warp;
+        const int oct = (u / n_cg) * tile + warp;
         ps_bar_sync(2, PS_RW_THREADS); // everyone is done with the previous unit's images
         if (tid == 0) {
             ps_mbar_expect_tx(&xbar, (uint32_t)ncol * img_bytes);
             for (int c = 0; c < ncol; c++) ps_bulk_g2s(s_act + (size_t)c * img_bytes, a.x_img + (size_t)(col0 + c) * img_bytes, img_bytes, &xbar);
         }
         ps_mbar_wait(&xbar, mu & 1);
-        {
+        if (warp < tile) {
             PsRwAcc acc[C];
 #pragma unroll
             for (int c = 0; c < C; c++) acc[c].a0 = acc[c].a1 = acc[c].am = 0.f;
