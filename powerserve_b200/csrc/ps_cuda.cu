@@ -2284,7 +2284,6 @@ int ps_cuda_forward_sessions(ps_cuda_ctx *ctx, const int32_t *session_ids, const
         PS_CK(cudaMallocHost(&ctx->h_sess_ptrs, bytes));
     }
     std::vector<ps_cuda_ctx::KvSet *> sets(n);
-    ps_cuda_ctx::KvSet active; // a view of the selected session's state
     int n_kv_max = 0;
     for (int i = 0; i < n; i++) {
         if (tokens[i] < 0 || tokens[i] >= d.vocab_size) return fail(ctx, PS_CUDA_ERR_INVALID, "forward_sessions: token %d outside the vocabulary", tokens[i]);
@@ -2487,7 +2486,7 @@ int ps_cuda_decode_greedy(ps_cuda_ctx *ctx, int32_t first_token, int n_steps, in
 // logits by ascending token id), as (logit, token) pairs - what ProbArray holds after TopKSampler::apply.
 int ps_cuda_sample_topk(ps_cuda_ctx *ctx, int row, int k, float *logits_out, int32_t *tokens_out) {
     std::lock_guard<std::mutex> lock(ctx->mu);
-    const int vocab = ctx->tp > 1 && ctx->logits_last == ctx->logits ? ctx->d.vocab_size : ctx->d.vocab_size;
+    const int vocab = ctx->d.vocab_size;
     if (k <= 0 || k > PS_TOPK_MAX || k > vocab) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: k = %d outside [1,%d]", k, std::min(PS_TOPK_MAX, vocab));
     if (!ctx->logits_last || row < 0 || row >= std::max(ctx->logits_rows, 1)) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: no logits row %d", row);
     if (!logits_out || !tokens_out) return fail(ctx, PS_CUDA_ERR_INVALID, "sample_topk: null output");
