@@ -123,7 +123,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -773,7 +773,14 @@ int launch_mv(ps_cuda_ctx *ctx, PsMvArgs a) {
     a.inv_k = 1.0 / (double)a.K;
     if ((double)a.K * a.inv_k != 1.0) a.inv_k = 0.0; // only exact reciprocals replace the division (power-of-two K)
     const size_t act = ((size_t)a.K + (size_t)nb * 4 + 127) & ~(size_t)127;
-    const size_t smem = act + (size_t)PS_MV_WARPS * a.ns * ((size_t)sb * blk + 8);
+    size_t smem = act + (size_t)PS_MV_WARPS * a.ns * ((size_t)sb * blk + 8);
+    // block-parallel mode (ps_mv32.cuh): at most one octet per CTA and a long row - the CTA's eight warps share the row's blocks
+    a.kpar = 0;
+    if (ctx->opt_mv_kpar && per_cta == 1 && nb >= 16 && !a.part_val) {
+        const size_t slice = ((size_t)((nb + PS_MV_WARPS - 1) / PS_MV_WARPS) * blk + 127) & ~(size_t)127;
+        const size_t need = act + (size_t)PS_MV_WARPS * slice + (size_t)nb * 96 * 4 + PS_MV_WARPS * 8;
+        if (need <= 200 * 1024) { a.kpar = (int)slice; smem = need; }
+    }
     if (smem > 200 * 1024) return fail(ctx, PS_CUDA_ERR_UNSUPPORTED, "32-block mat-vec: K = %d does not fit shared memory", a.K);
     static bool attr[64] = {};
     if (!attr[ctx->device]) {
@@ -2617,6 +2624,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "pdl")) ctx->opt_pdl = value;
     else if (!strcmp(name, "rw_ksplit")) ctx->opt_ksplit = value;   // opt-in (default 0): most warps that may share a row octet in the mat-vec launches with few octets per CTA; bit-exact but measured 3-4 % slower per step (profiles/r02_ab_matvec_ksplit_8b_ctx2048.txt)
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
+    else if (!strcmp(name, "mv_kpar")) ctx->opt_mv_kpar = value;         // 1 (default): 32-block mat-vec launches with one octet per CTA and long rows share the row's blocks among the CTA's warps
     else if (!strcmp(name, "rwm_tile")) ctx->opt_rwm_tile = value;       // 1 (default): the multi-column row-walker shrinks its row tile so that narrow batches use every SM; 0: 16-octet tiles
     else if (!strcmp(name, "pv_batch_min")) ctx->opt_pv_batch_min = value; // batches at least this wide use the query-blocked P.V kernel (prefill), narrower ones the per-(head, dim) warp kernel
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA

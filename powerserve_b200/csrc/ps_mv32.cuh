@@ -51,6 +51,7 @@ enum { PS_MV_PRO_PLAIN = 0, PS_MV_PRO_RMSNORM = 1, PS_MV_PRO_SILU = 2 };
 struct PsMvArgs {
     const uint8_t *w;      // [n_oct][nb][BLK]
     int n_oct, K, sb, ns;  // sb = blocks per ring stage (divides nb), ns = ring stages per warp
+    int kpar;              // block-parallel mode (one octet per CTA, long rows): slice capacity in bytes per warp, 0 = off
     const float *x;        // activation vector (PRO_SILU: the gate vector)
     const float *x2;       // PRO_SILU: the up vector
     const float *norm_w;   // PRO_RMSNORM
@@ -78,46 +79,9 @@ PS_D void ps_mv_quant4(const float4 v, uint32_t &word, float &d_out) {
     d_out = __half2float(__float2half_rn(d));
 }
 
-// Dynamic shared memory: [s_qs: K bytes][s_d: nb floats, padded to 128][rings: 8 warps x ns x stage_bytes][bars: 8 x ns x 8]
-template <int TYPE>
-__global__ void __launch_bounds__(PS_MV_THREADS) ps_k_mv32(const PsMvArgs a) {
-    using G = PsMv32<TYPE>;
-    extern __shared__ __align__(128) uint8_t ps_mv_smem[];
-    __shared__ double sh_red[PS_MV_WARPS];
-    __shared__ float sv[PS_MV_WARPS];
-    __shared__ int si[PS_MV_WARPS];
-    const int K = a.K, nb = K / 32, sb = a.sb, ns = a.ns;
-    const uint32_t stage_bytes = (uint32_t)sb * G::BLK;
-    uint32_t *s_qs = reinterpret_cast<uint32_t *>(ps_mv_smem);
-    float *s_d = reinterpret_cast<float *>(ps_mv_smem + K);
-    uint8_t *s_ring = ps_mv_smem + (((size_t)K + (size_t)nb * 4 + 127) & ~(size_t)127);
-    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + (size_t)PS_MV_WARPS * ns * stage_bytes);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, t = lane & 3;
-    const int o0 = (int)(((long long)blockIdx.x * a.n_oct) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.n_oct) / gridDim.x);
-    const int spo = nb / sb; // stages per octet
-    const int n_mine = (o0 + warp < o1) ? (o1 - o0 - warp - 1) / PS_MV_WARPS + 1 : 0;
-    const int n_stages = n_mine * spo;
-    uint8_t *my_ring = s_ring + (size_t)warp * ns * stage_bytes;
-    uint64_t *my_bar = s_bar + warp * ns;
-    auto issue = [&](int s) { // lane 0: request stage #s of this warp's stream into slot s % ns
-        const int oct = o0 + warp + (s / spo) * PS_MV_WARPS;
-        const uint8_t *src = a.w + ((size_t)oct * nb + (size_t)(s % spo) * sb) * G::BLK;
-        uint64_t *bar = my_bar + (s % ns);
-        ps_mbar_expect_tx(bar, stage_bytes);
-        ps_bulk_g2s(my_ring + (size_t)(s % ns) * stage_bytes, src, stage_bytes, bar);
-    };
-    // every warp runs its own ring: barriers are warp-private, so no CTA-wide synchronisation guards them
-    if (lane == 0) {
-        for (int s = 0; s < ns; s++) ps_mbar_init(my_bar + s, 1);
-        ps_fence_barrier_init();
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = 0; s < ns && s < n_stages; s++) issue(s);
-    }
-    __syncwarp();
-    ps_grid_dep_wait();
-    ps_grid_dep_launch();
-
-    // ---- prologue: (RMSNorm | SiLU.up) + quantize_row_q8_0 of the activation vector into shared memory
+// prologue of every launch: (RMSNorm | SiLU.up) + quantize_row_q8_0 of the activation vector into shared memory (all eight warps;
+// ends with a CTA barrier)
+PS_D void ps_mv_prologue(const PsMvArgs &a, uint32_t *s_qs, float *s_d, double *sh_red, int K, int nb, int tid, int warp, int lane) {
     float nscale = 1.f;
     if (a.pro == PS_MV_PRO_RMSNORM) {
         double ss = 0.0;
@@ -168,6 +132,141 @@ __global__ void __launch_bounds__(PS_MV_THREADS) ps_k_mv32(const PsMvArgs a) {
     }
     __syncthreads();
 
+}
+
+// epilogue of one octet: hsum_float_8 across the row's four threads, bias / residual, store, running arg-max
+PS_D void ps_mv_epilogue(const PsMvArgs &a, int oct, int r, int t, float a_lo, float a_hi, float &best_v, int &best_i) {
+    // hsum_float_8 (ggml-quants.c:62-68): (x4 + x0, x5 + x1, x6 + x2, x7 + x3) -> (r0 + r2) + (r1 + r3)
+    float res = __fadd_rn(a_hi, a_lo);
+    res = __fadd_rn(res, __shfl_xor_sync(PS_FULL, res, 2));
+    res = __fadd_rn(res, __shfl_xor_sync(PS_FULL, res, 1));
+    const int row = oct * 8 + r;
+    int sg = 0;
+    if (a.n_seg > 1 && row >= a.seg[1].row_begin) sg = 1;
+    if (a.n_seg > 2 && row >= a.seg[2].row_begin) sg = 2;
+    if (t == 0 && row < a.seg[sg].row_end) {
+        const int n = row - a.seg[sg].row_begin;
+        if (a.seg[sg].bias) res = __fadd_rn(res, a.seg[sg].bias[n]);
+        if (a.residual) res = __fadd_rn(a.residual[n], res);
+        a.seg[sg].dst[n] = res;
+        if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
+    }
+}
+
+// Dynamic shared memory: [s_qs: K bytes][s_d: nb floats, padded to 128][rings: 8 warps x ns x stage_bytes][bars: 8 x ns x 8]
+//
+// Block-parallel mode (a.kpar > 0; matrices with at most one octet per CTA and long rows, e.g. Qwen2's down projection:
+// 112 octets of 152 blocks): a lone warp would walk the whole row serially, so the row's blocks are dealt to the CTA's eight
+// warps instead.  Each warp streams its slice with one bulk copy, does the INTEGER work of its blocks and leaves, per block and
+// lane, the three numbers the chains need - fl(d_x d_y), float(S_lo), float(S_hi), all exact - in shared memory; after one CTA
+// barrier warp 0 advances the two FMA chains over all blocks IN ROW ORDER (the arithmetic of the one-warp walk) and runs
+// the epilogue.  Shared memory: [s_qs][s_d][slices: 8 x kpar bytes][factors: nb x 3 x 32 floats][bars: 8 x 8].
+template <int TYPE>
+__global__ void __launch_bounds__(PS_MV_THREADS) ps_k_mv32(const PsMvArgs a) {
+    using G = PsMv32<TYPE>;
+    extern __shared__ __align__(128) uint8_t ps_mv_smem[];
+    __shared__ double sh_red[PS_MV_WARPS];
+    __shared__ float sv[PS_MV_WARPS];
+    __shared__ int si[PS_MV_WARPS];
+    const int K = a.K, nb = K / 32, sb = a.sb, ns = a.ns;
+    const uint32_t stage_bytes = (uint32_t)sb * G::BLK;
+    uint32_t *s_qs = reinterpret_cast<uint32_t *>(ps_mv_smem);
+    float *s_d = reinterpret_cast<float *>(ps_mv_smem + K);
+    uint8_t *s_ring = ps_mv_smem + (((size_t)K + (size_t)nb * 4 + 127) & ~(size_t)127);
+    uint64_t *s_bar = reinterpret_cast<uint64_t *>(s_ring + (size_t)PS_MV_WARPS * ns * stage_bytes);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, r = lane >> 2, t = lane & 3;
+    const int o0 = (int)(((long long)blockIdx.x * a.n_oct) / gridDim.x), o1 = (int)(((long long)(blockIdx.x + 1) * a.n_oct) / gridDim.x);
+    const int spo = nb / sb; // stages per octet
+    const int n_mine = (o0 + warp < o1) ? (o1 - o0 - warp - 1) / PS_MV_WARPS + 1 : 0;
+    const int n_stages = n_mine * spo;
+    if (a.kpar) { // ---- block-parallel mode (see above)
+        uint8_t *slice = s_ring + (size_t)warp * a.kpar;
+        float *s_fac = reinterpret_cast<float *>(s_ring + (size_t)PS_MV_WARPS * a.kpar);
+        uint64_t *bar = reinterpret_cast<uint64_t *>(s_fac + (size_t)nb * 96) + warp;
+        const bool own = o0 < o1;                                       // CTAs beyond the octet count only take part in the dependency chain
+        const int b_lo = nb * warp / PS_MV_WARPS, b_hi = nb * (warp + 1) / PS_MV_WARPS;
+        if (lane == 0) {
+            ps_mbar_init(bar, 1);
+            ps_fence_barrier_init();
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            if (own && b_hi > b_lo) {
+                const uint32_t bytes = (uint32_t)(b_hi - b_lo) * G::BLK;
+                ps_mbar_expect_tx(bar, bytes);
+                ps_bulk_g2s(slice, a.w + ((size_t)o0 * nb + b_lo) * G::BLK, bytes, bar);
+            }
+        }
+        __syncwarp();
+        ps_grid_dep_wait();
+        ps_grid_dep_launch();
+        ps_mv_prologue(a, s_qs, s_d, sh_red, K, nb, tid, warp, lane);
+        if (!own) return;
+        if (b_hi > b_lo) ps_mbar_wait(bar, 0);
+        for (int i = b_lo; i < b_hi; i++) {
+            const uint8_t *blk = slice + (size_t)(i - b_lo) * G::BLK;
+            int S_lo, S_hi;
+            if (TYPE == 2) {
+                const uint32_t w = *reinterpret_cast<const uint32_t *>(blk + r * 16 + 4 * t);
+                const uint32_t lo = __vsub4(w & 0x0f0f0f0fu, 0x08080808u), hi = __vsub4((w >> 4) & 0x0f0f0f0fu, 0x08080808u);
+                S_lo = __dp4a((int)lo, (int)s_qs[i * 8 + t], 0);
+                S_hi = __dp4a((int)hi, (int)s_qs[i * 8 + 4 + t], 0);
+            } else {
+                const uint32_t w0 = *reinterpret_cast<const uint32_t *>(blk + r * 32 + 4 * t);
+                const uint32_t w1 = *reinterpret_cast<const uint32_t *>(blk + r * 32 + 16 + 4 * t);
+                S_lo = __dp4a((int)w0, (int)s_qs[i * 8 + t], 0);
+                S_hi = __dp4a((int)w1, (int)s_qs[i * 8 + 4 + t], 0);
+            }
+            const float xd = ps_half_bits_to_float(*reinterpret_cast<const unsigned short *>(blk + 8 * G::QB + 2 * r));
+            float *f = s_fac + (size_t)i * 96 + lane;
+            f[0] = __fmul_rn(xd, s_d[i]);
+            f[32] = __int2float_rn(S_lo);
+            f[64] = __int2float_rn(S_hi);
+        }
+        __syncthreads();
+        if (warp != 0) return;
+        float a_lo = 0.f, a_hi = 0.f;
+#pragma unroll 4
+        for (int i = 0; i < nb; i++) { // the two chains of this thread's AVX lanes, block by block in row order
+            const float *f = s_fac + (size_t)i * 96 + lane;
+            const float d = f[0];
+            a_lo = __fmaf_rn(d, f[32], a_lo);
+            a_hi = __fmaf_rn(d, f[64], a_hi);
+        }
+        float best_v = -INFINITY;
+        int best_i = 0x7fffffff;
+        ps_mv_epilogue(a, o0, r, t, a_lo, a_hi, best_v, best_i);
+        if (a.part_val) {
+#pragma unroll
+            for (int o = 16; o; o >>= 1) {
+                const float ov = __shfl_xor_sync(PS_FULL, best_v, o);
+                const int oi = __shfl_xor_sync(PS_FULL, best_i, o);
+                if (ov > best_v || (ov == best_v && oi < best_i)) { best_v = ov; best_i = oi; }
+            }
+            if (lane == 0) { a.part_val[blockIdx.x] = best_v; a.part_idx[blockIdx.x] = best_i; }
+        }
+        return;
+    }
+    uint8_t *my_ring = s_ring + (size_t)warp * ns * stage_bytes;
+    uint64_t *my_bar = s_bar + warp * ns;
+    auto issue = [&](int s) { // lane 0: request stage #s of this warp's stream into slot s % ns
+        const int oct = o0 + warp + (s / spo) * PS_MV_WARPS;
+        const uint8_t *src = a.w + ((size_t)oct * nb + (size_t)(s % spo) * sb) * G::BLK;
+        uint64_t *bar = my_bar + (s % ns);
+        ps_mbar_expect_tx(bar, stage_bytes);
+        ps_bulk_g2s(my_ring + (size_t)(s % ns) * stage_bytes, src, stage_bytes, bar);
+    };
+    // every warp runs its own ring: barriers are warp-private, so no CTA-wide synchronisation guards them
+    if (lane == 0) {
+        for (int s = 0; s < ns; s++) ps_mbar_init(my_bar + s, 1);
+        ps_fence_barrier_init();
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        for (int s = 0; s < ns && s < n_stages; s++) issue(s);
+    }
+    __syncwarp();
+    ps_grid_dep_wait();
+    ps_grid_dep_launch();
+
+    ps_mv_prologue(a, s_qs, s_d, sh_red, K, nb, tid, warp, lane);
+
     // ---- the stream
     float best_v = -INFINITY;
     int best_i = 0x7fffffff;
@@ -207,21 +306,7 @@ __global__ void __launch_bounds__(PS_MV_THREADS) ps_k_mv32(const PsMvArgs a) {
             if (lane == 0 && s + ns < n_stages) issue(s + ns);
             if (++slot == ns) { slot = 0; phase ^= 1; }
         }
-        // hsum_float_8 (ggml-quants.c:62-68): (x4 + x0, x5 + x1, x6 + x2, x7 + x3) -> (r0 + r2) + (r1 + r3)
-        float res = __fadd_rn(a_hi, a_lo);
-        res = __fadd_rn(res, __shfl_xor_sync(PS_FULL, res, 2));
-        res = __fadd_rn(res, __shfl_xor_sync(PS_FULL, res, 1));
-        const int row = oct * 8 + r;
-        int sg = 0;
-        if (a.n_seg > 1 && row >= a.seg[1].row_begin) sg = 1;
-        if (a.n_seg > 2 && row >= a.seg[2].row_begin) sg = 2;
-        if (t == 0 && row < a.seg[sg].row_end) {
-            const int n = row - a.seg[sg].row_begin;
-            if (a.seg[sg].bias) res = __fadd_rn(res, a.seg[sg].bias[n]);
-            if (a.residual) res = __fadd_rn(a.residual[n], res);
-            a.seg[sg].dst[n] = res;
-            if (res > best_v || (res == best_v && n < best_i)) { best_v = res; best_i = n; } // first maximum wins
-        }
+        ps_mv_epilogue(a, oct, r, t, a_lo, a_hi, best_v, best_i);
     }
     if (a.part_val) { // greedy pick, stage 1: the CTA's best (value, lowest index)
 #pragma unroll

@@ -148,6 +148,11 @@ def test_graph_replayed_operator_table_step_for_every_weight_type(preset):
         L.assert_bit_equal(lg_m, lg_u, f"{preset}: fused 32-block step vs table ops")
         ids_p, lg_p = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1)
         L.assert_bit_equal(lg_p, lg_u, f"{preset}: fused 32-block step, PDL + graph, vs table ops")
+        cm.be.set_option("mv_kpar", 0)      # without the block-parallel mode of the launches with one octet per CTA and long rows
+        ids_k, lg_k = run(cm, prompt, n_dec, fused=1, graph=1, pdl=1)
+        cm.be.set_option("mv_kpar", 1)
+        L.assert_bit_equal(lg_k, lg_u, f"{preset}: fused 32-block step without block-parallel launches vs table ops")
+        assert ids_k == ids_u
         cm.reset(); cm.prefill(prompt, 16)
         ids_l = list(cm.decode_greedy(int(prompt[-1]), n_dec))
         assert ids_m == ids_p == ids_l == ids_u

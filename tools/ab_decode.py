@@ -32,7 +32,7 @@ for spec in sets:
     for k in defaults:
         m.be.set_option(k, defaults[k])
     for k, v in opts.items():
-        defaults.setdefault(k, {"rw_ksplit": 0, "rw_defer": 0, "rw_unroll2": 1, "pdl": 1, "graph": 1, "rw_kb": 0, "ops_graph": 1, "attn_group": 0}.get(k, 0))
+        defaults.setdefault(k, {"rw_ksplit": 0, "rw_defer": 0, "rw_unroll2": 1, "pdl": 1, "graph": 1, "rw_kb": 0, "ops_graph": 1, "attn_group": 0, "mv_kpar": 1}.get(k, 0))
         m.be.set_option(k, int(v))
     m.be.kv_truncate(base_pos)
     ids = m.decode_greedy(1, 8)           # capture + warm-up; ids and logits are the parity sample
