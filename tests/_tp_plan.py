@@ -1,4 +1,5 @@
-"""Tensor-parallel sharding plan (host-side mirror of what `ps_cuda_bind_model` does for a context with tp_size > 1).
+"""Test support: tensor-parallel sharding plan (host-side mirror of what `ps_cuda_bind_model` does for a context with tp_size > 1;
+used by the gloo tests of the sharding logic, not by the product).
 
 Every matrix is ROW-sharded — rank r owns rows [r * rows / N, (r + 1) * rows / N) of W{K, rows} — so each output element
 is still one full-K dot product and the sharded model is bit-identical to the unsharded one; the sharded outputs are
@@ -10,7 +11,7 @@ from __future__ import annotations
 
 from typing import Dict, Tuple
 
-from . import gguf
+from powerserve_b200 import gguf
 
 ROW_SHARDED = ("attn_q.weight", "attn_k.weight", "attn_v.weight", "attn_output.weight", "ffn_gate.weight", "ffn_up.weight",
                "ffn_down.weight", "attn_q.bias", "attn_k.bias", "attn_v.bias")
@@ -41,4 +42,5 @@ def shard_tensor(name: str, t: gguf.GGUFTensor, rank: int, size: int, lm_head: b
 
 
 def gathers_per_token(n_layers: int, pick: bool = True) -> int:
-    return 4 * n_layers + (1 if pick else 1)
+    """exchanges of one decoded token: four per layer + one per token (the arg-max partials, or the logits)"""
+    return 4 * n_layers + 1

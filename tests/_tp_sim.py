@@ -8,7 +8,8 @@ import os
 
 import numpy as np
 
-from powerserve_b200 import gguf, tp
+from powerserve_b200 import gguf
+from tests import _tp_plan as tp
 from tests import _libs as L
 
 

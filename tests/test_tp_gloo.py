@@ -11,7 +11,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from powerserve_b200 import gguf, synth, tp
+from powerserve_b200 import gguf, synth
+from tests import _tp_plan as tp
 from tests import _libs as L
 from tests import _model as M
 
