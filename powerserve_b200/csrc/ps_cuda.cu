@@ -123,7 +123,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1, opt_attn_tile = 1;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -1826,6 +1826,44 @@ int ps_cuda_bind_model(ps_cuda_ctx *ctx, const ps_cuda_model_weights *w) {
 // `tree_base` >= 0: a tree batch (ps_cuda_forward_tree) - K / V rows go to cache SLOTS tree_base .. tree_base + bs - 1 whatever the
 // token positions are, and the attention bias is ctx->tree_bias (slot mask + in-batch tree mask) instead of the causal `pos` mask.
 struct SessRun { int n_kv_max; };
+// Scores and P.V of a batch over one cache (prefill chunk, verify batch): register-tiled kernels (option attn_tile, on
+// by default), else the round-1 kernels; narrow batches use the per-position / per-(head, dim) warp kernels.  nh / nkv
+// are the heads THIS rank owns.  The caller checks the launch (PS_LAUNCH_CK) after launch_batch_scores.
+static void launch_batch_scores(ps_cuda_ctx *ctx, int L, int nh, int nkv, int hs, int64_t n_kv, int bs) {
+    if (bs >= 8) {
+        const int r2 = nh / nkv;
+        const int qb = std::max(1, std::min(bs, 8192 / (r2 * hs)));
+        const dim3 grid((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb));
+        const size_t smem = (size_t)qb * r2 * hs * 4;
+        if (ctx->opt_attn_tile && hs == 128) ps_k_attn_scores_tile<4><<<grid, 128, smem, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, nh, nkv, n_kv, bs, qb);
+        else if (ctx->opt_attn_tile && hs == 64) ps_k_attn_scores_tile<2><<<grid, 128, smem, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, nh, nkv, n_kv, bs, qb);
+        else if (ctx->opt_attn_tile && hs == 32) ps_k_attn_scores_tile<1><<<grid, 128, smem, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, nh, nkv, n_kv, bs, qb);
+        else if (ctx->opt_attn_tile && hs == 256) ps_k_attn_scores_tile<8><<<grid, 128, smem, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, nh, nkv, n_kv, bs, qb);
+        else ps_k_attn_scores_batch<<<grid, 128, (size_t)qb * r2 * hs * 4, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, hs, nh, nkv, n_kv, bs, qb);
+    } else {
+        ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, hs, nh, nkv, n_kv, bs);
+    }
+}
+static int launch_batch_pv(ps_cuda_ctx *ctx, int L, int nh, int nkv, int hs, int64_t n_kv, int bs, int batch_min) {
+    const int64_t n_ctx = ctx->d.n_ctx;
+    if (bs >= batch_min && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
+        static bool pv_attr[64] = {};
+        if (!pv_attr[ctx->device]) {
+            PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+            pv_attr[ctx->device] = true;
+        }
+        const dim3 grid((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh);
+        static_assert(PS_PV_QB == PS_PVT_Q, "both P.V kernels block the queries by 8");
+        if (ctx->opt_attn_tile && hs % PS_PVT_D == 0) ps_k_attn_pv_tile<<<grid, 256, (size_t)PS_PVT_Q * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
+        else ps_k_attn_pv_batch<<<grid, 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
+    } else {
+        ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
+    }
+    PS_LAUNCH_CK();
+    return 0;
+}
+
 static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree_base = -1, const SessRun *sess = nullptr) {
     const ps_cuda_model_desc &d = ctx->d;
     const int64_t dim = d.dim, hs = d.head_size, nh = d.n_heads, nkv = d.n_kv_heads, kvd = hs * nkv, qdim = nh * hs, ffn = d.ffn_dim;
@@ -1892,25 +1930,11 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
             ps_k_sess_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv, (unsigned)bs), 128, 0, ctx->stream>>>(ctx->att, pl + d.max_batch, ctx->kq, (int)hs, (int)nh, (int)nkv, ctx->pos_dev, d.n_ctx, cs);
             PS_LAUNCH_CK();
         } else {
-        if (bs >= 8) {
-            const int r2 = (int)(nh / nkv);
-            const int qb = std::max(1, std::min(bs, (int)(8192 / (r2 * hs))));
-            ps_k_attn_scores_batch<<<dim3((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb)), 128, (size_t)qb * r2 * hs * 4, ctx->stream>>>(
-                ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs, qb);
-        } else {
-            ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
-        }
+        launch_batch_scores(ctx, L, (int)nh, (int)nkv, (int)hs, n_kv, bs);
         PS_LAUNCH_CK();
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, tree ? ctx->tree_bias : nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
-        if (bs >= ctx->opt_pv_batch_min && (size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
-            static bool pv_attr[64] = {};
-            if (!pv_attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr[ctx->device] = true; }
-            ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
-                ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
-        } else {
-            ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
-        }
+        if ((rc = launch_batch_pv(ctx, L, (int)nh, (int)nkv, (int)hs, n_kv, bs, ctx->opt_pv_batch_min))) return rc;
         PS_LAUNCH_CK();
         }
         if (tc) {
@@ -2041,25 +2065,11 @@ static int forward_ops_tp(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
         PS_LAUNCH_CK();
         ps_k_kv_store<<<grid1d(kvd * bs), 256, 0, ctx->stream>>>(ctx->kc[L], ctx->vct[L], ctx->kr, ctx->v, kvd, d.n_ctx, ctx->pos_dev, bs);
         PS_LAUNCH_CK();
-        if (bs >= 8) {
-            const int r2 = (int)(nh / nkv);
-            const int qb = std::max(1, std::min(bs, (int)(8192 / (r2 * hs))));
-            ps_k_attn_scores_batch<<<dim3((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb)), 128, (size_t)qb * r2 * hs * 4, ctx->stream>>>(
-                ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs, qb);
-        } else {
-            ps_k_attn_scores<<<dim3((unsigned)((n_kv + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->kq, ctx->kc[L], ctx->qr, (int)hs, (int)nh, (int)nkv, n_kv, bs);
-        }
+        launch_batch_scores(ctx, L, (int)nh, (int)nkv, (int)hs, n_kv, bs);
         PS_LAUNCH_CK();
         ps_k_softmax_ext<<<(unsigned)(bs * nh), 256, (size_t)n_kv * 4, ctx->stream>>>(ctx->kq, ctx->kq, nullptr, ctx->pos_dev, n_kv, bs, kq_scale);
         PS_LAUNCH_CK();
-        if ((size_t)PS_PV_QB * n_kv * 4 <= 200 * 1024) {
-            static bool pv_attr[64] = {};
-            if (!pv_attr[ctx->device]) { PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_batch, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); pv_attr[ctx->device] = true; }
-            ps_k_attn_pv_batch<<<dim3((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh), 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(
-                ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
-        } else {
-            ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, (int)hs, (int)nh, (int)nkv, n_kv, d.n_ctx, bs);
-        }
+        if ((rc = launch_batch_pv(ctx, L, (int)nh, (int)nkv, (int)hs, n_kv, bs, 0))) return rc;
         PS_LAUNCH_CK();
         if ((rc = tp_gather_rows(ctx, attb, ctx->att, bs, qdim_l))) return rc;                      // exchange 1: attention output
         if (tc) {
@@ -2626,6 +2636,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
     else if (!strcmp(name, "mv_kpar")) ctx->opt_mv_kpar = value;         // 1 (default): 32-block mat-vec launches with one octet per CTA and long rows share the row's blocks among the CTA's warps
     else if (!strcmp(name, "rwm_tile")) ctx->opt_rwm_tile = value;       // 1 (default): the multi-column row-walker shrinks its row tile so that narrow batches use every SM; 0: 16-octet tiles
+    else if (!strcmp(name, "attn_tile")) ctx->opt_attn_tile = value; // register-tiled scores / P.V kernels for batches (0: the round-1 kernels, for A/B)
     else if (!strcmp(name, "pv_batch_min")) ctx->opt_pv_batch_min = value; // batches at least this wide use the query-blocked P.V kernel (prefill), narrower ones the per-(head, dim) warp kernel
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA
     else if (!strcmp(name, "attn_group")) ctx->opt_attn_group = value; // 1: decode attention as one group-synchronised kernel per layer (bit-exact, slower so far: DESIGN.md 5b); 0 (default): scores kernel + soft-max / P.V kernel

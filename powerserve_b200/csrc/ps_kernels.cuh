@@ -863,6 +863,173 @@ __global__ void __launch_bounds__(256) ps_k_attn_pv_batch(float *__restrict__ ou
     }
 }
 
+// Register-tiled variants of the two batched attention kernels (prefill chunks, verify batches).  The arithmetic of
+// every dot product is that of ps_k_attn_scores_batch / ps_k_attn_pv_batch - ggml_vec_dot_f32 lane chains
+// (ggml.c:2092-2131), GGML_F32x8_REDUCE order 16, 8, 4, 1, 2 - only the data movement differs:
+//  * the 32-lane reductions run as a reduce-scatter: at every butterfly stage a lane keeps half of its sums and hands
+//    the other half to its partner, so 8 sums cost 4 + 2 + 1 + 1 + 1 shuffles instead of 40 (a + b == b + a, so the value
+//    a lane ends up with is the one the full butterfly leaves in it);
+//  * the scores kernel lets lane code c = lane >> 2 hold cache row (t ^ c) in register slot t, which makes the kept
+//    half "slots 0..n/2" on every lane - no selects;
+//  * the P.V kernel gives a warp an 8 (output dims) x 8 (queries) accumulator tile, so every probability read from
+//    shared memory and every V^T element read from L2 feeds 8 FMAs instead of 1 (the old kernel issued one
+//    shared-memory load per FMA and was bound by that pipe at ~16 % of the FMA rate).
+template <int STEPS> // head size / 32: the loops below carry no run-time predicates
+__global__ void __launch_bounds__(128) ps_k_attn_scores_tile(float *__restrict__ kq, const float *__restrict__ kc, const float *__restrict__ q,
+                                                             int n_heads, int n_kv_heads, int64_t n_kv, int bs, int qb) {
+    extern __shared__ float s_qb[]; // [qb * r2][hs]
+    constexpr int hs = 32 * STEPS;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, c = lane >> 2;
+    const int g = blockIdx.y, r2 = n_heads / n_kv_heads;
+    const int64_t j0 = (int64_t)blockIdx.x * 32 + warp * 8;
+    float kv[8][STEPS];
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const bool in = j0 + (t ^ c) < n_kv;
+        const float *kr = kc + (j0 + (t ^ c)) * (int64_t)(hs * n_kv_heads) + g * hs + lane;
+#pragma unroll
+        for (int s = 0; s < STEPS; s++) kv[t][s] = in ? kr[32 * s] : 0.f;
+    }
+    const int i0 = blockIdx.z * qb;
+    const int nq = min(qb, bs - i0);
+    const int chunk4 = r2 * hs / 4; // float4s per query: the r2 heads of a group are adjacent in q
+    for (int idx = tid; idx < nq * chunk4; idx += 128) {
+        const int qi = idx / chunk4, e = idx % chunk4;
+        reinterpret_cast<float4 *>(s_qb)[idx] = reinterpret_cast<const float4 *>(q + ((int64_t)(i0 + qi) * n_heads + g * r2) * hs)[e];
+    }
+    __syncthreads();
+    const bool writer = (lane & 3) == 0 && j0 + c < n_kv; // slot 0 of lane code c ends up as cache row j0 + c
+    const float *sq = s_qb + lane;
+    for (int hh = 0; hh < r2; hh++) {
+        float *dst = kq + ((int64_t)(g * r2 + hh) * bs + i0) * n_kv + j0 + c;
+#pragma unroll 2
+        for (int qi = 0; qi < nq; qi++) {
+            const float *qp = sq + (qi * r2 + hh) * hs;
+            float qe[STEPS];
+#pragma unroll
+            for (int s = 0; s < STEPS; s++) qe[s] = qp[32 * s];
+            float sum[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+                sum[t] = 0.f;
+#pragma unroll
+                for (int s = 0; s < STEPS; s++) sum[t] = __fmaf_rn(kv[t][s], qe[s], sum[t]);
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) sum[t] = __fadd_rn(sum[t], __shfl_xor_sync(PS_FULL, sum[t + 4], 16));
+#pragma unroll
+            for (int t = 0; t < 2; t++) sum[t] = __fadd_rn(sum[t], __shfl_xor_sync(PS_FULL, sum[t + 2], 8));
+            sum[0] = __fadd_rn(sum[0], __shfl_xor_sync(PS_FULL, sum[1], 4));
+            sum[0] = __fadd_rn(sum[0], __shfl_xor_sync(PS_FULL, sum[0], 1));
+            sum[0] = __fadd_rn(sum[0], __shfl_xor_sync(PS_FULL, sum[0], 2));
+            if (writer) dst[(int64_t)qi * n_kv] = sum[0];
+        }
+    }
+}
+
+// one reduce-scatter stage over N sums: the lane whose `up` bit is set keeps the upper half, the other the lower half
+template <int N>
+PS_D void ps_rs_stage(float (&a)[N], bool up, int mask) {
+#pragma unroll
+    for (int i = 0; i < N / 2; i++) {
+        const float keep = up ? a[i + N / 2] : a[i], send = up ? a[i] : a[i + N / 2];
+        a[i] = __fadd_rn(keep, __shfl_xor_sync(PS_FULL, send, mask));
+    }
+}
+
+#define PS_PVT_Q 8 // queries per CTA
+#define PS_PVT_D 8 // output dims per warp tile
+__global__ void __launch_bounds__(256, 2) ps_k_attn_pv_tile(float *__restrict__ out, const float *__restrict__ vct, const float *__restrict__ p,
+                                                            int hs, int n_heads, int n_kv_heads, int64_t n_kv, int64_t n_ctx, int bs) {
+    // probabilities, position-major: s_p4[j] = queries 0..3 at position j, s_p4[n_kv + j] = queries 4..7, so a lane
+    // fetches its eight probabilities of a chunk with two conflict-free 16-byte loads off one address register
+    extern __shared__ __align__(16) float4 s_p4[];
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int i0 = blockIdx.x * PS_PVT_Q, h = blockIdx.y, g = h / (n_heads / n_kv_heads);
+    const int nq = min(PS_PVT_Q, bs - i0);
+    const int nkv = (int)n_kv;
+    {
+        const float *pr = p + ((int64_t)h * bs + i0) * n_kv;
+        for (int j = tid; j < nkv; j += 256) {
+            float e[PS_PVT_Q];
+#pragma unroll
+            for (int qi = 0; qi < PS_PVT_Q; qi++) e[qi] = (qi < nq) ? pr[(int64_t)qi * n_kv + j] : 0.f;
+            s_p4[j] = make_float4(e[0], e[1], e[2], e[3]);
+            s_p4[nkv + j] = make_float4(e[4], e[5], e[6], e[7]);
+        }
+    }
+    __syncthreads();
+    const int nc = nkv >> 5; // full 32-position chunks; the rest are the leftovers of ggml_vec_dot_f32
+    const int np = nc << 5, ntail = nkv - np;
+    for (int d0 = warp * PS_PVT_D; d0 < hs; d0 += 8 * PS_PVT_D) { // hs is a multiple of PS_PVT_D (launch condition)
+        const float *vp[PS_PVT_D]; // one running pointer per V^T row: the loads below only add immediates
+#pragma unroll
+        for (int di = 0; di < PS_PVT_D; di++) vp[di] = vct + ((int64_t)g * hs + d0 + di) * n_ctx + lane;
+        const float4 *sp = s_p4 + lane;
+        float acc[PS_PVT_D * PS_PVT_Q]; // [di][qi]
+#pragma unroll
+        for (int k = 0; k < PS_PVT_D * PS_PVT_Q; k++) acc[k] = 0.f;
+        float v[3][PS_PVT_D]; // ring of V^T chunks, two in flight ahead of the FMAs
+#pragma unroll
+        for (int k = 0; k < 2; k++)
+            if (k < nc) {
+#pragma unroll
+                for (int di = 0; di < PS_PVT_D; di++) v[k][di] = vp[di][32 * k];
+            }
+        for (int c0 = 0; c0 < nc; c0 += 3) {
+#pragma unroll
+            for (int k = 0; k < 3; k++) {
+                const int c = c0 + k;
+                if (c < nc) {
+                    if (c + 2 < nc) {
+#pragma unroll
+                        for (int di = 0; di < PS_PVT_D; di++) v[(k + 2) % 3][di] = vp[di][32 * (k + 2)];
+                    }
+                    const float4 lo = sp[32 * k], hi = sp[nkv + 32 * k];
+                    const float pp[PS_PVT_Q] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
+#pragma unroll
+                    for (int di = 0; di < PS_PVT_D; di++)
+#pragma unroll
+                        for (int qi = 0; qi < PS_PVT_Q; qi++) acc[di * PS_PVT_Q + qi] = __fmaf_rn(v[k][di], pp[qi], acc[di * PS_PVT_Q + qi]);
+                }
+            }
+#pragma unroll
+            for (int di = 0; di < PS_PVT_D; di++) vp[di] += 96;
+            sp += 96;
+        }
+        // GGML_F32x8_REDUCE as a reduce-scatter: 64 sums -> 2 per lane.  Flat index = qi + 8 * di; the stages peel index
+        // bits 5, 4, 3 (lane bits 4, 3, 2), then bit 2 (lane bit 0, stage xor 1) and bit 1 (lane bit 1, stage xor 2).
+        ps_rs_stage<64>(acc, lane & 16, 16);
+        float a32[32];
+#pragma unroll
+        for (int k = 0; k < 32; k++) a32[k] = acc[k];
+        ps_rs_stage<32>(a32, lane & 8, 8);
+        float a16[16];
+#pragma unroll
+        for (int k = 0; k < 16; k++) a16[k] = a32[k];
+        ps_rs_stage<16>(a16, lane & 4, 4);
+        float a8[8];
+#pragma unroll
+        for (int k = 0; k < 8; k++) a8[k] = a16[k];
+        ps_rs_stage<8>(a8, lane & 1, 1);
+        float a4[4];
+#pragma unroll
+        for (int k = 0; k < 4; k++) a4[k] = a8[k];
+        ps_rs_stage<4>(a4, lane & 2, 2);
+        const int di = lane >> 2, qb = 4 * (lane & 1) + (lane & 2);
+        const float *vrow = vct + ((int64_t)g * hs + d0 + di) * n_ctx;
+        const float *sf = reinterpret_cast<const float *>(s_p4);
+#pragma unroll
+        for (int e = 0; e < 2; e++) {
+            const int qi = qb + e;
+            const float *pq = sf + (size_t)(qi >> 2) * nkv * 4 + (qi & 3);
+            float sum = a4[e];
+            for (int t = np; t < nkv; t++) sum = __fadd_rn(sum, __fmul_rn(vrow[t], pq[4 * t])); // leftovers: mul, then add, in order
+            if (qi < nq) out[((int64_t)(i0 + qi) * n_heads + h) * hs + d0 + di] = sum;
+        }
+    }
+}
+
 // GGMLBackend::silu_hadamard (src/backend/ggml/ggml.cpp:115-129)
 __global__ void ps_k_silu_hadamard(float *__restrict__ dst, const float *__restrict__ g, const float *__restrict__ u, int64_t n) {
     for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < n; t += (int64_t)gridDim.x * blockDim.x)
