@@ -596,8 +596,11 @@ template <int R2> int launch_attn(ps_cuda_ctx *ctx, int L, int r2 = R2, const fl
             return 0;
         }
     }
-    if ((rc = launch_k(ctx, ps_k_attn1<R2>, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], q_rot,
-                       (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx), r2))) return rc;
+    {
+        auto *k1 = (hs == 128) ? ps_k_attn1<R2, 4> : (hs == 64) ? ps_k_attn1<R2, 2> : ps_k_attn1<R2, 8>;
+        if ((rc = launch_k(ctx, k1, dim3((unsigned)(ctx->n_sm * (R2 <= 4 ? 4 : 2))), dim3(128), 0, ctx->kq, (const float *)ctx->kc[L], q_rot,
+                           (const int32_t *)ctx->pos_dev, hs, nkv, d.n_ctx, kq_scale, tl_slot(ctx), r2))) return rc;
+    }
     // probabilities of the group + (when they fit) the CTA's eight V^T rows, all sized for a full context
     const size_t row = (size_t)((d.n_ctx + 31) & ~31) * 4;
     const int v_smem = (R2 + 8) * row <= 200 * 1024 && d.n_ctx % 4 == 0;

@@ -237,10 +237,18 @@ template <int N> PS_D void ps_f32x8_reduce_n(float (&v)[N]) {
 //   wp[h][j] = fl(fl(dot_f32(K[j], q_h) * scale) + 0.0f)   written to `sc` ({n_ctx} per head), j < n_kv = pos + 1.
 // Persistent grid; a work item is (32-position chunk, kv head); a warp scores 8 cache rows against the R2 query heads
 // of the group, with all K loads of the item in flight before anything is consumed.
-template <int R2>
+// ST = head size / 32 when that is 1, 2 or 4 (no run-time predicates in the unrolled loops); ST = 8: any head size up
+// to 256.  The 8 x R2 dot products of a warp are reduced as ONE reduce-scatter over the 32 lanes: butterfly stage 16 / 8 /
+// 4 halves the cache rows a lane keeps, stages 1 / 2 halve the heads, and a + b == b + a makes the value a lane ends up
+// with the one the full GGML_F32x8_REDUCE butterfly would leave there - 8 R2 - 1 (+ plain stages) shuffles instead of
+// 40 R2.  Register slot (t, hh) of a lane holds cache row t ^ (lane >> 2) and head hh ^ ch (ch from lane bits 0, 1), so the
+// half a lane keeps is always "the lower slots" and no selects are needed.
+template <int R2, int ST>
 __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const float *__restrict__ kc, const float *__restrict__ q,
                                                   const int32_t *__restrict__ pos_dev, int hs, int n_kv_heads, int n_ctx, float scale, long long *tl, int r2) {
     __shared__ float s_q[R2][256];
+    constexpr int HB = (R2 == 1) ? 0 : (R2 == 2) ? 1 : (R2 == 4) ? 2 : 3;
+    static_assert(R2 == 1 || R2 == 2 || R2 == 4 || R2 == 8, "R2 is a power of two");
     ps_tl_min(tl, 0);
     // Everything this kernel reads except the query vector and cache row `pos` is older than the kernel before the
     // previous one (pos_dev: the last kernel of the previous step; cache rows < pos: earlier steps / the prefill), and a
@@ -249,19 +257,21 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
     const int pos = pos_dev[0];
     const int64_t n_kv = (int64_t)pos + 1;
     const int n_items = (int)((n_kv + 31) / 32) * n_kv_heads;
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, steps = hs / 32;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, steps = (ST == 8) ? hs / 32 : ST;
     const int kvd = hs * n_kv_heads;
+    const int ct = lane >> 2;
+    const int ch = (HB >= 1 ? (lane & 1) << (HB - 1) : 0) | (HB >= 2 ? ((lane >> 1) & 1) << (HB - 2) : 0);
     bool waited = false;
     for (int item = blockIdx.x; item < n_items; item += gridDim.x) {
         const int chunk = item / n_kv_heads, g = item % n_kv_heads;
         const int64_t j0 = (int64_t)chunk * 32 + warp * 8;
-        float kv[8][8];
+        float kv[8][ST];
 #pragma unroll
         for (int t = 0; t < 8; t++)
 #pragma unroll
-            for (int s = 0; s < 8; s++) {
+            for (int s = 0; s < ST; s++) {
                 kv[t][s] = 0.f;
-                if (s < steps && j0 + t < pos) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
+                if (s < steps && j0 + (t ^ ct) < pos) kv[t][s] = kc[(j0 + (t ^ ct)) * (int64_t)kvd + g * hs + 32 * s + lane];
             }
         if (!waited) {
             ps_grid_dep_wait();
@@ -273,35 +283,48 @@ __global__ void __launch_bounds__(128) ps_k_attn1(float *__restrict__ sc, const 
 #pragma unroll
             for (int t = 0; t < 8; t++)
 #pragma unroll
-                for (int s = 0; s < 8; s++)
-                    if (s < steps && j0 + t == pos) kv[t][s] = kc[(j0 + t) * (int64_t)kvd + g * hs + 32 * s + lane];
+                for (int s = 0; s < ST; s++)
+                    if (s < steps && j0 + (t ^ ct) == pos) kv[t][s] = kc[(j0 + (t ^ ct)) * (int64_t)kvd + g * hs + 32 * s + lane];
         }
         __syncthreads(); // the previous item's queries are no longer needed
         for (int idx = tid; idx < R2 * hs; idx += 128) s_q[idx / hs][idx % hs] = (idx < r2 * hs) ? q[(int64_t)g * r2 * hs + idx] : 0.f; // r2 <= R2 query heads per kv head
         __syncthreads();
-        float qv[R2][8];
+        float sum[8][R2];
 #pragma unroll
-        for (int hh = 0; hh < R2; hh++)
+        for (int hh = 0; hh < R2; hh++) {
+            float qv[ST];
 #pragma unroll
-            for (int s = 0; s < 8; s++) qv[hh][s] = (s < steps) ? s_q[hh][32 * s + lane] : 0.f;
+            for (int s = 0; s < ST; s++) qv[s] = (s < steps) ? s_q[hh ^ ch][32 * s + lane] : 0.f;
 #pragma unroll
-        for (int t = 0; t < 8; t++) {
-            float sum[R2];
+            for (int t = 0; t < 8; t++) {
+                sum[t][hh] = 0.f;
 #pragma unroll
-            for (int hh = 0; hh < R2; hh++) {
-                sum[hh] = 0.f;
-#pragma unroll
-                for (int s = 0; s < 8; s++)
-                    if (s < steps) sum[hh] = __fmaf_rn(kv[t][s], qv[hh][s], sum[hh]); // ggml_vec_dot_f32 lane chain (ggml.c:2092-2131)
+                for (int s = 0; s < ST; s++)
+                    if (s < steps) sum[t][hh] = __fmaf_rn(kv[t][s], qv[s], sum[t][hh]); // ggml_vec_dot_f32 lane chain (ggml.c:2092-2131)
             }
-            ps_f32x8_reduce_n<R2>(sum);
-            if (lane < r2 && j0 + t < n_kv) {
-                float v = sum[0];
+        }
 #pragma unroll
-                for (int hh = 1; hh < R2; hh++)
-                    if (lane == hh) v = sum[hh];
-                sc[(int64_t)(g * r2 + lane) * n_ctx + j0 + t] = __fadd_rn(__fmul_rn(v, scale), 0.0f);
-            }
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+            for (int hh = 0; hh < R2; hh++) sum[t][hh] = __fadd_rn(sum[t][hh], __shfl_xor_sync(PS_FULL, sum[t + 4][hh], 16));
+#pragma unroll
+        for (int t = 0; t < 2; t++)
+#pragma unroll
+            for (int hh = 0; hh < R2; hh++) sum[t][hh] = __fadd_rn(sum[t][hh], __shfl_xor_sync(PS_FULL, sum[t + 2][hh], 8));
+#pragma unroll
+        for (int hh = 0; hh < R2; hh++) sum[0][hh] = __fadd_rn(sum[0][hh], __shfl_xor_sync(PS_FULL, sum[1][hh], 4));
+        constexpr int N4 = (HB >= 1) ? R2 / 2 : 1; // values a lane keeps after stage xor 1
+#pragma unroll
+        for (int hh = 0; hh < N4; hh++) sum[0][hh] = __fadd_rn(sum[0][hh], __shfl_xor_sync(PS_FULL, sum[0][HB >= 1 ? hh + N4 : hh], 1));
+        constexpr int N5 = (HB >= 2) ? R2 / 4 : 1; // ... and after stage xor 2
+#pragma unroll
+        for (int hh = 0; hh < N5; hh++) sum[0][hh] = __fadd_rn(sum[0][hh], __shfl_xor_sync(PS_FULL, sum[0][HB >= 2 ? hh + N5 : hh], 2));
+        // slot hh < N5 now holds cache row j0 + ct, head hh ^ ch; lanes that differ only in unused code bits hold copies
+        const bool owner = (HB >= 2) || (HB == 1 ? (lane & 2) == 0 : (lane & 3) == 0);
+#pragma unroll
+        for (int hh = 0; hh < N5; hh++) {
+            const int head = hh ^ ch;
+            if (owner && head < r2 && j0 + ct < n_kv) sc[(int64_t)(g * r2 + head) * n_ctx + j0 + ct] = __fadd_rn(__fmul_rn(sum[0][hh], scale), 0.0f);
         }
     }
     if (!waited) { // no item for this CTA: it still takes part in the dependency chain
