@@ -64,3 +64,27 @@ def test_kv_rollback_and_batch_equivalence():
     c = cm.forward([int(prompt[24])])[0]
     L.assert_bit_equal(a, c, "rollback")
     cm.close()
+
+
+@pytest.mark.parametrize("preset", ["tiny-llama", "tiny-llama-hs128", "tiny-qwen2-r7", "tiny-q8-r3"])
+@pytest.mark.parametrize("n_prompt,batch", [(76, 37), (100, 17), (131, 64)])
+def test_tiled_batch_attention_ragged_shapes(preset, n_prompt, batch):
+    """The register-tiled scores / P.V kernels (reduce-scatter reductions, permuted cache rows, 8 x 8 accumulator tiles)
+    on shapes that hit every edge: query blocks that are not full (batch % 8), cache lengths with leftovers (n_kv % 32),
+    fewer than 32 cached positions, head sizes 64 / 128, 3 / 4 / 7 query heads per kv head.  Bit-equal to the oracle and
+    to the round-1 kernels (option attn_tile = 0)."""
+    d = M.model_dir(preset)
+    shape = synth.PRESETS[preset]
+    prompt = synth.random_prompt(shape.vocab_size, n_prompt, seed=11 + n_prompt)
+    om = M.OracleModel(d)
+    ids_o, lg_o = om.generate(prompt, 4, batch_size=batch)
+    om.close()
+    cm = capi.CudaModel(d, max_batch=128)
+    ids_c, lg_c = cm.generate(prompt, 4, batch_size=batch)
+    L.assert_bit_equal(lg_c, lg_o, f"{preset} logits, tiled attention")
+    assert ids_c == ids_o
+    cm.reset()
+    cm.be.set_option("attn_tile", 0)
+    ids_b, lg_b = cm.generate(prompt, 4, batch_size=batch)
+    L.assert_bit_equal(lg_b, lg_c, f"{preset} logits, round-1 batch attention kernels")
+    cm.close()
