@@ -123,7 +123,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1, opt_attn_tile = 1;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1, opt_attn_tile = 1, opt_tc_min = 8;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -1873,7 +1873,7 @@ static int forward_ops(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0, int tree
     const bool tree = tree_base >= 0;
     const int64_t n_kv = sess ? (int64_t)sess->n_kv_max : tree ? (int64_t)tree_base + bs : (int64_t)pos0 + bs; // pos.back() + 1 (session batch: the longest row)
     const float kq_scale = 1.0f / sqrtf((float)hs);
-    const bool tc = ctx->tc_ok && ctx->opt_tc && ctx->opt_fused && bs >= 16; // tensor-core GEMM on the fp16-expanded operands
+    const bool tc = ctx->tc_ok && ctx->opt_tc && ctx->opt_fused && bs >= ctx->opt_tc_min; // tensor-core GEMM on the fp16-expanded operands
     const bool rw = ctx->fused_ok && ctx->opt_fused && (bs > 1 || tree); // octet-interleaved copies exist: multi-column row-walker
     int rc;
     ps_k_get_embedding<<<(unsigned)bs, 256, 0, ctx->stream>>>(ctx->x, ctx->w_embd, ctx->t_embd, dim, ctx->tokens_dev);
@@ -2027,7 +2027,7 @@ static int forward_ops_tp(ps_cuda_ctx *ctx, int bs, int lm_head, int pos0) {
     const int tp = ctx->tp, rank = ctx->rank;
     const int64_t n_kv = (int64_t)pos0 + bs;
     const float kq_scale = 1.0f / sqrtf((float)hs);
-    const bool tc = ctx->tc_ok && ctx->opt_tc && bs >= 16;
+    const bool tc = ctx->tc_ok && ctx->opt_tc && bs >= ctx->opt_tc_min;
     int rc;
     if (!ctx->nccl_comm) return fail(ctx, PS_CUDA_ERR_INVALID, "tensor-parallel batch forward needs ps_cuda_tp_init");
     if (!ctx->tp_tmp) {
@@ -2639,6 +2639,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
     else if (!strcmp(name, "mv_kpar")) ctx->opt_mv_kpar = value;         // 1 (default): 32-block mat-vec launches with one octet per CTA and long rows share the row's blocks among the CTA's warps
     else if (!strcmp(name, "rwm_tile")) ctx->opt_rwm_tile = value;       // 1 (default): the multi-column row-walker shrinks its row tile so that narrow batches use every SM; 0: 16-octet tiles
+    else if (!strcmp(name, "tc_min")) ctx->opt_tc_min = std::max(2, value); // narrowest batch that takes the tcgen05 GEMM (narrower ones: multi-column row-walker)
     else if (!strcmp(name, "attn_tile")) ctx->opt_attn_tile = value; // register-tiled scores / P.V kernels for batches (0: the round-1 kernels, for A/B)
     else if (!strcmp(name, "pv_batch_min")) ctx->opt_pv_batch_min = value; // batches at least this wide use the query-blocked P.V kernel (prefill), narrower ones the per-(head, dim) warp kernel
     else if (!strcmp(name, "rw_unroll2")) ctx->opt_unroll2 = value; // tuning: two blocks per loop trip in the mat-vec launches with <= 8 octets per CTA

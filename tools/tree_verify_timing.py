@@ -17,6 +17,9 @@ desc = capi.desc_from_model_json(synth.model_json(shape), max_batch=128, n_ctx=4
 m = capi.CudaModel(desc=desc, tensors=tmap)
 m.prefill(synth.random_prompt(shape.vocab_size, ctx_len + 1), 128)
 base = m.position
+import os
+if os.environ.get("PS_TC_MIN"):
+    m.be.set_option("tc_min", int(os.environ["PS_TC_MIN"]))
 for bs in ([int(a) for a in sys.argv[4:]] or [1, 4, 8, 12, 16]):
     best = 1e9
     for _ in range(3):
