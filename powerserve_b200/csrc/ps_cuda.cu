@@ -123,7 +123,7 @@ struct ps_cuda_ctx {
     float *h_logits = nullptr;                                          // pinned staging for logits
     size_t h_logits_cap = 0;
     // options / counters
-    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 17, opt_mv_kpar = 1, opt_attn_tile = 1, opt_tc_min = 8;
+    int opt_graph = 1, opt_fused = 1, opt_pdl = 1, opt_ktime = 0, opt_tc = 1, opt_kb = 0, opt_cta_trace = 1, opt_attn_fused = 0, opt_unroll2 = 1, opt_ksplit = 0, opt_defer = 0, opt_rwm_tile = 1, opt_pv_batch_min = 3, opt_mv_kpar = 1, opt_attn_tile = 1, opt_tc_min = 6, opt_scores_batch_min = 2;
     bool tc_ok = false;        // tensor-core prefill operands are resident
     uint8_t *tc_b = nullptr;   // B operand blocks of the current activation batch
     size_t tc_b_bytes = 0;
@@ -1833,7 +1833,7 @@ struct SessRun { int n_kv_max; };
 // by default), else the round-1 kernels; narrow batches use the per-position / per-(head, dim) warp kernels.  nh / nkv
 // are the heads THIS rank owns.  The caller checks the launch (PS_LAUNCH_CK) after launch_batch_scores.
 static void launch_batch_scores(ps_cuda_ctx *ctx, int L, int nh, int nkv, int hs, int64_t n_kv, int bs) {
-    if (bs >= 8) {
+    if (bs >= ctx->opt_scores_batch_min) {
         const int r2 = nh / nkv;
         const int qb = std::max(1, std::min(bs, 8192 / (r2 * hs)));
         const dim3 grid((unsigned)((n_kv + 31) / 32), (unsigned)nkv, (unsigned)((bs + qb - 1) / qb));
@@ -1856,10 +1856,13 @@ static int launch_batch_pv(ps_cuda_ctx *ctx, int L, int nh, int nkv, int hs, int
             PS_CK(cudaFuncSetAttribute(ps_k_attn_pv_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
             pv_attr[ctx->device] = true;
         }
-        const dim3 grid((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh);
+        dim3 grid((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh);
+        const dim3 grid1 = grid;
+        if (ctx->opt_attn_tile && hs % PS_PVT_D == 0)
+            while ((int)(grid.x * grid.y * grid.z) * 2 <= ctx->n_sm * 2 && (int)grid.z * 2 * 8 * PS_PVT_D <= hs) grid.z *= 2; // narrow batch: split the dim groups over more CTAs
         static_assert(PS_PV_QB == PS_PVT_Q, "both P.V kernels block the queries by 8");
         if (ctx->opt_attn_tile && hs % PS_PVT_D == 0) ps_k_attn_pv_tile<<<grid, 256, (size_t)PS_PVT_Q * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
-        else ps_k_attn_pv_batch<<<grid, 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
+        else ps_k_attn_pv_batch<<<grid1, 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
     } else {
         ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
     }
@@ -2639,6 +2642,7 @@ int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value) {
     else if (!strcmp(name, "rw_defer")) ctx->opt_defer = value;     // bit k: launch kind k (1 Wdown, 2 gate|up, 3 q|k|v, 4 Wo, 5 lm_head) requests its weight stream after its activation vector
     else if (!strcmp(name, "mv_kpar")) ctx->opt_mv_kpar = value;         // 1 (default): 32-block mat-vec launches with one octet per CTA and long rows share the row's blocks among the CTA's warps
     else if (!strcmp(name, "rwm_tile")) ctx->opt_rwm_tile = value;       // 1 (default): the multi-column row-walker shrinks its row tile so that narrow batches use every SM; 0: 16-octet tiles
+    else if (!strcmp(name, "scores_batch_min")) ctx->opt_scores_batch_min = std::max(1, value); // batches at least this wide use the query-blocked scores kernel
     else if (!strcmp(name, "tc_min")) ctx->opt_tc_min = std::max(2, value); // narrowest batch that takes the tcgen05 GEMM (narrower ones: multi-column row-walker)
     else if (!strcmp(name, "attn_tile")) ctx->opt_attn_tile = value; // register-tiled scores / P.V kernels for batches (0: the round-1 kernels, for A/B)
     else if (!strcmp(name, "pv_batch_min")) ctx->opt_pv_batch_min = value; // batches at least this wide use the query-blocked P.V kernel (prefill), narrower ones the per-(head, dim) warp kernel

@@ -961,7 +961,8 @@ __global__ void __launch_bounds__(256, 2) ps_k_attn_pv_tile(float *__restrict__ 
     __syncthreads();
     const int nc = nkv >> 5; // full 32-position chunks; the rest are the leftovers of ggml_vec_dot_f32
     const int np = nc << 5, ntail = nkv - np;
-    for (int d0 = warp * PS_PVT_D; d0 < hs; d0 += 8 * PS_PVT_D) { // hs is a multiple of PS_PVT_D (launch condition)
+    // hs is a multiple of PS_PVT_D (launch condition); gridDim.z CTAs share the dim groups of a (query block, head) when the batch is narrow
+    for (int d0 = ((int)blockIdx.z * 8 + warp) * PS_PVT_D; d0 < hs; d0 += (int)gridDim.z * 8 * PS_PVT_D) {
         const float *vp[PS_PVT_D]; // one running pointer per V^T row: the loads below only add immediates
 #pragma unroll
         for (int di = 0; di < PS_PVT_D; di++) vp[di] = vct + ((int64_t)g * hs + d0 + di) * n_ctx + lane;

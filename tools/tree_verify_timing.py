@@ -18,8 +18,8 @@ m = capi.CudaModel(desc=desc, tensors=tmap)
 m.prefill(synth.random_prompt(shape.vocab_size, ctx_len + 1), 128)
 base = m.position
 import os
-if os.environ.get("PS_TC_MIN"):
-    m.be.set_option("tc_min", int(os.environ["PS_TC_MIN"]))
+for kv in filter(None, os.environ.get("PS_OPTS", "").split(",")):  # e.g. PS_OPTS=tc_min=16,pv_batch_min=2
+    m.be.set_option(kv.split("=")[0], int(kv.split("=")[1]))
 for bs in ([int(a) for a in sys.argv[4:]] or [1, 4, 8, 12, 16]):
     best = 1e9
     for _ in range(3):
