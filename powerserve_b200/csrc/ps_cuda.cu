@@ -1858,10 +1858,11 @@ static int launch_batch_pv(ps_cuda_ctx *ctx, int L, int nh, int nkv, int hs, int
         }
         dim3 grid((unsigned)((bs + PS_PV_QB - 1) / PS_PV_QB), (unsigned)nh);
         const dim3 grid1 = grid;
-        if (ctx->opt_attn_tile && hs % PS_PVT_D == 0)
+        const bool tile = ctx->opt_attn_tile && hs % PS_PVT_D == 0 && PS_PVT_RING + (size_t)PS_PVT_Q * n_kv * 4 <= 200 * 1024;
+        if (tile)
             while ((int)(grid.x * grid.y * grid.z) * 2 <= ctx->n_sm * 2 && (int)grid.z * 2 * 8 * PS_PVT_D <= hs) grid.z *= 2; // narrow batch: split the dim groups over more CTAs
         static_assert(PS_PV_QB == PS_PVT_Q, "both P.V kernels block the queries by 8");
-        if (ctx->opt_attn_tile && hs % PS_PVT_D == 0) ps_k_attn_pv_tile<<<grid, 256, (size_t)PS_PVT_Q * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
+        if (tile) ps_k_attn_pv_tile<<<grid, 256, PS_PVT_RING + (size_t)PS_PVT_Q * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
         else ps_k_attn_pv_batch<<<grid1, 256, (size_t)PS_PV_QB * n_kv * 4, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);
     } else {
         ps_k_attn_pv<<<dim3((unsigned)((hs + 3) / 4), (unsigned)nkv), 128, 0, ctx->stream>>>(ctx->att, ctx->vct[L], ctx->kq, hs, nh, nkv, n_kv, n_ctx, bs);

@@ -939,15 +939,44 @@ PS_D void ps_rs_stage(float (&a)[N], bool up, int mask) {
 
 #define PS_PVT_Q 8 // queries per CTA
 #define PS_PVT_D 8 // output dims per warp tile
+#define PS_PVT_DEPTH 4 // V^T chunks in flight per warp (cp.async ring in shared memory: no registers held by loads in flight)
+#define PS_PVT_RING (8 * PS_PVT_DEPTH * PS_PVT_D * 32 * 4) // bytes: 8 warps x depth x 8 rows x 32 positions
+PS_D void ps_cp_async4(float *dst_smem, const float *src) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src) : "memory");
+}
+PS_D void ps_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> PS_D void ps_cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
 __global__ void __launch_bounds__(256, 2) ps_k_attn_pv_tile(float *__restrict__ out, const float *__restrict__ vct, const float *__restrict__ p,
                                                             int hs, int n_heads, int n_kv_heads, int64_t n_kv, int64_t n_ctx, int bs) {
-    // probabilities, position-major: s_p4[j] = queries 0..3 at position j, s_p4[n_kv + j] = queries 4..7, so a lane
-    // fetches its eight probabilities of a chunk with two conflict-free 16-byte loads off one address register
-    extern __shared__ __align__(16) float4 s_p4[];
+    // [ring: 8 warps][PS_PVT_DEPTH][PS_PVT_D][32] V^T chunks, then the probabilities, position-major: s_p4[j] = queries 0..3
+    // at position j, s_p4[n_kv + j] = queries 4..7, so a lane fetches its eight probabilities of a chunk with two
+    // conflict-free 16-byte loads off one address register
+    extern __shared__ __align__(16) float4 s_pvt[];
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    float *ring = reinterpret_cast<float *>(s_pvt) + warp * (PS_PVT_DEPTH * PS_PVT_D * 32) + lane; // every lane reads back only what it copied itself
+    float4 *s_p4 = s_pvt + PS_PVT_RING / 16;
     const int i0 = blockIdx.x * PS_PVT_Q, h = blockIdx.y, g = h / (n_heads / n_kv_heads);
     const int nq = min(PS_PVT_Q, bs - i0);
     const int nkv = (int)n_kv;
+    const int nc = nkv >> 5; // full 32-position chunks; the rest are the leftovers of ggml_vec_dot_f32
+    const int np = nc << 5;
+    // hs is a multiple of PS_PVT_D (launch condition); gridDim.z CTAs share the dim groups of a (query block, head) when the batch is narrow
+    const int d_first = ((int)blockIdx.z * 8 + warp) * PS_PVT_D, d_step = (int)gridDim.z * 8 * PS_PVT_D;
+    const float *vp[PS_PVT_D]; // one running pointer per V^T row: the copies below only add immediates
+    auto issue = [&](bool in, int slot, int off) { // a chunk of the current dim group -> ring slot (always one group per call, possibly empty)
+        if (in) {
+#pragma unroll
+            for (int di = 0; di < PS_PVT_D; di++) ps_cp_async4(ring + (slot * PS_PVT_D + di) * 32, vp[di] + off);
+        }
+        ps_cp_async_commit();
+    };
+    if (d_first < hs) { // the first dim group's V^T chunks are on their way while the probabilities are staged
+#pragma unroll
+        for (int di = 0; di < PS_PVT_D; di++) vp[di] = vct + ((int64_t)g * hs + d_first + di) * n_ctx + lane;
+#pragma unroll
+        for (int k = 0; k < PS_PVT_DEPTH - 1; k++) issue(k < nc, k, 32 * k);
+    }
     {
         const float *pr = p + ((int64_t)h * bs + i0) * n_kv;
         for (int j = tid; j < nkv; j += 256) {
@@ -959,44 +988,40 @@ __global__ void __launch_bounds__(256, 2) ps_k_attn_pv_tile(float *__restrict__ 
         }
     }
     __syncthreads();
-    const int nc = nkv >> 5; // full 32-position chunks; the rest are the leftovers of ggml_vec_dot_f32
-    const int np = nc << 5, ntail = nkv - np;
-    // hs is a multiple of PS_PVT_D (launch condition); gridDim.z CTAs share the dim groups of a (query block, head) when the batch is narrow
-    for (int d0 = ((int)blockIdx.z * 8 + warp) * PS_PVT_D; d0 < hs; d0 += (int)gridDim.z * 8 * PS_PVT_D) {
-        const float *vp[PS_PVT_D]; // one running pointer per V^T row: the loads below only add immediates
-#pragma unroll
-        for (int di = 0; di < PS_PVT_D; di++) vp[di] = vct + ((int64_t)g * hs + d0 + di) * n_ctx + lane;
+    for (int d0 = d_first; d0 < hs; d0 += d_step) {
         const float4 *sp = s_p4 + lane;
         float acc[PS_PVT_D * PS_PVT_Q]; // [di][qi]
 #pragma unroll
         for (int k = 0; k < PS_PVT_D * PS_PVT_Q; k++) acc[k] = 0.f;
-        float v[3][PS_PVT_D]; // ring of V^T chunks, two in flight ahead of the FMAs
+        for (int c0 = 0; c0 < nc; c0 += PS_PVT_DEPTH) {
 #pragma unroll
-        for (int k = 0; k < 2; k++)
-            if (k < nc) {
-#pragma unroll
-                for (int di = 0; di < PS_PVT_D; di++) v[k][di] = vp[di][32 * k];
-            }
-        for (int c0 = 0; c0 < nc; c0 += 3) {
-#pragma unroll
-            for (int k = 0; k < 3; k++) {
+            for (int k = 0; k < PS_PVT_DEPTH; k++) {
                 const int c = c0 + k;
-                if (c < nc) {
-                    if (c + 2 < nc) {
+                if (c < nc) { // warp-uniform
+                    issue(c + PS_PVT_DEPTH - 1 < nc, (k + PS_PVT_DEPTH - 1) % PS_PVT_DEPTH, 32 * (k + PS_PVT_DEPTH - 1)); // refills the slot consumed one chunk ago
+                    ps_cp_async_wait<PS_PVT_DEPTH - 1>();                                // chunk c has landed
+                    float v[PS_PVT_D];
 #pragma unroll
-                        for (int di = 0; di < PS_PVT_D; di++) v[(k + 2) % 3][di] = vp[di][32 * (k + 2)];
-                    }
+                    for (int di = 0; di < PS_PVT_D; di++) v[di] = ring[(k * PS_PVT_D + di) * 32];
                     const float4 lo = sp[32 * k], hi = sp[nkv + 32 * k];
                     const float pp[PS_PVT_Q] = {lo.x, lo.y, lo.z, lo.w, hi.x, hi.y, hi.z, hi.w};
 #pragma unroll
                     for (int di = 0; di < PS_PVT_D; di++)
 #pragma unroll
-                        for (int qi = 0; qi < PS_PVT_Q; qi++) acc[di * PS_PVT_Q + qi] = __fmaf_rn(v[k][di], pp[qi], acc[di * PS_PVT_Q + qi]);
+                        for (int qi = 0; qi < PS_PVT_Q; qi++) acc[di * PS_PVT_Q + qi] = __fmaf_rn(v[di], pp[qi], acc[di * PS_PVT_Q + qi]);
                 }
             }
 #pragma unroll
-            for (int di = 0; di < PS_PVT_D; di++) vp[di] += 96;
-            sp += 96;
+            for (int di = 0; di < PS_PVT_D; di++) vp[di] += 32 * PS_PVT_DEPTH;
+            sp += 32 * PS_PVT_DEPTH;
+        }
+        ps_cp_async_wait<0>();
+        if (d0 + d_step < hs) { // next dim group of this warp: its first chunks fly during the reduction below
+            const int64_t adv = (int64_t)d_step * n_ctx - (int64_t)((nc + PS_PVT_DEPTH - 1) / PS_PVT_DEPTH) * (32 * PS_PVT_DEPTH);
+#pragma unroll
+            for (int di = 0; di < PS_PVT_D; di++) vp[di] += adv;
+#pragma unroll
+            for (int k = 0; k < PS_PVT_DEPTH - 1; k++) issue(k < nc, k, 32 * k);
         }
         // GGML_F32x8_REDUCE as a reduce-scatter: 64 sums -> 2 per lane.  Flat index = qi + 8 * di; the stages peel index
         // bits 5, 4, 3 (lane bits 4, 3, 2), then bit 2 (lane bit 0, stage xor 1) and bit 1 (lane bit 1, stage xor 2).
