@@ -58,6 +58,10 @@ PRESETS: Dict[str, ModelShape] = {
     # small shapes for parity tests (same structure, seconds on the CPU oracle)
     "tiny-llama": ModelShape("tiny-llama", "llama", 512, 1536, 2, 8, 2, 64, 1024, False, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=512),
     "tiny-llama-hs128": ModelShape("tiny-llama-hs128", "llama", 512, 1024, 2, 4, 2, 128, 768, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=384),
+    # head sizes off the templated fast paths of the attention kernels (32 / 96 / 256: generic step loops, round-1 batch kernels)
+    "tiny-hs32": ModelShape("tiny-hs32", "llama", 512, 1024, 2, 16, 4, 32, 512, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256),
+    "tiny-hs96": ModelShape("tiny-hs96", "llama", 512, 1024, 2, 8, 2, 96, 512, True, 2, 5e5, 1e-5, GGML_Q4_K, n_ctx=256),
+    "tiny-hs256": ModelShape("tiny-hs256", "llama", 512, 1024, 2, 2, 1, 256, 512, True, 0, 5e5, 1e-5, GGML_Q4_K, n_ctx=256),
     "tiny-qwen2": ModelShape("tiny-qwen2", "qwen2", 256, 608, 2, 4, 2, 64, 512, True, 2, 1e6, 1e-6, GGML_Q4_0, n_ctx=256, qkv_bias=True),
     # query heads per kv head that are not a power of two (Qwen2-0.5B has 14 / 2 = 7): the decode attention kernels run
     # with the next power-of-two template and r2 active heads

@@ -88,3 +88,24 @@ def test_tiled_batch_attention_ragged_shapes(preset, n_prompt, batch):
     ids_b, lg_b = cm.generate(prompt, 4, batch_size=batch)
     L.assert_bit_equal(lg_b, lg_c, f"{preset} logits, round-1 batch attention kernels")
     cm.close()
+
+
+@pytest.mark.parametrize("preset", ["tiny-hs32", "tiny-hs96", "tiny-hs256"])
+def test_head_sizes_off_the_templated_paths(preset):
+    """Head sizes 32 / 96 / 256: the decode scores kernel's generic step loop (ST = 8 template), the head-size-templated
+    batch scores kernel for 32 and 256, the round-1 batch kernels for 96.  Prefill in chunks, host-driven decode and the
+    device-resident greedy loop, bit-equal to the oracle."""
+    d = M.model_dir(preset)
+    shape = synth.PRESETS[preset]
+    prompt = synth.random_prompt(shape.vocab_size, 45, seed=5)
+    om = M.OracleModel(d)
+    ids_o, lg_o = om.generate(prompt, 8, batch_size=19)
+    om.close()
+    cm = capi.CudaModel(d, max_batch=32)
+    ids_c, lg_c = cm.generate(prompt, 8, batch_size=19)
+    L.assert_bit_equal(lg_c, lg_o, f"{preset} logits")
+    assert ids_c == ids_o
+    cm.reset()
+    cm.prefill(prompt, 19)
+    assert list(cm.decode_greedy(int(prompt[-1]), 8)) == ids_o
+    cm.close()
