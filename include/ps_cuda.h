@@ -212,7 +212,11 @@ int ps_cuda_tp_import(ps_cuda_ctx *ctx, const void *handles, int n);
  * produce bit-identical results; they exist so tests can prove it.  "ktime" = 1 runs the fused step un-graphed with
  * CUDA events around every mat-vec launch (bench.py's roofline leg); "trace" = 1 records a per-kernel device timeline;
  * "cta_trace" = k (with "trace") adds a per-CTA stream trace of one mat-vec launch site (1 Wdown, 2 gate|up, 3 QKV, 4 Wo,
- * 5 lm_head; trace slots 256..); "rw_kb" = n caps the blocks per TMA ring stage of the mat-vec (tuning; default 16). */
+ * 5 lm_head; trace slots 256..); "rw_kb" = n caps the blocks per TMA ring stage of the mat-vec (tuning; default 16).
+ * Kernel choice for batches (prefill chunks, verify batches; every choice computes the same bits): "attn_tile" = 0 runs
+ * the round-1 batch attention kernels instead of the register-tiled ones; "tc_min" = n is the narrowest batch that takes
+ * the tcgen05 GEMM (default 6; narrower ones walk with the multi-column row-walker); "scores_batch_min" (default 2) and
+ * "pv_batch_min" (default 3) are the narrowest batches for the query-blocked scores / P.V kernels. */
 int ps_cuda_set_option(ps_cuda_ctx *ctx, const char *name, int value);
 /* counters: "kernel_launches" (kernels enqueued since create), "graph_replays", "h2d_bytes", "d2h_bytes",
  * "last_device_ns" (CUDA-event time, on the context stream, of the last forward / decode_greedy call),

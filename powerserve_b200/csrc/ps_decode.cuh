@@ -457,6 +457,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
         float vtail;
         if (v_smem) {
             ps_mbar_wait(&bar_v, 0);
+            PS_A2_PROBE(6);
             const float *vs = s_v + warp * stride;
             vtail = (lane < ntail) ? vs[np + lane] : 0.f;
 #pragma unroll 8
@@ -479,6 +480,7 @@ __global__ void __launch_bounds__(PS_A2_THREADS) ps_k_attn2(float *__restrict__ 
                     }
             }
         }
+        PS_A2_PROBE(7);
         ps_f32x8_reduce_n<R2>(sum);
         for (int t = 0; t < ntail; t++) { // leftovers: mul, then add, in order (every lane computes the same chain)
             const float v = __shfl_sync(PS_FULL, vtail, t);
