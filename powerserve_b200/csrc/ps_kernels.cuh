@@ -705,19 +705,19 @@ __global__ void __launch_bounds__(256) ps_k_softmax_ext(float *__restrict__ dst,
 #pragma unroll
         for (int l = 0; l < 8; l++) {
             v[l] = ps_v_expf(__fadd_rn(wp[gi * 8 + l], -mx));
-            dp[gi * 8 + l] = v[l];
+            wp[gi * 8 + l] = v[l]; // the exponentials stay in shared memory: the row goes to global memory once, scaled
         }
         const float r0 = __fadd_rn(v[4], v[0]), r1 = __fadd_rn(v[5], v[1]), r2 = __fadd_rn(v[6], v[2]), r3 = __fadd_rn(v[7], v[3]);
         s += (double)__fadd_rn(__fadd_rn(r0, r2), __fadd_rn(r1, r3));
     }
     for (int64_t j = n8 + threadIdx.x; j < ne0; j += blockDim.x) { // scalar tail: libm expf
         const float v = ps_expf_glibc(__fadd_rn(wp[j], -mx));
-        dp[j] = v;
+        wp[j] = v;
         s += (double)v;
     }
     const double sum = ps_block_sum_double(s, sh);
     const float inv = (float)(1.0 / sum);
-    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) dp[j] = __fmul_rn(dp[j], inv);
+    for (int64_t j = threadIdx.x; j < ne0; j += blockDim.x) dp[j] = __fmul_rn(wp[j], inv);
 }
 
 // mat_mul(v_view, kq) + permute + cont (norm_attention.cpp:138-151): out[i][h*hs + d] = vec_dot_f32(n_kv, Vt row, P row).
