@@ -9,7 +9,7 @@
 //   * A operand (weights): per (128-row tile, super-block, lane l) a K = 32 fp16 tile of sc_j*q4, expanded ONCE at bind time
 //     into HBM in the UMMA canonical K-major layout (2 B / weight: 15 GB for Llama-3.1-8B — the 180 GB part pays for zero
 //     dequantisation work on the prefill path); the mins use one shared K = 16 tile of the m_j.
-//   * B operand (activations): per (32-column group, super-block, lane) the q8 bytes as fp16, plus half-block sums for the
+//   * B operand (activations): per (16-column group, super-block, lane) the q8 bytes as fp16, plus half-block sums for the
 //     mins, written per forward call by ps_k_tc_prep_b (same quantiser as everywhere else).
 //   * per super-block: 16 + 4 tcgen05.mma (M = 128, N = 16, K = 16) into 12 x 16 TMEM columns (double-buffered); 16
 //     epilogue warps read the exact integers back (12 tcgen05.ld in flight, one wait) and advance the FMA chains in
@@ -27,10 +27,10 @@
 #define PS_TC_THREADS ((PS_TC_EPI_WARPS + 2) * 32)
 // operand blocks in global / shared memory (bytes)
 #define PS_TC_A_TILE (PS_TC_M * 16 * 2)                    // one MMA's A operand: 128 rows x K16 fp16 = 4096
-#define PS_TC_B_TILE (PS_TC_N * 16 * 2)                    // one MMA's B operand: 32 cols x K16 fp16 = 1024
+#define PS_TC_B_TILE (PS_TC_N * 16 * 2)                    // one MMA's B operand: 16 cols x K16 fp16 = 512
 #define PS_TC_A_BLOCK (16 * PS_TC_A_TILE + PS_TC_A_TILE + PS_TC_M * 8)  // 8 lanes x 2 + mins tile + (xd, xmin) per row = 70656
-#define PS_TC_B_BLOCK (16 * PS_TC_B_TILE + 4 * PS_TC_B_TILE + PS_TC_N * 4) // 8 lanes x 2 + 4 mins tiles + yd per column = 20608
-#define PS_TC_STAGE (PS_TC_A_BLOCK + PS_TC_B_BLOCK)        // 91264
+#define PS_TC_B_BLOCK (16 * PS_TC_B_TILE + 4 * PS_TC_B_TILE + PS_TC_N * 4) // 8 lanes x 2 + 4 mins tiles + yd per column = 10304
+#define PS_TC_STAGE (PS_TC_A_BLOCK + PS_TC_B_BLOCK)        // 80960
 #define PS_TC_STAGES 2
 
 // canonical K-major, no-swizzle UMMA tile: [k-chunk (2)][8-row group][8 rows][8 fp16]  (cute: ((8,n),2):((1,SBO),LBO))
